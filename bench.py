@@ -1,0 +1,368 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the brick hot path on B200 (contract: see the build brief / DESIGN.md section 6).
+
+Workload (BASELINE.json configs[2], the configuration the metric's weak-scaling claim is quoted on):
+weak scaling, 7-point star stencil (stencils/mpi7pt.py), 512^3 FP64 cells per GPU in 8^3 bricks, periodic Cartesian
+process grid (1 / 2x1x1 / 2x2x1 / 2x2x2), ghost depth 8.  One "step" = one exchange period of the reference's time
+loop (weak/main.cu:246-287): ghost-zone exchange + ST_ITER(=8) sweeps.  GStencil/s counts interior points only
+(weak/main.cu:315-317).  The other stencils (13/25/125-point) are timed in the same run and reported under "others".
+
+  python bench.py [--gpus N --steps K --warmup W] [--stencil mpi7pt] [--size 512]       # product arm
+  python bench.py --impl reference ...                                                  # reference CPU arm
+Under torchrun (N>1) every rank drives one GPU; rank 0 prints the single JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+# bind OpenMP threads of the CPU reference leg -- only where a single process runs it
+if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+    os.environ.setdefault("OMP_PROC_BIND", "close")
+
+import numpy as np  # noqa: E402
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CART = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}  # MPI_Dims_create order (weak/args.cpp:101)
+
+
+def measured_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.thread.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus):
+    """one process per GPU under torchrun; returns (rank, world, torch.distributed or None)"""
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world == 1:
+        return 0, 1, None
+    import torch
+    import torch.distributed as dist
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, dist
+
+
+def max_over_ranks(dist, value):
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(dist):
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize()
+
+
+def wire_peers(bk, dom_obj, dist, rank, world):
+    """exchange CUDA-IPC handles of storage[0] and of the flag buffer, map every neighbour's memory"""
+    from bricklib_b200.weak import Handshake
+    import ctypes as C
+    L = bk.load()
+    if dist is None:
+        dom_obj.connect()
+        return
+    hs = Handshake(world)
+    h_store, h_flag = C.create_string_buffer(64), C.create_string_buffer(64)
+    bk._lib.check(L.bk_ipc_export(dom_obj.storage[0].dat.ptr, h_store))
+    bk._lib.check(L.bk_ipc_export(hs.buf.ptr, h_flag))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (h_store.raw, h_flag.raw))
+    ptrs = {}
+    hs.peer[rank] = hs.buf.ptr
+    for p in dom_obj.peers:
+        sp, fp = C.c_void_p(), C.c_void_p()
+        bk._lib.check(L.bk_ipc_open(gathered[p][0], C.byref(sp)))
+        bk._lib.check(L.bk_ipc_open(gathered[p][1], C.byref(fp)))
+        ptrs[p] = sp.value
+        hs.peer[p] = fp.value
+    dom_obj.connect(ptrs, hs)
+
+
+def time_periods(bk, d, steps, warmup, dist):
+    """W warm-up periods, then K timed periods between barriers; returns (seconds max over ranks, sweep seconds, launches)"""
+    L = bk.load()
+    for _ in range(warmup):
+        d.period()
+    bk.device_sync()
+    barrier(dist)
+    ev0, ev1 = bk.Event(), bk.Event()
+    launches = 0
+    ev0.record()
+    for _ in range(steps):
+        launches += d.period()
+    ev1.record()
+    ev1.sync()
+    bk.device_sync()
+    barrier(dist)
+    sec = ev0.elapsed_ms(ev1) / 1e3
+    return max_over_ranks(dist, sec), launches
+
+
+def time_sweeps(bk, d, reps):
+    """the dominant kernel alone: `reps` full-interior sweeps between two events on the launching stream"""
+    t = d.grid.dims
+    lo, hi = (1, 1, 1), tuple(x - 1 for x in t)
+    for s in range(3):
+        d._sweep(s % 2, 1 - s % 2, lo, hi, None)
+    bk.device_sync()
+    ev0, ev1 = bk.Event(), bk.Event()
+    ev0.record()
+    for s in range(reps):
+        d._sweep(s % 2, 1 - s % 2, lo, hi, None)
+    ev1.record()
+    ev1.sync()
+    return ev0.elapsed_ms(ev1) / 1e3 / reps
+
+
+def e2e_periods(bk, d, steps):
+    """same period, but the field starts and ends in (pinned) HOST memory every step: H2D of the brick storage,
+    exchange + ST_ITER sweeps, D2H of the result storage -- all inside the timed region"""
+    import ctypes as C
+    L = bk.load()
+    nbytes = d.storage[0].dat.nbytes
+    host = C.c_void_p()
+    bk._lib.check(L.bk_host_alloc(C.byref(host), nbytes))
+    bk._lib.check(L.bk_memcpy_d2h(host, d.storage[0].dat.ptr, nbytes, None))
+    bk.device_sync()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        bk._lib.check(L.bk_memcpy_h2d(d.storage[0].dat.ptr, host, nbytes, None))
+        d.period()
+        bk._lib.check(L.bk_memcpy_d2h(host, d.storage[0].dat.ptr, nbytes, None))
+        bk._lib.check(L.bk_stream_sync(None))
+    sec = time.perf_counter() - t0
+    L.bk_host_free(host)
+    return sec / steps, nbytes
+
+
+def reference_period_seconds(stencil_id, size, periods, warm=1):
+    """the reference's own CPU implementation of the path (oracle/_ref: its BrickDecomp, its exchange() over the
+    in-process MPI stand-in, its generated AVX brick code) on all host threads; else the C port.  Returns
+    (seconds per period, kind, cores, isa)."""
+    import oracle
+    from oracle import schedule as S
+    R = oracle.ref()
+    if R is not None:
+        be, kind, isa, cores = S.RefBackend(), "reference", R.isa, R.threads
+    else:
+        be, kind, isa, cores = S.PortBackend(), "port", "scalar-c", os.cpu_count()
+    dom = (size,) * 3
+    be.setup(dom, (1, 1, 1))
+    rng = np.random.default_rng(0x5EED)
+    be.store[0][0][512:] = rng.random(be.store[0][0].size - 512)
+    it = oracle.ST_ITER[stencil_id]
+
+    def period():
+        be.exchange()
+        for s in range(it):
+            be.sweep(stencil_id, s % 2, 1 - s % 2, skip=1 if s == it - 1 else 0)
+
+    for _ in range(warm):
+        period()
+    t0 = time.perf_counter()
+    for _ in range(periods):
+        period()
+    return (time.perf_counter() - t0) / periods, kind, cores, isa
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    st = oracle.STENCILS[args.stencil]
+    size = args.size
+    sec, kind, cores, isa = reference_period_seconds(st, size, args.steps, max(1, min(args.warmup, 1)))
+    it = oracle.ST_ITER[st]
+    gst = size ** 3 * it / sec / 1e9
+    line = {
+        "impl": "reference", "metric": "GStencil/s", "value": gst, "unit": "GStencil/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"weak {args.stencil} {size}^3 per rank, 8^3 bricks, 1 exchange + {it} sweeps per step",
+                   "ranks": 1, "note": "reference CPU path (OpenMP + generated %s code), single process" % isa},
+        "cpu_baseline": {"value": gst, "unit": "GStencil/s", "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} periods of {size}^3 after 1 warm-up"},
+        "e2e": {"value": gst, "unit": "GStencil/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--stencil", default="mpi7pt", choices=["mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt"])
+    ap.add_argument("--size", type=int, default=512, help="cells per axis per GPU")
+    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip other stencils / e2e / cpu baseline")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "brick", "tiled"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import bricklib_b200 as bk
+    rank, world, dist = dist_setup(args.gpus)
+    if world == 1:
+        bk._lib.check(bk.load().bk_set_device(0))
+    n = world
+    cart = CART.get(n)
+    if cart is None:
+        raise SystemExit("supported GPU counts: 1, 2, 4, 8")
+    coo = [(a, b, c) for a in range(cart[0]) for b in range(cart[1]) for c in range(cart[2])][rank]
+    kernel = {"auto": bk.KERNEL_AUTO, "brick": bk.KERNEL_BRICK, "tiled": bk.KERNEL_TILED}[args.kernel]
+    st = bk.STENCILS[args.stencil]
+    size = args.size
+    dom = (size,) * 3
+    pts = size ** 3
+
+    d = bk.WeakDomain(dom, st, cart, coo, rank, kernel)
+    wire_peers(bk, d, dist, rank, world)
+    if not args.no_overlap:
+        d.enable_overlap()
+    rng = np.random.default_rng(0x5EED + rank)
+    host = rng.random(d.decomp.nbricks * 512)
+    host[:512] = 0.0
+    d.storage[0].from_host(host)
+    del host
+
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+    sec, launches = time_periods(bk, d, args.steps, args.warmup, dist)
+    clocks = sampler.stop() if rank == 0 else None
+    it = d.st_iter
+    value = pts * it * n * args.steps / sec / 1e9
+
+    peak, peak_src = measured_peak()
+    sweep_s = time_sweeps(bk, d, 20)
+    achieved = 16.0 * pts / sweep_s / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.stencil)
+    except Exception:
+        pass
+
+    line = {
+        "metric": "GStencil/s", "value": value, "unit": "GStencil/s", "n_gpus": n, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"weak {args.stencil} {size}^3 per GPU, 8^3 bricks, 1 exchange + {it} sweeps per step",
+                   "process_grid": "x".join(map(str, cart)), "exchange_MB_per_gpu_per_step": d.view.bytes / 1e6,
+                   "overlap": not args.no_overlap, "kernel": args.kernel,
+                   "l2": f"inputs larger than L2: {2 * d.storage[0].dat.nbytes / 1e9:.2f} GB streamed per sweep"},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "stencil sweep, one launch = 512^3 interior points x 16 B",
+                     "kernel_ms": sweep_s * 1e3, "peak_source": peak_src},
+        "clocks": clocks,
+    }
+
+    if n == 1 and not args.no_extras:
+        others = {}
+        for name, sid in bk.STENCILS.items():
+            if name in ("7pt", args.stencil):
+                continue
+            d.stencil, d.st_iter = sid, bk.load().bk_stencil_st_iter(sid)
+            s2, _ = time_periods(bk, d, max(3, args.steps // 4), 3, None)
+            k2 = time_sweeps(bk, d, 10)
+            others[name] = {"GStencil/s": pts * d.st_iter * max(3, args.steps // 4) / s2 / 1e9,
+                            "sweep_ms": k2 * 1e3, "algorithmic_GB/s": 16.0 * pts / k2 / 1e9,
+                            "frac_of_hbm_peak": 16.0 * pts / k2 / 1e9 / peak,
+                            "GFLOP/s": (2 * bk.load().bk_stencil_points(sid) - 1) * pts / k2 / 1e9}
+        d.stencil, d.st_iter = st, it
+        line["others"] = others
+        e2e_s, nbytes = e2e_periods(bk, d, 5)
+        line["e2e"] = {"value": pts * it / e2e_s / 1e9, "unit": "GStencil/s", "h2d_bytes_per_step": nbytes,
+                       "d2h_bytes_per_step": nbytes,
+                       "what": "field in pinned host memory before and after every step: H2D storage, period, D2H"}
+        try:
+            cs, kind, cores, isa = reference_period_seconds(st, size, 2, 1)
+            line["cpu_baseline"] = {"value": pts * it / cs / 1e9, "unit": "GStencil/s", "cores": cores, "kind": kind,
+                                    "sample": f"2 periods (exchange + {it} sweeps) of {size}^3 after 1 warm-up, {isa}"}
+        except Exception as exc:  # the checker is optional for the product arm
+            line["cpu_baseline"] = {"value": None, "unit": "GStencil/s", "cores": 0, "kind": "port",
+                                    "sample": f"unavailable: {exc}"}
+    elif n > 1:
+        e2e_s, nbytes = e2e_periods(bk, d, 3)
+        e2e_s = max_over_ranks(dist, e2e_s)
+        line["e2e"] = {"value": pts * it * n / e2e_s / 1e9, "unit": "GStencil/s", "h2d_bytes_per_step": nbytes,
+                       "d2h_bytes_per_step": nbytes,
+                       "what": "per rank: H2D storage, period, D2H; max over ranks"}
+
+    if rank == 0:
+        print(json.dumps(line))
+    if dist is not None:
+        barrier(dist)
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,17 @@
+"""bricklib_b200 -- B200-native hot path of bricklib: FP64 brick stencils + ghost-zone exchange.
+
+The product is libbrick_b200.so (CUDA kernels for sm_100a behind the C ABI in include/bricklib_b200.h).  This package is
+the thin host-side mirror of the reference interface used by tests/, bench.py and the weak-scaling loop; the C++
+template surface lives in include/*.h and the drivers in drivers/.
+"""
+from ._lib import (BK_OK, KERNEL_AUTO, KERNEL_BRICK, KERNEL_TILED, STENCILS, BrickError, load)  # noqa: F401
+from .core import (BRICK, Brick, BrickDecomp, BrickInfo, BrickStorage, DeviceBuffer, DeviceGrid, Event,  # noqa: F401
+                   ExchangeView, compareBrick, copyFromBrick, copyToBrick, device_sync, init_grid, stencil,
+                   stencil_list)
+from .weak import WeakDomain, shell_boxes  # noqa: F401
+
+
+def have_gpu():
+    import ctypes
+    n = ctypes.c_int()
+    return load().bk_device_count(ctypes.byref(n)) == 0 and n.value > 0

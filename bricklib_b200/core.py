@@ -1,0 +1,295 @@
+"""Host-side mirror of the reference's brick interface, over the C ABI (include/bricklib_b200.h).
+
+Same names and argument meaning as the reference so the parity tests read like its drivers:
+  BrickStorage / BrickInfo / Brick      include/brick.h:53-395        (device resident here)
+  init_grid                             include/bricksetup.h:73-90
+  copyToBrick / copyFromBrick           include/bricksetup.h:172-221
+  compareBrick                          include/brickcompare.h:30-57  (explicit tolerance)
+  BrickDecomp, ExchangeView             include/brick-mpi.h:82-124, :178-513
+  brick_kernel launch -> stencil()      weak/main.cu:35-43, :277-282
+Python is plumbing for tests/bench; the C++ drivers in drivers/ use the same C ABI through include/*.h.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Field, Region, Seg, check, load
+
+BRICK = 512  # elements of an 8x8x8 brick
+
+
+def _l3(v):
+    return (C.c_long * 3)(*[int(x) for x in v])
+
+
+def _u3(v):
+    return (C.c_uint * 3)(*[int(x) for x in v])
+
+
+class DeviceBuffer:
+    """cudaMalloc'ed bytes (IPC-exportable, unlike a slice of a caching allocator)."""
+
+    def __init__(self, nbytes):
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        check(load().bk_dev_alloc(C.byref(p), self.nbytes))
+        self.ptr = p.value
+        self._owned = True
+
+    @classmethod
+    def from_numpy(cls, a, stream=None):
+        a = np.ascontiguousarray(a)
+        b = cls(a.nbytes)
+        b.upload(a, stream)
+        return b
+
+    def upload(self, a, stream=None):
+        a = np.ascontiguousarray(a)
+        assert a.nbytes <= self.nbytes
+        check(load().bk_memcpy_h2d(self.ptr, a.ctypes.data, a.nbytes, stream))
+        check(load().bk_stream_sync(stream))
+
+    def download(self, dtype, count=None, offset_bytes=0, stream=None):
+        dtype = np.dtype(dtype)
+        n = (self.nbytes - offset_bytes) // dtype.itemsize if count is None else int(count)
+        out = np.empty(n, dtype=dtype)
+        check(load().bk_memcpy_d2h(out.ctypes.data, self.ptr + offset_bytes, out.nbytes, stream))
+        check(load().bk_stream_sync(stream))
+        return out
+
+    def zero(self, stream=None):
+        check(load().bk_dev_memset(self.ptr, 0, self.nbytes, stream))
+
+    def free(self):
+        if self._owned and self.ptr:
+            load().bk_dev_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class BrickInfo:
+    """BrickInfo<3>: the adjacency list, mirrored to the device (replaces movBrickInfo, brick-gpu.h:43-57)."""
+
+    def __init__(self, adj_host):
+        adj_host = np.ascontiguousarray(adj_host, dtype=np.uint32).reshape(-1, 27)
+        self.nbricks = adj_host.shape[0]
+        self.adj_host = adj_host
+        self.adj = DeviceBuffer.from_numpy(adj_host)
+
+    def allocate(self, step):
+        return BrickStorage.allocate(self.nbricks, step)
+
+
+class BrickStorage:
+    """BrickStorage on the device: `chunks` bricks, `step` elements apart (brick.h:53-82)."""
+
+    def __init__(self, chunks, step, dat):
+        self.chunks, self.step, self.dat = int(chunks), int(step), dat
+
+    @classmethod
+    def allocate(cls, chunks, step):
+        buf = DeviceBuffer(int(chunks) * int(step) * 8)
+        buf.zero()  # the null brick (id 0) and padding read as 0.0 instead of garbage
+        return cls(chunks, step, buf)
+
+    def brick_ptr(self, b, offset=0):
+        return self.dat.ptr + (int(b) * self.step + offset) * 8
+
+    def to_host(self):
+        return self.dat.download(np.float64)
+
+    def from_host(self, a):
+        self.dat.upload(np.ascontiguousarray(a, dtype=np.float64))
+
+
+class Brick:
+    """Brick<Dim<8,8,8>,Dim<4,8>>(bInfo, bStorage, offset): a view (brick.h:389-393)."""
+
+    def __init__(self, info, storage, offset=0):
+        self.info, self.storage, self.offset = info, storage, int(offset)
+        self.step = storage.step
+        self.dat = storage.dat.ptr + self.offset * 8
+
+
+def init_grid(dimlist):
+    """init_grid<3>(grid_ptr, dimlist): returns (grid[k][j][i] host array, BrickInfo)."""
+    n = int(np.prod(dimlist))
+    grid = np.zeros(n, dtype=np.uint32)
+    adj = np.zeros((n, 27), dtype=np.uint32)
+    check(load().bk_init_grid(_l3(dimlist), grid.ctypes.data_as(_lib.up), adj.ctypes.data_as(_lib.up)))
+    return grid.reshape(tuple(dimlist)[::-1]), adj
+
+
+class DeviceGrid:
+    """dense brick-id array on the device + its extents (i first)."""
+
+    def __init__(self, grid_host):
+        self.host = np.ascontiguousarray(grid_host, dtype=np.uint32)
+        self.dims = tuple(self.host.shape[::-1])
+        self.dev = DeviceBuffer.from_numpy(self.host)
+
+
+def copyToBrick(dimlist, padding, ghost, arr_dev, grid, brick, stream=None):
+    check(load().bk_copy_to_brick(_l3(dimlist), _l3(padding), _l3(ghost), arr_dev.ptr, grid.dev.ptr, brick.dat,
+                                  brick.step, stream))
+
+
+def copyFromBrick(dimlist, padding, ghost, arr_dev, grid, brick, stream=None):
+    check(load().bk_copy_from_brick(_l3(dimlist), _l3(padding), _l3(ghost), arr_dev.ptr, grid.dev.ptr, brick.dat,
+                                    brick.step, stream))
+
+
+def compareBrick(dimlist, padding, ghost, arr_dev, grid, brick, tol=1e-12, stream=None):
+    """returns (ok, mismatching cells, max relative difference)"""
+    bad = C.c_ulonglong()
+    rel = C.c_double()
+    check(load().bk_compare_brick(_l3(dimlist), _l3(padding), _l3(ghost), arr_dev.ptr, grid.dev.ptr, brick.dat,
+                                  brick.step, tol, C.byref(bad), C.byref(rel), stream))
+    return bad.value == 0, bad.value, rel.value
+
+
+def _field(b_in, b_out):
+    assert b_in.info is b_out.info or b_in.info.adj.ptr == b_out.info.adj.ptr
+    return Field(b_in.info.adj.ptr, b_in.dat, b_in.step, b_out.dat, b_out.step)
+
+
+def _coeff(coeff):
+    if coeff is None:
+        return None
+    c = np.ascontiguousarray(coeff, dtype=np.float64)
+    return c.ctypes.data_as(_lib.dp)
+
+
+def stencil(stencil_id, grid, b_in, b_out, lo=None, hi=None, coeff=None, kernel=_lib.KERNEL_AUTO, stream=None):
+    """out = stencil(in) over the brick box [lo,hi) of `grid` -- the brick_kernel<<<...>>> launch."""
+    lo = (0, 0, 0) if lo is None else lo
+    hi = grid.dims if hi is None else hi
+    f = _field(b_in, b_out)
+    check(load().bk_stencil_apply(stencil_id, C.byref(f), grid.dev.ptr, _u3(grid.dims), _u3(lo), _u3(hi),
+                                  _coeff(coeff), kernel, stream))
+
+
+def stencil_list(stencil_id, ids_dev, n, b_in, b_out, coeff=None, stream=None):
+    f = _field(b_in, b_out)
+    check(load().bk_stencil_apply_list(stencil_id, C.byref(f), ids_dev.ptr, n, _coeff(coeff), stream))
+
+
+class BrickDecomp:
+    """BrickDecomp<3,8,8,8>(dims, depth) + initialize(skin3d_good) (brick-mpi.h:178-513)."""
+
+    def __init__(self, dims, depth=8):
+        h = C.c_void_p()
+        check(load().bk_decomp_create(C.byref(h), _u3(dims), depth))
+        self._h = h
+        L = load()
+        self.dims, self.depth = tuple(int(x) for x in dims), depth
+        self.nbricks = L.bk_decomp_nbricks(h)
+        sep, t = (C.c_uint * 3)(), (C.c_uint * 3)()
+        check(L.bk_decomp_sep_pos(h, sep))
+        check(L.bk_decomp_tdims(h, t))
+        self.sep_pos, self.tdims = tuple(sep), tuple(t)
+        n = self.tdims[0] * self.tdims[1] * self.tdims[2]
+        self.grid = np.ctypeslib.as_array(L.bk_decomp_grid(h), shape=(n,)).reshape(self.tdims[::-1]).copy()
+        self.adj = np.ctypeslib.as_array(L.bk_decomp_adj(h), shape=(self.nbricks * 27,)).reshape(-1, 27).copy()
+        self.ghost, self.skin = [], []
+        for which, dst in ((0, self.ghost), (1, self.skin)):
+            for i in range(L.bk_decomp_nregions(h)):
+                r = Region()
+                check(L.bk_decomp_region(h, which, i, C.byref(r)))
+                dst.append(r)
+        ss = (C.c_long * 26)()
+        check(L.bk_decomp_skin_size(h, ss))
+        self.skin_size = list(ss)
+        self.rank_map = {}
+        self._info = None
+
+    def populate(self, cart, coo):
+        """populate(comm, bDecomp, 0, 1, coo) for a periodic Cartesian grid of processes."""
+        sets, ranks = (C.c_uint64 * 27)(), (C.c_int * 27)()
+        check(load().bk_rank_map((C.c_int * 3)(*cart), (C.c_int * 3)(*coo), sets, ranks))
+        self.rank_map = {int(s): int(r) for s, r in zip(sets, ranks)}
+        return self.rank_map
+
+    def getBrickInfo(self):
+        if self._info is None:
+            self._info = BrickInfo(self.adj)
+        return self._info
+
+    def id_list(self, which):
+        n = load().bk_decomp_list(self._h, which, None)
+        ids = np.zeros(n, dtype=np.uint32)
+        load().bk_decomp_list(self._h, which, ids.ctypes.data_as(_lib.up))
+        return ids
+
+    def exchange_bytes(self, step=BRICK):
+        return sum(g.len for g in self.ghost) * step * 8
+
+    def __del__(self):
+        try:
+            load().bk_decomp_destroy(self._h)
+        except Exception:
+            pass
+
+
+class ExchangeView:
+    """One fused pull of every ghost region of a storage: ghost[i] <- peer_base[rank_map[ghost[i].neighbor]] skin[i].
+
+    Stands in for ExchangeView::exchange / BrickDecomp::exchange (brick-mpi.h:96-123, :466-495).  `peer_ptrs[r]` is the
+    device address of rank r's storage as seen from THIS process (own pointer, or a CUDA-IPC mapping)."""
+
+    def __init__(self, decomp, storage, peer_ptrs, my_rank=0):
+        segs = (Seg * len(decomp.ghost))()
+        self.remote_bytes = 0
+        for i, (g, s) in enumerate(zip(decomp.ghost, decomp.skin)):
+            peer = decomp.rank_map[g.neighbor]
+            segs[i].src = peer_ptrs[peer] + s.pos * storage.step * 8
+            segs[i].dst = storage.dat.ptr + g.pos * storage.step * 8
+            segs[i].bytes = g.len * storage.step * 8
+            if peer != my_rank:
+                self.remote_bytes += segs[i].bytes
+        h = C.c_void_p()
+        check(load().bk_xplan_create(C.byref(h), segs, len(decomp.ghost)))
+        self._h = h
+        self.bytes = load().bk_xplan_bytes(h)
+
+    def exchange(self, stream=None):
+        check(load().bk_xplan_run(self._h, stream))
+
+    def exchange_sync(self, wait_flags, signal_flags, epoch, stream=None):
+        w = (C.c_void_p * max(1, len(wait_flags)))(*wait_flags)
+        s = (C.c_void_p * max(1, len(signal_flags)))(*signal_flags)
+        check(load().bk_xplan_run_sync(self._h, w, len(wait_flags), s, len(signal_flags), epoch, stream))
+
+    def __del__(self):
+        try:
+            load().bk_xplan_destroy(self._h)
+        except Exception:
+            pass
+
+
+def device_sync():
+    check(load().bk_device_sync())
+
+
+class Event:
+    def __init__(self):
+        e = C.c_void_p()
+        check(load().bk_event_create(C.byref(e)))
+        self.h = e
+
+    def record(self, stream=None):
+        check(load().bk_event_record(self.h, stream))
+
+    def sync(self):
+        check(load().bk_event_sync(self.h))
+
+    def elapsed_ms(self, later):
+        ms = C.c_float()
+        check(load().bk_event_elapsed_ms(self.h, later.h, C.byref(ms)))
+        return ms.value

@@ -1,0 +1,185 @@
+// bk_exchange.cu -- ghost-zone exchange as ONE kernel over a list of contiguous brick ranges.
+//
+// Because BrickDecomp lays every ghost and skin region out as a contiguous run of bricks, an exchange is a list of
+// plain range copies ghost[i] <- peer.skin[i] (include/brick-mpi.h:466-495 posts them as 42 Irecv/Isend pairs;
+// strong/main.cu:76-83 cudaCopy moves one range per CTA with 8-byte accesses).  Here a whole plan (all 42 ranges of a
+// subdomain, or every link of a strong-scaling rank) runs as a single persistent kernel: the ranges are cut into
+// 16 KiB chunks, CTAs stride over the chunk list, every thread moves 16 bytes per access with four loads in flight.
+// A source pointer may live in a peer GPU (CUDA IPC / peer access): the loads then cross NVLink, which makes this a
+// PULL exchange -- no pack, no unpack, no staging buffer.  The optional flags implement the cross-process handshake.
+#include "bk_common.h"
+#include <vector>
+
+struct bk_xplan {
+  bk_seg_t *segs_dev = nullptr;
+  unsigned long long *chunk_first_dev = nullptr;  // prefix sum of chunks per segment, nseg+1 entries
+  int nseg = 0;
+  unsigned long long nchunks = 0;
+  size_t bytes = 0;
+  uint64_t **flagbuf_dev = nullptr;  // scratch for flag pointer lists (64 wait + 64 signal)
+};
+
+namespace {
+
+constexpr unsigned kChunkBytes = 16384;
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ void spin_until(const uint64_t *flag, uint64_t value) {
+  const volatile uint64_t *f = flag;
+  while (*f < value) __nanosleep(64);
+}
+
+__global__ void __launch_bounds__(kThreads) k_xplan(const bk_seg_t *__restrict__ segs,
+                                                   const unsigned long long *__restrict__ first, int nseg,
+                                                   unsigned long long nchunks, uint64_t *const *wait_flags, int nwait) {
+  if (nwait > 0) {
+    if (threadIdx.x < nwait) spin_until(wait_flags[threadIdx.x], (uint64_t) (size_t) wait_flags[64]);
+    __syncthreads();
+  }
+  for (unsigned long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+    int lo = 0, hi = nseg;  // segment s with first[s] <= c < first[s+1]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (first[mid] <= c) lo = mid; else hi = mid;
+    }
+    const bk_seg_t sg = segs[lo];
+    const size_t off = (size_t) (c - first[lo]) * kChunkBytes;
+    const size_t n16 = (min((size_t) kChunkBytes, sg.bytes - off)) >> 4;
+    const int4 *src = reinterpret_cast<const int4 *>(static_cast<const char *>(sg.src) + off);
+    int4 *dst = reinterpret_cast<int4 *>(static_cast<char *>(sg.dst) + off);
+    if (n16 == kChunkBytes / 16) {
+      int4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = src[threadIdx.x + u * kThreads];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) dst[threadIdx.x + u * kThreads] = v[u];
+    } else {
+      for (size_t x = threadIdx.x; x < n16; x += kThreads) dst[x] = src[x];
+    }
+  }
+}
+
+// after the copy kernel: make the writes visible system-wide, then raise the flags (possibly in peer memory)
+__global__ void k_signal(uint64_t *const *flags, int n, uint64_t value) {
+  __threadfence_system();
+  if ((int) threadIdx.x < n) {
+    volatile uint64_t *f = flags[threadIdx.x];
+    *f = value;
+  }
+  __threadfence_system();
+}
+__global__ void k_wait(const uint64_t *const *flags, int n, uint64_t value) {
+  if ((int) threadIdx.x < n) spin_until(flags[threadIdx.x], value);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int launch_copy(bk_xplan *p, uint64_t *const *wait_dev, int nwait, cudaStream_t s) {
+  if (p->nchunks == 0 && nwait == 0) return BK_OK;
+  unsigned long long want = p->nchunks ? p->nchunks : 1;
+  const unsigned long long cap = (unsigned long long) sm_count() * 8;
+  const unsigned grid = (unsigned) (want < cap ? want : cap);
+  k_xplan<<<grid, kThreads, 0, s>>>(p->segs_dev, p->chunk_first_dev, p->nseg, p->nchunks, wait_dev, nwait);
+  BK_LAUNCHED();
+  return BK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bk_xplan_create(bk_xplan_t **out, const bk_seg_t *segs, int nseg) {
+  BK_REQUIRE(out && (segs || nseg == 0) && nseg >= 0, "bad arguments");
+  std::vector<unsigned long long> first(nseg + 1, 0);
+  size_t total = 0;
+  for (int i = 0; i < nseg; ++i) {
+    BK_REQUIRE(segs[i].bytes % 16 == 0 && ((size_t) segs[i].src % 16) == 0 && ((size_t) segs[i].dst % 16) == 0,
+               "segments must be 16-byte aligned and sized");
+    first[i + 1] = first[i] + (segs[i].bytes + kChunkBytes - 1) / kChunkBytes;
+    total += segs[i].bytes;
+  }
+  bk_xplan *p = new bk_xplan();
+  p->nseg = nseg;
+  p->nchunks = first[nseg];
+  p->bytes = total;
+  if (nseg) {
+    BK_CUDA(cudaMalloc(&p->segs_dev, sizeof(bk_seg_t) * nseg));
+    BK_CUDA(cudaMemcpy(p->segs_dev, segs, sizeof(bk_seg_t) * nseg, cudaMemcpyHostToDevice));
+  }
+  BK_CUDA(cudaMalloc(&p->chunk_first_dev, sizeof(unsigned long long) * (nseg + 1)));
+  BK_CUDA(cudaMemcpy(p->chunk_first_dev, first.data(), sizeof(unsigned long long) * (nseg + 1), cudaMemcpyHostToDevice));
+  BK_CUDA(cudaMalloc(&p->flagbuf_dev, sizeof(uint64_t *) * 192));
+  *out = p;
+  return BK_OK;
+}
+
+int bk_xplan_destroy(bk_xplan_t *p) {
+  if (!p) return BK_OK;
+  cudaFree(p->segs_dev);
+  cudaFree(p->chunk_first_dev);
+  cudaFree(p->flagbuf_dev);
+  delete p;
+  return BK_OK;
+}
+
+size_t bk_xplan_bytes(const bk_xplan_t *p) { return p ? p->bytes : 0; }
+
+int bk_xplan_run(bk_xplan_t *p, void *stream) {
+  BK_REQUIRE(p, "null plan");
+  return launch_copy(p, nullptr, 0, (cudaStream_t) stream);
+}
+
+int bk_xplan_run_sync(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwait, uint64_t *const *signal_flags,
+                      int nsignal, uint64_t epoch, void *stream) {
+  BK_REQUIRE(p, "null plan");
+  BK_REQUIRE(nwait >= 0 && nwait <= 64 && nsignal >= 0 && nsignal <= 64, "at most 64 flags each");
+  cudaStream_t s = (cudaStream_t) stream;
+  // flag pointer lists travel through a small device scratch: [0,64) wait pointers, [64] = epoch, [65,129) signals
+  uint64_t *host[130] = {nullptr};
+  for (int i = 0; i < nwait; ++i) host[i] = const_cast<uint64_t *>(wait_flags[i]);
+  host[64] = (uint64_t *) (size_t) epoch;
+  for (int i = 0; i < nsignal; ++i) host[65 + i] = signal_flags[i];
+  BK_CUDA(cudaMemcpyAsync(p->flagbuf_dev, host, sizeof(host), cudaMemcpyHostToDevice, s));
+  int rc = launch_copy(p, p->flagbuf_dev, nwait, s);
+  if (rc != BK_OK) return rc;
+  if (nsignal > 0) {
+    k_signal<<<1, 64, 0, s>>>(p->flagbuf_dev + 65, nsignal, epoch);
+    BK_LAUNCHED();
+  }
+  return BK_OK;
+}
+
+int bk_flags_signal(uint64_t *const *flags, int n, uint64_t value, void *stream) {
+  BK_REQUIRE(flags && n > 0 && n <= 64, "1..64 flags");
+  uint64_t **dev = nullptr;
+  cudaStream_t s = (cudaStream_t) stream;
+  BK_CUDA(cudaMallocAsync(&dev, sizeof(uint64_t *) * n, s));
+  BK_CUDA(cudaMemcpyAsync(dev, flags, sizeof(uint64_t *) * n, cudaMemcpyHostToDevice, s));
+  k_signal<<<1, 64, 0, s>>>(dev, n, value);
+  BK_LAUNCHED();
+  BK_CUDA(cudaFreeAsync(dev, s));
+  return BK_OK;
+}
+
+int bk_flags_wait(const uint64_t *const *flags, int n, uint64_t value, void *stream) {
+  BK_REQUIRE(flags && n > 0 && n <= 64, "1..64 flags");
+  uint64_t **dev = nullptr;
+  cudaStream_t s = (cudaStream_t) stream;
+  BK_CUDA(cudaMallocAsync(&dev, sizeof(uint64_t *) * n, s));
+  BK_CUDA(cudaMemcpyAsync(dev, flags, sizeof(uint64_t *) * n, cudaMemcpyHostToDevice, s));
+  k_wait<<<1, 64, 0, s>>>(dev, n, value);
+  BK_LAUNCHED();
+  BK_CUDA(cudaFreeAsync(dev, s));
+  return BK_OK;
+}
+
+}  // extern "C"

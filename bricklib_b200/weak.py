@@ -1,0 +1,178 @@
+"""The weak-scaling time loop (weak/main.cu:246-287) on one GPU per process.
+
+Per exchange period:  ghost <- neighbours' skin  (one fused pull kernel over the 42 contiguous brick ranges, peers
+reached through CUDA-IPC mappings over NVLink; self-neighbours are ordinary device copies in the same kernel), then
+ST_ITER sweeps ping-ponging in -> out -> in.  The last sweep of a period skips the ghost shell (weak/main.cpp:209).
+
+Overlap (25-point stencil, ST_ITER = 2, matters most): the inner bricks [2,n-2)^3 never read ghost bricks, so their
+first sweep runs on the compute stream WHILE the pull kernel runs on the comm stream; the six boundary slabs follow
+once the pull has finished.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, core
+from ._lib import check, load
+
+PADDING = 8
+GZ = 8
+
+
+class Handshake:
+    """Cross-process flags in IPC-shared device memory.
+
+    flags[r*2+0] on rank p = "rank r's skin is final for epoch e" (written by r, polled by p before pulling),
+    flags[r*2+1] on rank p = "rank r has finished pulling p's skin for epoch e" (p polls before overwriting skin)."""
+
+    def __init__(self, world):
+        self.world = world
+        self.buf = core.DeviceBuffer(max(1, world) * 2 * 8)
+        self.buf.zero()
+        core.device_sync()
+        self.peer = {}  # rank -> base pointer of that rank's flag buffer as seen here
+
+    def ready_flag_on(self, peer, writer):
+        return self.peer[peer] + (writer * 2 + 0) * 8
+
+    def done_flag_on(self, peer, writer):
+        return self.peer[peer] + (writer * 2 + 1) * 8
+
+
+class WeakDomain:
+    """One subdomain: decomposition, two storages, exchange plan, sweep schedule."""
+
+    def __init__(self, dom, stencil_id, cart=(1, 1, 1), coo=(0, 0, 0), rank=0, kernel=_lib.KERNEL_AUTO):
+        self.dom = tuple(dom)
+        self.stencil = stencil_id
+        self.kernel = kernel
+        self.rank = rank
+        self.cart = tuple(cart)
+        self.world = cart[0] * cart[1] * cart[2]
+        L = load()
+        self.st_iter = L.bk_stencil_st_iter(stencil_id)
+        self.decomp = core.BrickDecomp(dom, GZ)
+        self.decomp.populate(cart, coo)
+        self.info = self.decomp.getBrickInfo()
+        self.grid = core.DeviceGrid(self.decomp.grid)
+        self.storage = [self.info.allocate(core.BRICK), self.info.allocate(core.BRICK)]
+        self.bricks = [core.Brick(self.info, s, 0) for s in self.storage]
+        self.peers = sorted({self.decomp.rank_map[g.neighbor] for g in self.decomp.ghost} - {rank})
+        self.view = None
+        self.hs = None
+        self.epoch = 0
+        self.comm_stream = None
+        self.ev_comm = self.ev_comp = None
+
+    # ---- wiring -------------------------------------------------------------------------------------------------
+    def connect(self, peer_storage_ptrs=None, handshake=None):
+        """peer_storage_ptrs[r]: device pointer of rank r's storage[0] visible here (self entry may be omitted)."""
+        ptrs = dict(peer_storage_ptrs or {})
+        ptrs[self.rank] = self.storage[0].dat.ptr
+        self.view = core.ExchangeView(self.decomp, self.storage[0], ptrs, self.rank)
+        self.hs = handshake
+
+    def enable_overlap(self):
+        s = C.c_void_p()
+        check(load().bk_stream_create(C.byref(s)))
+        self.comm_stream = s
+        self.ev_comm, self.ev_comp = core.Event(), core.Event()
+
+    # ---- data ---------------------------------------------------------------------------------------------------
+    def load_interior(self, field):
+        """field[k][j][i] = interior cells; ghost cells are left zero (filled by the first exchange)."""
+        ext = tuple(n + 2 * (PADDING + GZ) for n in self.dom[::-1])
+        arr = np.zeros(ext)
+        o = PADDING + GZ
+        arr[o:-o, o:-o, o:-o] = field
+        dev = core.DeviceBuffer.from_numpy(arr)
+        strideg = tuple(n + 2 * GZ for n in self.dom)
+        core.copyToBrick(strideg, (PADDING,) * 3, (0,) * 3, dev, self.grid, self.bricks[0])
+        core.device_sync()
+        dev.free()
+
+    def read_interior(self, which=0):
+        ext = tuple(n + 2 * (PADDING + GZ) for n in self.dom[::-1])
+        dev = core.DeviceBuffer(int(np.prod(ext)) * 8)
+        dev.zero()
+        core.copyFromBrick(self.dom, (PADDING,) * 3, (GZ,) * 3, dev, self.grid, self.bricks[which])
+        arr = dev.download(np.float64).reshape(ext)
+        dev.free()
+        o = PADDING + GZ
+        return np.ascontiguousarray(arr[o:-o, o:-o, o:-o])
+
+    # ---- the time loop ------------------------------------------------------------------------------------------
+    def _sweep(self, src, dst, lo, hi, stream):
+        core.stencil(self.stencil, self.grid, self.bricks[src], self.bricks[dst], lo, hi, None, self.kernel, stream)
+
+    def _exchange(self, stream):
+        if self.hs is None or not self.peers:
+            self.view.exchange(stream)
+            return
+        hs, e = self.hs, self.epoch
+        # tell every peer my skin is final, pull theirs once they say the same, then tell them I am done reading
+        sig = (C.c_void_p * len(self.peers))(*[hs.ready_flag_on(p, self.rank) for p in self.peers])
+        check(load().bk_flags_signal(sig, len(self.peers), e, stream))
+        waits = [hs.ready_flag_on(self.rank, p) for p in self.peers]
+        dones = [hs.done_flag_on(p, self.rank) for p in self.peers]
+        self.view.exchange_sync(waits, dones, e, stream)
+
+    def _wait_peers_done(self, stream):
+        if self.hs is None or not self.peers:
+            return
+        w = (C.c_void_p * len(self.peers))(*[self.hs.done_flag_on(self.rank, p) for p in self.peers])
+        check(load().bk_flags_wait(w, len(self.peers), self.epoch, stream))
+
+    def period(self, stream=None):
+        """one exchange + ST_ITER sweeps; returns the number of kernel launches issued"""
+        n0 = load().bk_launch_count()
+        self.epoch += 1
+        t = self.grid.dims
+        full_lo, full_hi = (0, 0, 0), t
+        if self.comm_stream is None:
+            self._exchange(stream)
+            for s in range(self.st_iter):
+                last = s == self.st_iter - 1
+                if s == 1:
+                    self._wait_peers_done(stream)  # sweep 1 rewrites storage[0], whose skin peers were reading
+                lo, hi = ((1, 1, 1), tuple(x - 1 for x in t)) if last else (full_lo, full_hi)
+                self._sweep(s % 2, 1 - s % 2, lo, hi, stream)
+        else:
+            cs = self.comm_stream
+            self.ev_comp.record(stream)
+            check(load().bk_stream_wait_event(cs, self.ev_comp.h))  # previous period's sweeps wrote the skin
+            self._exchange(cs)
+            self.ev_comm.record(cs)
+            g = GZ // 8
+            in_lo, in_hi = (2 * g,) * 3, tuple(x - 2 * g for x in t)
+            self._sweep(0, 1, in_lo, in_hi, stream)  # inner bricks: no ghost input, overlaps the pull
+            check(load().bk_stream_wait_event(stream, self.ev_comm.h))
+            first_hi = t if self.st_iter > 1 else tuple(x - g for x in t)
+            first_lo = (0, 0, 0) if self.st_iter > 1 else (g,) * 3
+            for lo, hi in shell_boxes(first_lo, first_hi, in_lo, in_hi):
+                self._sweep(0, 1, lo, hi, stream)
+            for s in range(1, self.st_iter):
+                last = s == self.st_iter - 1
+                if s == 1:
+                    self._wait_peers_done(stream)
+                lo, hi = ((g,) * 3, tuple(x - g for x in t)) if last else (full_lo, full_hi)
+                self._sweep(s % 2, 1 - s % 2, lo, hi, stream)
+        return load().bk_launch_count() - n0
+
+
+def shell_boxes(lo, hi, in_lo, in_hi):
+    """the six slabs of box [lo,hi) minus inner box [in_lo,in_hi): two k-slabs, two j-slabs, two i-slabs"""
+    out = []
+    if in_lo[2] > lo[2]:
+        out.append((lo, (hi[0], hi[1], in_lo[2])))
+    if hi[2] > in_hi[2]:
+        out.append(((lo[0], lo[1], in_hi[2]), hi))
+    if in_lo[1] > lo[1]:
+        out.append(((lo[0], lo[1], in_lo[2]), (hi[0], in_lo[1], in_hi[2])))
+    if hi[1] > in_hi[1]:
+        out.append(((lo[0], in_hi[1], in_lo[2]), (hi[0], hi[1], in_hi[2])))
+    if in_lo[0] > lo[0]:
+        out.append(((lo[0], in_lo[1], in_lo[2]), (in_lo[0], in_hi[1], in_hi[2])))
+    if hi[0] > in_hi[0]:
+        out.append(((in_hi[0], in_lo[1], in_lo[2]), (hi[0], in_hi[1], in_hi[2])))
+    return out

@@ -1,0 +1,178 @@
+/*
+ * bricklib_b200.h -- C ABI of libbrick_b200.so: the B200 (sm_100a) implementation of bricklib's hot path
+ * (FP64 7/13/25/125-point stencils over 8x8x8 bricks + ghost-zone exchange).
+ *
+ * The reference (CtopCsUtahEdu/bricklib) has no runtime FFI: its seam is source level -- the brick(...) macro inside a
+ * __global__ function, the kernel launch, BrickDecomp::exchange and the movBrick* helpers.
+ * Each entry point below names the reference interface it stands in for (file:line under the reference tree).
+ * The C++ headers next to this file (brick.h, brick-mpi.h, ...) re-create the reference's template surface on top of
+ * these calls; INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes only.  "dev" pointers are CUDA device pointers on the current device,
+ * "host" pointers are ordinary memory.  Every call returns 0 (BK_OK) or a negative code; bk_last_error() gives text.
+ * `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Nothing is thread-hostile: state is
+ * per call or per handle.  There is NO CPU fallback: without a CUDA device every compute call fails with BK_ECUDA.
+ */
+#ifndef BRICKLIB_B200_H
+#define BRICKLIB_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BK_OK 0
+#define BK_EINVAL (-1)   /* bad argument */
+#define BK_ECUDA (-2)    /* CUDA runtime error (text in bk_last_error) */
+#define BK_ENOMEM (-3)
+#define BK_EUNSUPPORTED (-4)
+
+/* stencil ids = the reference's stencil specs, stencils/{7pt,mpi7pt,mpi13pt,mpi25pt,mpi125pt}.py */
+enum { BK_ST_7PT = 0, BK_ST_MPI7PT = 1, BK_ST_MPI13PT = 2, BK_ST_MPI25PT = 3, BK_ST_MPI125PT = 4, BK_ST_COUNT = 5 };
+
+/* kernel families (bk_stencil_apply picks; tests can force one through `flags`) */
+#define BK_KERNEL_AUTO 0u
+#define BK_KERNEL_BRICK 1u  /* one CTA per brick, neighbours through adj: works for any brick set */
+#define BK_KERNEL_TILED 2u  /* CTA marches a column of bricks of a dense grid box: the fast path */
+
+const char *bk_version(void);
+const char *bk_last_error(void);
+
+/* ---- stencil metadata (stencils/fake.h:11-33, :39-344) --------------------------------------------------------- */
+int bk_stencil_radius(int stencil);  /* 1,1,2,4,2 */
+int bk_stencil_st_iter(int stencil); /* sweeps per ghost exchange: 8,8,4,2,4 (= ghost depth 8 / radius) */
+int bk_stencil_points(int stencil);  /* 7,7,13,25,125 */
+
+/* ---- device plumbing (stands in for include/brick-gpu.h:43-103 movBrickInfo/movBrickStorage, cudaarray.h:11-31) - */
+int bk_device_count(int *n);
+int bk_set_device(int dev);
+int bk_dev_alloc(void **dev, size_t bytes); /* cudaMalloc: 256-B aligned, exportable with bk_ipc_export */
+int bk_dev_free(void *dev);
+int bk_dev_memset(void *dev, int byte, size_t bytes, void *stream);
+int bk_host_alloc(void **host, size_t bytes); /* pinned */
+int bk_host_free(void *host);
+int bk_memcpy_h2d(void *dev, const void *host, size_t bytes, void *stream);
+int bk_memcpy_d2h(void *host, const void *dev, size_t bytes, void *stream);
+int bk_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
+int bk_stream_create(void **stream);
+int bk_stream_destroy(void *stream);
+int bk_stream_sync(void *stream);
+int bk_device_sync(void);
+/* events: timing on the launching stream (stencils/stencils_cu.h:13-28 cutime_func) and cross-stream ordering */
+int bk_event_create(void **ev);
+int bk_event_destroy(void *ev);
+int bk_event_record(void *ev, void *stream);
+int bk_event_sync(void *ev);
+int bk_event_elapsed_ms(void *start, void *stop, float *ms);
+int bk_stream_wait_event(void *stream, void *ev);
+
+/* ---- grids and adjacency (host side, pure integer work) -------------------------------------------------------- */
+/* init_grid<3> (include/bricksetup.h:73-90): grid[p] = p, adj by +-stride, out of linear range -> 0.
+ * dimlist = bricks per axis, i first.  grid: prod(dimlist) unsigned; adj: prod(dimlist)*27 unsigned. */
+int bk_init_grid(const long *dimlist, unsigned *grid_host, unsigned *adj_host);
+
+/* BrickDecomp<3,8,8,8>(dims, depth).initialize(skin3d_good) (include/brick-mpi.h:304-460, src/brick-mpi.cpp:25-52),
+ * DECOMP_PAGEUNALIGN numbering (the weak/strong CUDA drivers' configuration, weak/CMakeLists.txt:32). */
+typedef struct bk_decomp bk_decomp_t;
+typedef struct {
+  uint64_t neighbor;          /* BitSet.set (include/bitset.h): bit a = +axis a, bit 31+a = -axis a, axis 1 = i */
+  unsigned skin_st, skin_ed;  /* range in the skin list */
+  unsigned pos, len;          /* first brick id and number of bricks (contiguous) */
+  unsigned first_pad, last_pad; /* always 0 for 4 KiB bricks; kept for BrickDecomp::g_region layout parity */
+} bk_region_t;
+
+int bk_decomp_create(bk_decomp_t **d, const unsigned *dom_cells, unsigned depth_cells);
+int bk_decomp_destroy(bk_decomp_t *d);
+unsigned bk_decomp_nbricks(const bk_decomp_t *d);                /* BrickInfo::nbricks, includes null brick 0 */
+int bk_decomp_sep_pos(const bk_decomp_t *d, unsigned *sep3);     /* BrickDecomp::sep_pos */
+int bk_decomp_tdims(const bk_decomp_t *d, unsigned *tdims3);     /* bricks per axis incl. ghost shell */
+const unsigned *bk_decomp_grid(const bk_decomp_t *d);            /* BrickDecomp::operator[]: [k][j][i] -> id */
+const unsigned *bk_decomp_adj(const bk_decomp_t *d);             /* BrickInfo<3>::adj, nbricks*27 */
+int bk_decomp_nregions(const bk_decomp_t *d);                    /* ghost.size() == skin.size() (42) */
+int bk_decomp_region(const bk_decomp_t *d, int which /*0 ghost,1 skin*/, int i, bk_region_t *out);
+int bk_decomp_skin_size(const bk_decomp_t *d, long *out26);      /* BrickDecomp::skin_size */
+/* brick-id lists for overlap: which 0 = inner (reads no ghost), 1 = skin, 2 = ghost; returns count, fills if non-NULL */
+long bk_decomp_list(const bk_decomp_t *d, int which, unsigned *ids_host);
+
+/* populate(comm, bDecomp, 0, 1, coo) (include/brick-mpi.h:730-753) for a periodic Cartesian grid `cart` (cart[0]
+ * slowest, MPI order) seen from coordinates `coo`: 27 (set, rank) pairs in allneighbors order. */
+int bk_rank_map(const int *cart, const int *coo, uint64_t *sets27, int *ranks27);
+/* Z-Morton helpers for the strong driver (include/zmort.h:18-105) */
+unsigned long bk_zmort_encode(const unsigned long *coord3);
+int bk_zmort_decode(unsigned long id, unsigned long *coord3);
+
+/* ---- array <-> brick on the device (include/bricksetup.h:139-221, include/brickcompare.h:30-57) ---------------- */
+/* dimlist/padding/ghost in cells, i first, meaning exactly as in copyToBrick<3>(dimlist, padding, ghost, arr, grid, b) */
+int bk_copy_to_brick(const long *dimlist, const long *padding, const long *ghost, const double *arr_dev,
+                     const unsigned *grid_dev, double *dat_dev, size_t step, void *stream);
+int bk_copy_from_brick(const long *dimlist, const long *padding, const long *ghost, double *arr_dev,
+                       const unsigned *grid_dev, const double *dat_dev, size_t step, void *stream);
+/* compareBrick with an explicit tolerance: counts cells with |a-b| >= tol && |a-b| >= (|a|+|b|)*tol; also returns the
+ * largest relative difference.  Synchronises `stream`. */
+int bk_compare_brick(const long *dimlist, const long *padding, const long *ghost, const double *arr_dev,
+                     const unsigned *grid_dev, const double *dat_dev, size_t step, double tol,
+                     unsigned long long *mismatches, double *max_rel, void *stream);
+
+/* ---- the stencil sweep ---------------------------------------------------------------------------------------- */
+/* One field pair = the two Brick<Dim<8,8,8>,Dim<4,8>> objects a reference kernel receives by value
+ * (include/brick.h:353-395): dat pointers already include the field offset, steps are in elements. */
+typedef struct {
+  const unsigned *adj; /* dev, BrickInfo<3>::adj */
+  const double *in;    /* dev, Brick::dat of the input  */
+  size_t in_step;      /* Brick::step */
+  double *out;         /* dev, Brick::dat of the output */
+  size_t out_step;
+} bk_field_t;
+
+/* Replaces the launch  brick_kernel<<<dim3(strideb...),32>>>(grid, in, out, stride)  (weak/main.cu:35-43, :277-282;
+ * stencils/3axis.cu:28-37, :163-169): out = stencil(in) for every brick of the half-open brick box [lo,hi) of the dense
+ * id array `grid_dev` (gdims = bricks per axis, i first).  coeff_host: 7 doubles for BK_ST_7PT (coeff[0..6] of
+ * single/cpu.cpp:11-17), ignored (may be NULL) otherwise.  Asynchronous on `stream`. */
+int bk_stencil_apply(int stencil, const bk_field_t *f, const unsigned *grid_dev, const unsigned *gdims,
+                     const unsigned *lo, const unsigned *hi, const double *coeff_host, unsigned flags, void *stream);
+/* same over an explicit list of brick ids (inner / skin / ghost lists for overlap; any adjacency-defined set) */
+int bk_stencil_apply_list(int stencil, const bk_field_t *f, const unsigned *ids_dev, size_t n,
+                          const double *coeff_host, void *stream);
+/* strong/main.cu:85-99 brick_kernel over `nsub` subdomains that share grid/adj: fields[s] per subdomain (host array) */
+int bk_stencil_apply_multi(int stencil, const bk_field_t *fields_dev, unsigned nsub, const unsigned *grid_dev,
+                           const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff_host,
+                           void *stream);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+unsigned long long bk_launch_count(void);
+
+/* ---- ghost exchange --------------------------------------------------------------------------------------------- */
+/* A batch of contiguous copies executed by ONE kernel; replaces cudaCopy<<<links,64>>> (strong/main.cu:76-83) and,
+ * with src pointing into a peer GPU's storage, the MPI_Isend/Irecv pairs of BrickDecomp::exchange
+ * (include/brick-mpi.h:466-495).  bytes must be multiples of 16, pointers 16-B aligned. */
+typedef struct {
+  const void *src;
+  void *dst;
+  size_t bytes;
+} bk_seg_t;
+typedef struct bk_xplan bk_xplan_t;
+int bk_xplan_create(bk_xplan_t **plan, const bk_seg_t *segs_host, int nseg);
+int bk_xplan_destroy(bk_xplan_t *plan);
+size_t bk_xplan_bytes(const bk_xplan_t *plan);
+/* run the plan on `stream`.  wait/signal (optional, may be NULL/0) implement the cross-process handshake:
+ * before copying, spin until every wait_flags[i] >= epoch; after copying (and a system fence) store epoch to every
+ * signal_flags[i] (peer-visible device memory). */
+int bk_xplan_run(bk_xplan_t *plan, void *stream);
+int bk_xplan_run_sync(bk_xplan_t *plan, const uint64_t *const *wait_flags, int nwait, uint64_t *const *signal_flags,
+                      int nsignal, uint64_t epoch, void *stream);
+/* tiny kernels for the handshake on a stream: store `value` to n flags / spin until n flags >= value */
+int bk_flags_signal(uint64_t *const *flags, int n, uint64_t value, void *stream);
+int bk_flags_wait(const uint64_t *const *flags, int n, uint64_t value, void *stream);
+
+/* CUDA IPC so each process (one per GPU) can map its neighbours' brick storage and flags */
+#define BK_IPC_HANDLE_BYTES 64
+int bk_ipc_export(void *dev, unsigned char *handle64);
+int bk_ipc_open(const unsigned char *handle64, void **dev);
+int bk_ipc_close(void *dev);
+int bk_peer_enable(int peer_dev); /* single-process multi-GPU: cudaDeviceEnablePeerAccess */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

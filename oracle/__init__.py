@@ -13,6 +13,10 @@ import ctypes as C
 import os
 import subprocess
 
+# The reference's CPU path is timed with bound OpenMP threads (OMP_PROC_BIND=close); unbound
+# threads scale negatively on virtualised hosts.  Must be in the environment before libgomp initialises.
+os.environ.setdefault("OMP_PROC_BIND", "close")
+
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))

@@ -1,0 +1,218 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle: single sweeps, the weak time loop, full-size
+properties.  Tolerance: 1e-12 relative (BASELINE.json north_star), written in TOL below."""
+import os
+
+import numpy as np
+import pytest
+
+import bricklib_b200 as bk
+import oracle
+from oracle import schedule as S
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+PAD = GZ = 8
+KERNELS = {"brick": bk.KERNEL_BRICK, "auto": bk.KERNEL_AUTO}
+
+
+def rel(a, b):
+    d = np.abs(a - b)
+    return float((d / (np.abs(a) + np.abs(b) + 1e-300)).max())
+
+
+def run_single(stencil, arr, N, coeff, kernel, interleaved=True):
+    """the single/cuda.cpp configuration: init_grid layout, in/out interleaved in one storage (step 1024)"""
+    n = tuple(N) if isinstance(N, tuple) else (N,) * 3
+    nb = tuple((x + 2 * GZ) // 8 for x in n)
+    grid_h, adj = bk.init_grid(nb)
+    info = bk.BrickInfo(adj)
+    grid = bk.DeviceGrid(grid_h)
+    if interleaved:
+        st = info.allocate(1024)
+        b_in, b_out = bk.Brick(info, st, 0), bk.Brick(info, st, 512)
+    else:
+        b_in, b_out = bk.Brick(info, info.allocate(512), 0), bk.Brick(info, info.allocate(512), 0)
+    dev = bk.DeviceBuffer.from_numpy(arr)
+    bk.copyToBrick(tuple(x + 2 * GZ for x in n), (PAD,) * 3, (0,) * 3, dev, grid, b_in)
+    bk.stencil(stencil, grid, b_in, b_out, (1, 1, 1), tuple(x - 1 for x in nb), coeff, kernel)
+    out = bk.DeviceBuffer(arr.nbytes)
+    out.zero()
+    bk.copyFromBrick(n, (PAD,) * 3, (GZ,) * 3, out, grid, b_out)
+    res = out.download(np.float64).reshape(arr.shape)
+    return res, (grid, b_out, info)
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+def test_single_sweep_against_reference_fixture(golden_dir, kernel):
+    z = np.load(os.path.join(golden_dir, "single_sweep.npz"))
+    o = PAD + GZ
+    for name, st in bk.STENCILS.items():
+        res, _ = run_single(st, z["input"], 16, z["coeff"][:7], KERNELS[kernel])
+        assert rel(res[o:-o, o:-o, o:-o], z["out_" + name]) < TOL, name
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+@pytest.mark.parametrize("shape", [(32, 32, 32), (40, 24, 72), (8, 8, 8), (64, 16, 8)])
+def test_single_sweep_against_oracle_port(kernel, shape):
+    P = oracle.port()
+    rng = np.random.default_rng(hash(shape) & 0xffff)
+    arr = rng.random(tuple(x + 2 * (PAD + GZ) for x in shape[::-1]))
+    coeff = rng.random(7)
+    o = PAD + GZ
+    for st in range(5):
+        for inter in (True, False):
+            res, (grid, b_out, _) = run_single(st, arr, shape, coeff, KERNELS[kernel], inter)
+            want = P.sweep_array(st, arr, (o,) * 3, tuple(o + x for x in shape), coeff)
+            assert rel(res[o:-o, o:-o, o:-o], want[o:-o, o:-o, o:-o]) < TOL, (st, inter)
+            # the device comparator (compareBrick, tightened to 1e-12) agrees
+            ok, bad, worst = bk.compareBrick(shape, (PAD,) * 3, (GZ,) * 3, bk.DeviceBuffer.from_numpy(want), grid, b_out,
+                                             TOL)
+            assert ok and bad == 0 and worst < TOL
+
+
+def test_compare_brick_detects_a_single_wrong_cell():
+    rng = np.random.default_rng(5)
+    shape = (16, 16, 16)
+    arr = rng.random(tuple(x + 2 * (PAD + GZ) for x in shape[::-1]))
+    res, (grid, b_out, _) = run_single(1, arr, shape, None, bk.KERNEL_BRICK)
+    res[PAD + GZ + 3, PAD + GZ + 4, PAD + GZ + 5] *= 1.0 + 1e-9
+    ok, bad, worst = bk.compareBrick(shape, (PAD,) * 3, (GZ,) * 3, bk.DeviceBuffer.from_numpy(res), grid, b_out, TOL)
+    assert not ok and bad == 1 and 1e-10 < worst < 1e-8
+
+
+def test_list_launch_equals_box_launch():
+    rng = np.random.default_rng(9)
+    d = bk.BrickDecomp((32, 24, 40), 8)
+    info = d.getBrickInfo()
+    grid = bk.DeviceGrid(d.grid)
+    s_in, s_a, s_b = info.allocate(512), info.allocate(512), info.allocate(512)
+    s_in.from_host(rng.random(d.nbricks * 512))
+    b_in, b_a, b_b = bk.Brick(info, s_in), bk.Brick(info, s_a), bk.Brick(info, s_b)
+    for st in (1, 2, 3, 4):
+        bk.stencil(st, grid, b_in, b_a, kernel=bk.KERNEL_BRICK)
+        ids = np.arange(1, d.nbricks, dtype=np.uint32)
+        bk.stencil_list(st, bk.DeviceBuffer.from_numpy(ids), len(ids), b_in, b_b)
+        assert np.array_equal(s_a.to_host(), s_b.to_host())
+
+
+class CudaBackend:
+    """oracle.schedule backend protocol, implemented with the product (one WeakDomain per emulated rank)."""
+
+    def __init__(self, kernel=bk.KERNEL_AUTO, overlap=False):
+        self.kernel, self.overlap = kernel, overlap
+
+    def run(self, stencil, dom, cart, periods, fields):
+        """single rank, periodic self-exchange, the product's own period() schedule (optionally overlapped)"""
+        assert tuple(cart) == (1, 1, 1)
+        d = bk.WeakDomain(dom, stencil, cart, (0, 0, 0), 0, self.kernel)
+        d.connect()
+        d.load_interior(fields[0])
+        if self.overlap:
+            d.enable_overlap()
+        for _ in range(periods):
+            d.period()
+        bk.device_sync()
+        return [d.read_interior(0)]
+
+    def run_lockstep(self, stencil, dom, cart, periods, fields):
+        coos = S.cart_coords(cart)
+        doms = [bk.WeakDomain(dom, stencil, cart, coo, r, self.kernel) for r, coo in enumerate(coos)]
+        ptrs = {r: d.storage[0].dat.ptr for r, d in enumerate(doms)}
+        for d, f in zip(doms, fields):
+            d.connect(ptrs)
+            d.load_interior(f)
+        it = doms[0].st_iter
+        for _ in range(periods):
+            for d in doms:
+                d.view.exchange()
+            bk.device_sync()
+            for s in range(it):
+                for d in doms:
+                    d._sweep(s % 2, 1 - s % 2, (0, 0, 0), d.grid.dims, None)
+            bk.device_sync()
+        return [d.read_interior(0) for d in doms]
+
+
+@pytest.mark.parametrize("kernel", list(KERNELS))
+@pytest.mark.parametrize("overlap", [False, True])
+def test_weak_loop_single_rank_against_reference_fixture(golden_dir, kernel, overlap):
+    z = np.load(os.path.join(golden_dir, "weak_steps.npz"))
+    dom, cart = (24, 16, 32), (1, 1, 1)
+    for name, st in bk.STENCILS.items():
+        if st == 0:
+            continue
+        res = CudaBackend(KERNELS[kernel], overlap).run(st, dom, cart, 2, [z["in_c111"]])
+        assert rel(res[0], z["out_c111_" + name]) < TOL, name
+
+
+def test_weak_loop_two_ranks_on_one_gpu_against_reference_fixture(golden_dir):
+    z = np.load(os.path.join(golden_dir, "weak_steps.npz"))
+    dom, cart = (24, 16, 32), (2, 1, 1)
+    for name, st in bk.STENCILS.items():
+        if st == 0:
+            continue
+        res = CudaBackend().run_lockstep(st, dom, cart, 2, S.split_global(z["in_c211"], cart, dom))
+        assert rel(S.join_global(res, cart, dom), z["out_c211_" + name]) < TOL, name
+
+
+@pytest.mark.parametrize("cart,dom", [((2, 2, 2), (16, 24, 16)), ((3, 1, 2), (16, 16, 16))])
+def test_weak_loop_many_ranks_against_oracle_port(cart, dom):
+    rng = np.random.default_rng(21)
+    glob = rng.random((cart[0] * dom[2], cart[1] * dom[1], cart[2] * dom[0]))
+    fields = S.split_global(glob, cart, dom)
+    for st in (1, 3, 4):
+        res = CudaBackend().run_lockstep(st, dom, cart, 1, fields)
+        want = S.periodic_steps(st, glob, oracle.ST_ITER[st])
+        assert rel(S.join_global(res, cart, dom), want) < TOL, st
+
+
+# ---- full size (BASELINE.json: 512^3 per GPU): size-independent properties ---------------------------------------
+@pytest.fixture(scope="module")
+def big():
+    d = bk.WeakDomain((512, 512, 512), bk.STENCILS["mpi7pt"])
+    d.connect()
+    return d
+
+
+@pytest.mark.parametrize("name", ["mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt"])
+def test_full_size_constant_field_is_a_fixed_point(big, name):
+    """every MPI stencil's coefficients sum to 1 (fake.h:11-33): a constant field stays constant under the whole
+    exchange + ST_ITER-sweep period, ghost bricks included"""
+    big.stencil = bk.STENCILS[name]
+    big.st_iter = bk.load().bk_stencil_st_iter(big.stencil)
+    n = big.decomp.nbricks * 512
+    host = np.full(n, 3.25)
+    host[:512] = 0.0          # null brick
+    big.storage[0].from_host(host)
+    big.storage[1].dat.zero()
+    big.period()
+    bk.device_sync()
+    out = big.storage[0].to_host()
+    lo, hi = big.decomp.sep_pos[0] * 0 + 512, big.decomp.sep_pos[1] * 512   # inner + skin bricks = the interior
+    assert np.abs(out[lo:hi] - 3.25).max() < 3.25 * TOL
+
+
+def test_full_size_matches_oracle_on_a_sampled_slab(big):
+    """512^3 single sweep: compare a 16-cell-thick slab through the middle with the C port's array form"""
+    P = oracle.port()
+    rng = np.random.default_rng(77)
+    for name in ("mpi7pt", "mpi25pt", "mpi125pt"):
+        st = bk.STENCILS[name]
+        big.stencil = st
+        host = rng.random(big.decomp.nbricks * 512)
+        host[:512] = 0.0
+        big.storage[0].from_host(host)
+        big._sweep(0, 1, (1, 1, 1), tuple(x - 1 for x in big.grid.dims), None)
+        bk.device_sync()
+        out = big.storage[1].to_host().reshape(-1, 8, 8, 8)
+        inp = host.reshape(-1, 8, 8, 8)
+        g = big.decomp.grid
+        # assemble bricks k in [30,36), j in [10,16), all i around the slab into arrays
+        ks, js = slice(29, 37), slice(9, 17)
+        sub = g[ks, js, :]
+        def assemble(src):
+            a = src[sub]                         # [bk][bj][bi][k][j][i]
+            return np.ascontiguousarray(a.transpose(0, 3, 1, 4, 2, 5).reshape(sub.shape[0] * 8, sub.shape[1] * 8, sub.shape[2] * 8))
+        a_in, a_out = assemble(inp), assemble(out)
+        want = P.sweep_array(st, a_in, (8, 8, 8), (a_in.shape[2] - 8, a_in.shape[1] - 8, a_in.shape[0] - 8))
+        assert rel(a_out[8:-8, 8:-8, 8:-8], want[8:-8, 8:-8, 8:-8]) < TOL, name
