@@ -1,9 +1,396 @@
-// bk_stencil_tiled.cu -- placeholder until the marching kernel lands: report "unsupported" so the dispatcher in
-// bk_stencil.cu falls through to the per-brick family (a CUDA kernel, never a CPU path).
+// bk_stencil_tiled.cu -- the fast path for box-shaped launches of the STAR stencils (7/13/25-point).
+//
+// Replaces the body codegen/vecscatter generates for brick("mpi*pt.py","CUDA",(8,8,8),(4,8),b) (one warp per brick,
+// 8-byte loads, dev_shl shuffles; launched by brick_kernel, weak/main.cu:35-43) with a TMA-staged marching kernel:
+//
+//   * a CTA owns a tile of TI x TJ bricks in (i,j) and marches along k through KL brick layers (a "segment");
+//   * one producer warp streams the column into a ring of D shared-memory stages, G planes per stage, with 1-D bulk
+//     async copies (cp.async.bulk ... mbarrier::complete_tx): a brick's G planes are G*512 contiguous bytes, so one
+//     copy per own brick and per i-neighbour brick, and G copies of R rows (R*64 contiguous bytes) per j-neighbour;
+//     full/empty mbarriers, no __syncthreads in the steady state;
+//   * consumer threads own an (x-pair) x (YT rows) patch of one brick and keep 2R+1 partial outputs per point in
+//     registers: plane t is read ONCE from shared memory and scattered along k into the outputs t-R..t+R, the i/j
+//     neighbours of plane t are read from the same stage (128-bit LDS, bank-conflict free thanks to a 64-byte skew of
+//     odd brick columns), finished planes go straight to global memory with 128-bit stores.
+// HBM sees every input byte once (halo re-reads hit L2 because neighbouring tiles run concurrently) and every output
+// byte once: 16 B per point, the roofline SURVEY.md section 8(d) counts.
+//
+// Brick ids come from the dense `grid` array (BrickDecomp::operator[] / init_grid order); positions outside the grid
+// read brick 0, the null brick every out-of-domain adjacency entry points to (include/brick-mpi.h:275-277).  The
+// per-brick family in bk_stencil.cu remains the general path for arbitrary adjacency.
+//
+// Summation order per output point (fixed): k-minus taps d=R..1, centre, i taps d=1..R (+d then -d), j taps d=1..R
+// (+d then -d), k-plus taps d=1..R.  Parity with the reference is to 1e-12 relative, not bitwise.
 #include "bk_common.h"
-namespace bk {
-int launch_tiled(int, const bk_field_t &, const unsigned *, const unsigned *, const unsigned *, const unsigned *,
-                 const double *, cudaStream_t) {
-  return BK_EUNSUPPORTED;
+#include <cstdint>
+
+namespace {
+
+using bk::StarCoef;
+
+struct TiledArgs {
+  const double *in;
+  double *out;
+  unsigned long long in_step, out_step;  // elements between consecutive bricks
+  const unsigned *grid;
+  int gx, gy, gz;  // grid extents in bricks
+  int lo[3], hi[3];
+  int ntx;  // tiles along i
+  int kl;   // brick layers per k segment
+};
+
+// ---- PTX helpers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      " .reg .pred p;\n"
+      " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      " selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+// ---- compile-time geometry --------------------------------------------------------------------------------------
+template <int R_, int YT_, int TI_, int TJ_, int G_, int D_>
+struct Cfg {
+  static constexpr int R = R_, YT = YT_, TI = TI_, TJ = TJ_, G = G_, D = D_;
+  static constexpr int W = 2 * R + 1;                 // partial outputs in flight per point
+  static constexpr int RUP = ((R + G - 1) / G) * G;   // halo planes streamed before/after a segment (multiple of G)
+  static constexpr int SW = TI + 2;                   // slot columns: i-halo, TI own, i-halo
+  static constexpr int SH = TJ + 1;                   // slot rows: row 0 = shared j-halo slots, then TJ own rows
+  static constexpr int SLOTP = G * 512 + 64;          // slot pitch; odd columns are skewed by 64 B (bank spreading)
+  static constexpr int STAGE = ((SH * SW * SLOTP + 64 + 127) / 128) * 128;
+  static constexpr int NCONS = TI * TJ * 32 / YT;     // consumer threads: 4 x-pairs * 8/YT row groups per brick
+  static constexpr int NCW = NCONS / 32;
+  static constexpr int NT = NCONS + 32;               // + one producer warp
+  static constexpr int NCOPY = TI * TJ + 2 * TJ + 2 * TI;  // copy jobs per stage (j-halo jobs issue G copies)
+  static constexpr int JOBS = (NCOPY + 31) / 32;
+  static constexpr size_t SMEM = (size_t) D * STAGE + 2 * D * 8 + 128;
+  static_assert(8 % G == 0 && 8 % YT == 0 && TI % 2 == 0 && 2 * R <= 8, "geometry");
+  __host__ __device__ static constexpr int slotoff(int bi, int bj) { return (bj * SW + bi) * SLOTP + (bi & 1) * 64; }
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_star(const __grid_constant__ TiledArgs a, const __grid_constant__ StarCoef cf) {
+  constexpr int R = C::R, YT = C::YT, TI = C::TI, TJ = C::TJ, G = C::G, D = C::D, W = C::W, RUP = C::RUP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // dynamic shared memory is only guaranteed 16-B aligned: align the ring to 128 B by hand
+  unsigned char *ring = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127);
+  const uint32_t ring_u32 = smem_u32(ring);
+  const uint32_t bar_full = ring_u32 + D * C::STAGE;
+  const uint32_t bar_empty = bar_full + D * 8;
+
+  const int tid = threadIdx.x;
+  const int tx = blockIdx.x % a.ntx, ty = blockIdx.x / a.ntx;
+  const int i0 = a.lo[0] + tx * TI, j0 = a.lo[1] + ty * TJ;
+  const int kb0 = a.lo[2] + blockIdx.y * a.kl;
+  const int nl = min(a.kl, a.hi[2] - kb0);  // brick layers in this segment
+  const int P = nl * 8 + 2 * RUP;            // planes streamed; plane t is absolute plane kb0*8 - RUP + t
+  const int NS = P / G;
+
+  if (tid == 0) {
+    for (int s = 0; s < D; ++s) {
+      mbar_init(bar_full + 8 * s, 32);        // every producer lane arrives once per fill
+      mbar_init(bar_empty + 8 * s, C::NCW);   // one arrival per consumer warp per drain
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= C::NCONS) {
+    // ================================================ producer warp ============================================
+    const int lane = tid - C::NCONS;
+    int sbi[C::JOBS], sbj[C::JOBS], kind[C::JOBS];  // slot coordinates; kind 0 none, 1 whole slot, 2 low rows, 3 high rows
+    uint32_t dsto[C::JOBS];
+    unsigned idn[C::JOBS];
+#pragma unroll
+    for (int q = 0; q < C::JOBS; ++q) {
+      int job = lane + 32 * q;
+      kind[q] = 0;
+      sbi[q] = sbj[q] = 0;
+      if (job < TI * TJ) {
+        kind[q] = 1, sbi[q] = 1 + job % TI, sbj[q] = 1 + job / TI;
+      } else if ((job -= TI * TJ) < 2 * TJ) {
+        kind[q] = 1, sbi[q] = (job & 1) ? TI + 1 : 0, sbj[q] = 1 + (job >> 1);
+      } else if ((job -= 2 * TJ) < 2 * TI) {
+        kind[q] = 2 + (job & 1), sbi[q] = 1 + (job >> 1), sbj[q] = (job & 1) ? TJ + 1 : 0;
+      }
+      // both j-halo kinds land in slot row 0: rows [8-R,8) from below (kind 2), rows [0,R) from above (kind 3)
+      dsto[q] = C::slotoff(sbi[q], kind[q] >= 2 ? 0 : sbj[q]) + (kind[q] == 2 ? (8 - R) * 64 : 0);
+    }
+    auto brick_id = [&](int q, int kb) -> unsigned {
+      const int gi = i0 + sbi[q] - 1, gj = j0 + sbj[q] - 1;
+      if (kind[q] == 0 || gi < 0 || gi >= a.gx || gj < 0 || gj >= a.gy || kb < 0 || kb >= a.gz) return 0u;
+      return __ldg(a.grid + ((size_t) kb * a.gy + gj) * a.gx + gi);
+    };
+    const int z_first = kb0 * 8 - RUP;  // may be negative (only when kb0 == 0)
+    int kb = (z_first >= 0) ? z_first / 8 : -((7 - z_first) / 8);
+    int pz = z_first - kb * 8;
+#pragma unroll
+    for (int q = 0; q < C::JOBS; ++q) idn[q] = brick_id(q, kb);
+    unsigned idc[C::JOBS];
+    int st = 0;
+    uint32_t ph = 0;
+    bool fresh = true;  // idn holds the ids of layer kb
+    for (int n = 0; n < NS; ++n) {
+      if (fresh) {
+#pragma unroll
+        for (int q = 0; q < C::JOBS; ++q) idc[q] = idn[q], idn[q] = brick_id(q, kb + 1);  // prefetch next layer
+        fresh = false;
+      }
+      if (n >= D) mbar_wait(bar_empty + 8 * st, ph ^ 1);
+      uint32_t bytes = 0;
+#pragma unroll
+      for (int q = 0; q < C::JOBS; ++q) bytes += kind[q] == 0 ? 0 : kind[q] == 1 ? G * 512 : G * R * 64;
+      const uint32_t fb = bar_full + 8 * st;
+      mbar_expect_tx(fb, bytes);
+      const uint32_t sb = ring_u32 + st * C::STAGE;
+#pragma unroll
+      for (int q = 0; q < C::JOBS; ++q) {
+        const double *src = a.in + (size_t) idc[q] * a.in_step + pz * 64;
+        if (kind[q] == 1) {
+          bulk_g2s(sb + dsto[q], src, G * 512, fb);
+        } else if (kind[q] >= 2) {
+          src += (kind[q] == 2 ? (8 - R) * 8 : 0);
+#pragma unroll
+          for (int g = 0; g < G; ++g) bulk_g2s(sb + dsto[q] + g * 512, src + g * 64, R * 64, fb);
+        }
+      }
+      pz += G;
+      if (pz == 8) pz = 0, ++kb, fresh = true;
+      if (++st == D) st = 0, ph ^= 1;
+    }
+    return;
+  }
+
+  // ================================================== consumers ================================================
+  const int c = tid & 3;                 // x-pair inside the brick row: cells x0 = 2c, 2c+1
+  const int e = (tid >> 2) & 1;          // brick parity inside a pair of i-adjacent bricks
+  int rest = tid >> 3;
+  const int y0 = (rest % (8 / YT)) * YT;  // first of my YT rows
+  rest /= (8 / YT);
+  const int bi = (rest % (TI / 2)) * 2 + e, bj = rest / (TI / 2);
+  const int own_slot = C::slotoff(bi + 1, bj + 1);
+  const int own_off = own_slot + y0 * 64 + c * 16;
+  // byte offsets (from the stage base, plane 0) of the 2R j-halo rows: below rows y0-R..y0-1, above rows y0+YT..
+  int joff[2 * R];
+#pragma unroll
+  for (int h = 0; h < 2 * R; ++h) {
+    const int ya = (h < R) ? y0 - R + h : y0 + YT + (h - R);
+    int base;
+    if (ya < 0)
+      base = C::slotoff(bi + 1, bj) + (8 + ya) * 64;  // bj == 0 -> slot row 0 = the shared j-halo slot
+    else if (ya >= 8)
+      base = C::slotoff(bi + 1, (bj == TJ - 1) ? 0 : bj + 2) + (ya - 8) * 64;
+    else
+      base = own_slot + ya * 64;
+    joff[h] = base + c * 16;
+  }
+  // i-halo offsets relative to the address of my x-pair in a row
+  const int dl = C::slotoff(bi, bj + 1) - own_slot, dr = C::slotoff(bi + 2, bj + 1) - own_slot;
+  constexpr int NI = (R % 2 == 0) ? R / 2 : R;  // loads per side: 16-B chunks for even R, single cells for odd R
+  int ioffL[NI], ioffR[NI];
+#pragma unroll
+  for (int m = 1; m <= NI; ++m) {
+    if (R % 2 == 0) {
+      ioffL[m - 1] = -16 * m + ((c - m < 0) ? dl + 64 : 0);
+      ioffR[m - 1] = 16 * m + ((c + m > 3) ? dr - 64 : 0);
+    } else {  // cell x0-m / x0+1+m
+      ioffL[m - 1] = -8 * m + ((2 * c - m < 0) ? dl + 64 : 0);
+      ioffR[m - 1] = 8 * (1 + m) + ((2 * c + 1 + m > 7) ? dr - 64 : 0);
+    }
+  }
+
+  const bool mine = (i0 + bi < a.hi[0]) && (j0 + bj < a.hi[1]);  // bricks of a partial tile are staged, not stored
+  const unsigned *gcol = a.grid + ((size_t) kb0 * a.gy + (j0 + bj)) * a.gx + (i0 + bi);
+  const size_t glayer = (size_t) a.gy * a.gx;
+  unsigned id_next = mine ? __ldg(gcol) : 0u;
+  double *outp = a.out;
+
+  double2 acc[W][YT];
+#pragma unroll
+  for (int w = 0; w < W; ++w)
+#pragma unroll
+    for (int r = 0; r < YT; ++r) acc[w][r] = make_double2(0.0, 0.0);
+
+  int st = 0, pl = 0;
+  uint32_t ph = 0;
+  int orel = -R - RUP;  // output plane finished by the current iteration, relative to the segment start
+  const int nout = nl * 8;
+
+#pragma unroll 1
+  for (int tb = 0; tb < P; tb += W) {
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+      if (tb + u < P) {
+        if (pl == 0) mbar_wait(bar_full + 8 * st, ph);
+        const unsigned char *pb = ring + st * C::STAGE + pl * 512;
+        double2 v[YT];
+#pragma unroll
+        for (int r = 0; r < YT; ++r) v[r] = *reinterpret_cast<const double2 *>(pb + own_off + r * 64);
+
+        // ---- k taps, first half: this plane is the +d neighbour of outputs t-d ------------------------------------
+        const int sF = ((u - R) % W + W) % W;  // slot of output t-R: finished by this plane
+#pragma unroll
+        for (int r = 0; r < YT; ++r) {
+          acc[sF][r].x = fma(cf.cp[2][R - 1], v[r].x, acc[sF][r].x);
+          acc[sF][r].y = fma(cf.cp[2][R - 1], v[r].y, acc[sF][r].y);
+        }
+        if (orel >= 0 && orel < nout) {
+          const int oz = orel & 7;
+          if (oz == 0) {
+            outp = a.out + (size_t) id_next * a.out_step + y0 * 8 + c * 2;
+            if (mine && (orel >> 3) + 1 < nl) id_next = __ldg(gcol + ((orel >> 3) + 1) * glayer);
+          }
+          if (mine) {
+#pragma unroll
+            for (int r = 0; r < YT; ++r) *reinterpret_cast<double2 *>(outp + oz * 64 + r * 8) = acc[sF][r];
+          }
+        }
+#pragma unroll
+        for (int d = R - 1; d >= 1; --d) {
+          const int s = ((u - d) % W + W) % W;
+#pragma unroll
+          for (int r = 0; r < YT; ++r) {
+            acc[s][r].x = fma(cf.cp[2][d - 1], v[r].x, acc[s][r].x);
+            acc[s][r].y = fma(cf.cp[2][d - 1], v[r].y, acc[s][r].y);
+          }
+        }
+        // ---- centre + in-plane taps of output t ------------------------------------------------------------------
+        const int s0 = u % W;
+        double2 rows[YT + 2 * R];
+#pragma unroll
+        for (int h = 0; h < R; ++h) rows[h] = *reinterpret_cast<const double2 *>(pb + joff[h]);
+#pragma unroll
+        for (int r = 0; r < YT; ++r) rows[R + r] = v[r];
+#pragma unroll
+        for (int h = 0; h < R; ++h) rows[R + YT + h] = *reinterpret_cast<const double2 *>(pb + joff[R + h]);
+#pragma unroll
+        for (int r = 0; r < YT; ++r) {
+          double line[2 * R + 2];  // cells x0-R .. x0+1+R of row r
+          line[R] = v[r].x, line[R + 1] = v[r].y;
+          const unsigned char *pr = pb + own_off + r * 64;
+          if constexpr (R % 2 == 0) {
+#pragma unroll
+            for (int m = 1; m <= R / 2; ++m) {
+              const double2 lft = *reinterpret_cast<const double2 *>(pr + ioffL[m - 1]);
+              const double2 rgt = *reinterpret_cast<const double2 *>(pr + ioffR[m - 1]);
+              line[R - 2 * m] = lft.x, line[R - 2 * m + 1] = lft.y;
+              line[R + 2 * m] = rgt.x, line[R + 2 * m + 1] = rgt.y;
+            }
+          } else {
+#pragma unroll
+            for (int m = 1; m <= R; ++m) {
+              line[R - m] = *reinterpret_cast<const double *>(pr + ioffL[m - 1]);
+              line[R + 1 + m] = *reinterpret_cast<const double *>(pr + ioffR[m - 1]);
+            }
+          }
+          double ax = fma(cf.c0, v[r].x, acc[s0][r].x), ay = fma(cf.c0, v[r].y, acc[s0][r].y);
+#pragma unroll
+          for (int d = 1; d <= R; ++d) {
+            ax = fma(cf.cp[0][d - 1], line[R + d], ax);
+            ay = fma(cf.cp[0][d - 1], line[R + 1 + d], ay);
+            ax = fma(cf.cm[0][d - 1], line[R - d], ax);
+            ay = fma(cf.cm[0][d - 1], line[R + 1 - d], ay);
+          }
+#pragma unroll
+          for (int d = 1; d <= R; ++d) {
+            ax = fma(cf.cp[1][d - 1], rows[R + r + d].x, ax);
+            ay = fma(cf.cp[1][d - 1], rows[R + r + d].y, ay);
+            ax = fma(cf.cm[1][d - 1], rows[R + r - d].x, ax);
+            ay = fma(cf.cm[1][d - 1], rows[R + r - d].y, ay);
+          }
+          acc[s0][r].x = ax, acc[s0][r].y = ay;
+        }
+        // ---- k taps, second half: this plane is the -d neighbour of outputs t+d -----------------------------------
+#pragma unroll
+        for (int d = 1; d <= R - 1; ++d) {
+          const int s = (u + d) % W;
+#pragma unroll
+          for (int r = 0; r < YT; ++r) {
+            acc[s][r].x = fma(cf.cm[2][d - 1], v[r].x, acc[s][r].x);
+            acc[s][r].y = fma(cf.cm[2][d - 1], v[r].y, acc[s][r].y);
+          }
+        }
+        const int sN = (u + R) % W;  // slot of output t+R: first contribution, (re)initialises the slot
+#pragma unroll
+        for (int r = 0; r < YT; ++r) {
+          acc[sN][r].x = cf.cm[2][R - 1] * v[r].x;
+          acc[sN][r].y = cf.cm[2][R - 1] * v[r].y;
+        }
+
+        ++orel;
+        if (++pl == G) {
+          pl = 0;
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(bar_empty + 8 * st);
+          if (++st == D) st = 0, ph ^= 1;
+        }
+      }
+    }
+  }
+}
+
+template <class C>
+int launch_cfg(const TiledArgs &a0, const StarCoef &cf, cudaStream_t s) {
+  BK_CUDA(cudaFuncSetAttribute(k_star<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
+  TiledArgs a = a0;
+  const int nx = a.hi[0] - a.lo[0], ny = a.hi[1] - a.lo[1], nz = a.hi[2] - a.lo[2];
+  if (nx <= 0 || ny <= 0 || nz <= 0) return BK_OK;
+  a.ntx = (nx + C::TI - 1) / C::TI;
+  const int nty = (ny + C::TJ - 1) / C::TJ;
+  // k segments: long enough to amortise the 2R halo planes, short enough to give every SM several CTAs
+  const int nseg = (nz + 15) / 16;
+  a.kl = (nz + nseg - 1) / nseg;
+  const int segs = (nz + a.kl - 1) / a.kl;
+  dim3 grid((unsigned) (a.ntx * nty), (unsigned) segs, 1);
+  k_star<C><<<grid, C::NT, C::SMEM, s>>>(a, cf);
+  BK_LAUNCHED();
+  return BK_OK;
+}
+
+}  // namespace
+
+namespace bk {
+
+int launch_tiled(int stencil, const bk_field_t &f, const unsigned *grid, const unsigned *gdims, const unsigned *lo,
+                 const unsigned *hi, const double *coeff, cudaStream_t s) {
+  if (stencil == BK_ST_MPI125PT) return BK_EUNSUPPORTED;  // cube stencil: per-brick family for now
+  StarCoef sc;
+  const int r = star_coef_for(stencil, coeff, &sc);
+  if (r < 0) return BK_EINVAL;
+  if (((size_t) f.in | (size_t) f.out) & 15 || (f.in_step & 1) || (f.out_step & 1)) return BK_EUNSUPPORTED;
+  TiledArgs a;
+  a.in = f.in, a.out = f.out, a.in_step = f.in_step, a.out_step = f.out_step, a.grid = grid;
+  a.gx = (int) gdims[0], a.gy = (int) gdims[1], a.gz = (int) gdims[2];
+  for (int d = 0; d < 3; ++d) a.lo[d] = (int) lo[d], a.hi[d] = (int) hi[d];
+  a.ntx = a.kl = 0;
+  if (r == 1) return launch_cfg<Cfg<1, 4, 8, 2, 2, 3>>(a, sc, s);
+  if (r == 2) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3>>(a, sc, s);
+  return launch_cfg<Cfg<4, 4, 4, 4, 2, 3>>(a, sc, s);
+}
+
 }  // namespace bk
