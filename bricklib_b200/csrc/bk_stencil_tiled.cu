@@ -23,6 +23,7 @@
 // (+d then -d), k-plus taps d=1..R.  Parity with the reference is to 1e-12 relative, not bitwise.
 #include "bk_common.h"
 #include <cstdint>
+#include <cstdlib>
 
 namespace {
 
@@ -74,27 +75,31 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 // ---- compile-time geometry --------------------------------------------------------------------------------------
-template <int R_, int YT_, int TI_, int TJ_, int G_, int D_>
+template <int R_, int YT_, int TI_, int TJ_, int G_, int D_, int MAXREG_ = 255, int NPW_ = 1>
 struct Cfg {
   static constexpr int R = R_, YT = YT_, TI = TI_, TJ = TJ_, G = G_, D = D_;
   static constexpr int W = 2 * R + 1;                 // partial outputs in flight per point
   static constexpr int RUP = ((R + G - 1) / G) * G;   // halo planes streamed before/after a segment (multiple of G)
   static constexpr int SW = TI + 2;                   // slot columns: i-halo, TI own, i-halo
   static constexpr int SH = TJ + 1;                   // slot rows: row 0 = shared j-halo slots, then TJ own rows
-  static constexpr int SLOTP = G * 512 + 64;          // slot pitch; odd columns are skewed by 64 B (bank spreading)
-  static constexpr int STAGE = ((SH * SW * SLOTP + 64 + 127) / 128) * 128;
+  static constexpr int SLOTP = G * 512 + 64;          // slot pitch = 64 mod 128: i-adjacent bricks land in opposite bank halves
+  static constexpr int STAGE = ((SH * SW * SLOTP + 127) / 128) * 128;
   static constexpr int NCONS = TI * TJ * 32 / YT;     // consumer threads: 4 x-pairs * 8/YT row groups per brick
   static constexpr int NCW = NCONS / 32;
-  static constexpr int NT = NCONS + 32;               // + one producer warp
+  static constexpr int NPW = NPW_;                    // producer warps (bulk-copy issue is instruction bound)
+  static constexpr int NT = NCONS + 32 * NPW;
   static constexpr int NCOPY = TI * TJ + 2 * TJ + 2 * TI;  // copy jobs per stage (j-halo jobs issue G copies)
-  static constexpr int JOBS = (NCOPY + 31) / 32;
+  static constexpr int JOBS = (NCOPY + 32 * NPW - 1) / (32 * NPW);
+  static constexpr int MAXREG = MAXREG_;              // register cap (chosen so that the intended CTAs/SM fit)
   static constexpr size_t SMEM = (size_t) D * STAGE + 2 * D * 8 + 128;
   static_assert(8 % G == 0 && 8 % YT == 0 && TI % 2 == 0 && 2 * R <= 8, "geometry");
-  __host__ __device__ static constexpr int slotoff(int bi, int bj) { return (bj * SW + bi) * SLOTP + (bi & 1) * 64; }
+  // SW is even, so the bank half of a slot depends on its column only: a quarter warp (4 x-pairs of 2 i-adjacent
+  // bricks) reads 8 distinct 16-B bank groups
+  __host__ __device__ static constexpr int slotoff(int bi, int bj) { return (bj * SW + bi) * SLOTP; }
 };
 
 template <class C>
-__global__ void __launch_bounds__(C::NT) k_star(const __grid_constant__ TiledArgs a, const __grid_constant__ StarCoef cf) {
+__device__ __forceinline__ void star_body(const TiledArgs &a, const StarCoef &cf) {
   constexpr int R = C::R, YT = C::YT, TI = C::TI, TJ = C::TJ, G = C::G, D = C::D, W = C::W, RUP = C::RUP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // dynamic shared memory is only guaranteed 16-B aligned: align the ring to 128 B by hand
@@ -113,7 +118,7 @@ __global__ void __launch_bounds__(C::NT) k_star(const __grid_constant__ TiledArg
 
   if (tid == 0) {
     for (int s = 0; s < D; ++s) {
-      mbar_init(bar_full + 8 * s, 32);        // every producer lane arrives once per fill
+      mbar_init(bar_full + 8 * s, 32 * C::NPW);  // every producer lane arrives once per fill
       mbar_init(bar_empty + 8 * s, C::NCW);   // one arrival per consumer warp per drain
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -122,13 +127,14 @@ __global__ void __launch_bounds__(C::NT) k_star(const __grid_constant__ TiledArg
 
   if (tid >= C::NCONS) {
     // ================================================ producer warp ============================================
-    const int lane = tid - C::NCONS;
+    // jobs are dealt round-robin over the producer warps, then over lanes
+    const int pw = (tid - C::NCONS) >> 5, lane = tid & 31;
     int sbi[C::JOBS], sbj[C::JOBS], kind[C::JOBS];  // slot coordinates; kind 0 none, 1 whole slot, 2 low rows, 3 high rows
     uint32_t dsto[C::JOBS];
     unsigned idn[C::JOBS];
 #pragma unroll
     for (int q = 0; q < C::JOBS; ++q) {
-      int job = lane + 32 * q;
+      int job = pw + C::NPW * (lane + 32 * q);
       kind[q] = 0;
       sbi[q] = sbj[q] = 0;
       if (job < TI * TJ) {
@@ -355,19 +361,58 @@ __global__ void __launch_bounds__(C::NT) k_star(const __grid_constant__ TiledArg
 }
 
 template <class C>
+__global__ void __launch_bounds__(C::NT) k_star(const __grid_constant__ TiledArgs a, const __grid_constant__ StarCoef cf) {
+  star_body<C>(a, cf);
+}
+// same body under an explicit register cap (so that two CTAs fit one SM)
+template <class C>
+__global__ void __launch_bounds__(C::NT) __maxnreg__(C::MAXREG) k_star_capped(const __grid_constant__ TiledArgs a,
+                                                                               const __grid_constant__ StarCoef cf) {
+  star_body<C>(a, cf);
+}
+
+template <class C>
 int launch_cfg(const TiledArgs &a0, const StarCoef &cf, cudaStream_t s) {
-  BK_CUDA(cudaFuncSetAttribute(k_star<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
+  void (*kern)(const TiledArgs, const StarCoef);
+  if constexpr (C::MAXREG < 255) kern = k_star_capped<C>; else kern = k_star<C>;
+  BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
+  if (getenv("BK_DEBUG")) {
+    cudaFuncAttributes fa;
+    int nb = -1;
+    cudaFuncGetAttributes(&fa, kern);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::NT, C::SMEM);
+    fprintf(stderr, "[bk] k_star R=%d YT=%d tile=%dx%d G=%d D=%d: %d thr, %d regs, %zu B smem, %zu B local, %d CTA/SM\n", C::R,
+            C::YT, C::TI, C::TJ, C::G, C::D, C::NT, fa.numRegs, C::SMEM, fa.localSizeBytes, nb);
+  }
   TiledArgs a = a0;
   const int nx = a.hi[0] - a.lo[0], ny = a.hi[1] - a.lo[1], nz = a.hi[2] - a.lo[2];
   if (nx <= 0 || ny <= 0 || nz <= 0) return BK_OK;
   a.ntx = (nx + C::TI - 1) / C::TI;
   const int nty = (ny + C::TJ - 1) / C::TJ;
-  // k segments: long enough to amortise the 2R halo planes, short enough to give every SM several CTAs
-  const int nseg = (nz + 15) / 16;
-  a.kl = (nz + nseg - 1) / nseg;
+  // k segments: every CTA streams kl*8 + 2*RUP planes and the launch takes ceil(CTAs / resident slots) rounds, so pick
+  // the segment count that minimises rounds * planes (long segments amortise the halo planes, short ones fill the
+  // last round)
+  static int slots = 0;
+  if (!slots) {
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NT, C::SMEM);
+    slots = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  int best_seg = 1;
+  long best_cost = -1;
+  for (int nseg = 1; nseg <= nz; ++nseg) {
+    const int kl = (nz + nseg - 1) / nseg;
+    const long ctas = (long) a.ntx * nty * ((nz + kl - 1) / kl);
+    const long cost = ((ctas + slots - 1) / slots) * (kl * 8 + 2 * C::RUP + 24);  // +24: pipeline fill per CTA
+    if (best_cost < 0 || cost < best_cost) best_cost = cost, best_seg = nseg;
+  }
+  a.kl = (nz + best_seg - 1) / best_seg;
+  if (const char *e = getenv("BK_STAR_KL")) a.kl = atoi(e) > 0 ? atoi(e) : a.kl;  // developer knob
   const int segs = (nz + a.kl - 1) / a.kl;
   dim3 grid((unsigned) (a.ntx * nty), (unsigned) segs, 1);
-  k_star<C><<<grid, C::NT, C::SMEM, s>>>(a, cf);
+  kern<<<grid, C::NT, C::SMEM, s>>>(a, cf);
   BK_LAUNCHED();
   return BK_OK;
 }
@@ -388,9 +433,43 @@ int launch_tiled(int stencil, const bk_field_t &f, const unsigned *grid, const u
   a.gx = (int) gdims[0], a.gy = (int) gdims[1], a.gz = (int) gdims[2];
   for (int d = 0; d < 3; ++d) a.lo[d] = (int) lo[d], a.hi[d] = (int) hi[d];
   a.ntx = a.kl = 0;
-  if (r == 1) return launch_cfg<Cfg<1, 4, 8, 2, 2, 3>>(a, sc, s);
-  if (r == 2) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3>>(a, sc, s);
-  return launch_cfg<Cfg<4, 4, 4, 4, 2, 3>>(a, sc, s);
+  int v = 0;
+  if (const char *e = getenv("BK_STAR_VARIANT")) v = atoi(e);  // developer knob: alternative geometries
+  if (r == 1) {
+    if (v == 1) return launch_cfg<Cfg<1, 4, 4, 4, 2, 3>>(a, sc, s);
+    if (v == 2) return launch_cfg<Cfg<1, 2, 8, 2, 2, 3>>(a, sc, s);
+    if (v == 3) return launch_cfg<Cfg<1, 4, 8, 4, 2, 3>>(a, sc, s);
+    if (v == 4) return launch_cfg<Cfg<1, 4, 8, 2, 1, 4>>(a, sc, s);
+    if (v == 5) return launch_cfg<Cfg<1, 4, 6, 4, 2, 5>>(a, sc, s);
+    if (v == 6) return launch_cfg<Cfg<1, 4, 4, 4, 2, 4>>(a, sc, s);
+    if (v == 7) return launch_cfg<Cfg<1, 4, 4, 4, 2, 3, 255, 4>>(a, sc, s);
+    if (v == 9) return launch_cfg<Cfg<1, 4, 8, 2, 2, 3>>(a, sc, s);
+    return launch_cfg<Cfg<1, 4, 4, 4, 2, 3, 255, 2>>(a, sc, s);
+  }
+  if (r == 2) {
+    if (v == 1) return launch_cfg<Cfg<2, 4, 8, 2, 2, 3>>(a, sc, s);
+    if (v == 2) return launch_cfg<Cfg<2, 2, 4, 4, 2, 3>>(a, sc, s);
+    if (v == 3) return launch_cfg<Cfg<2, 4, 8, 4, 2, 3>>(a, sc, s);
+    if (v == 4) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 128>>(a, sc, s);
+    if (v == 5) return launch_cfg<Cfg<2, 4, 6, 4, 2, 5>>(a, sc, s);
+    if (v == 6) return launch_cfg<Cfg<2, 4, 4, 4, 2, 6>>(a, sc, s);
+    if (v == 7) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 128, 4>>(a, sc, s);
+    if (v == 9) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3>>(a, sc, s);
+    return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 128, 2>>(a, sc, s);
+  }
+  if (v == 1) return launch_cfg<Cfg<4, 4, 4, 4, 2, 3, 200>>(a, sc, s);
+  if (v == 2) return launch_cfg<Cfg<4, 2, 4, 4, 2, 3>>(a, sc, s);
+  if (v == 3) return launch_cfg<Cfg<4, 4, 8, 4, 2, 3>>(a, sc, s);
+  if (v == 5) return launch_cfg<Cfg<4, 4, 4, 4, 2, 6>>(a, sc, s);
+  if (v == 6) return launch_cfg<Cfg<4, 4, 6, 4, 2, 5>>(a, sc, s);
+  if (v == 7) return launch_cfg<Cfg<4, 4, 6, 4, 1, 9>>(a, sc, s);
+  if (v == 8) return launch_cfg<Cfg<4, 4, 4, 4, 1, 8>>(a, sc, s);
+  if (v == 9) return launch_cfg<Cfg<4, 4, 4, 4, 2, 3, 255, 4>>(a, sc, s);
+  if (v == 10) return launch_cfg<Cfg<4, 2, 4, 4, 2, 3, 255, 4>>(a, sc, s);
+  if (v == 11) return launch_cfg<Cfg<4, 4, 6, 4, 2, 5, 255, 2>>(a, sc, s);
+  if (v == 12) return launch_cfg<Cfg<4, 4, 4, 4, 2, 5, 255, 4>>(a, sc, s);
+  if (v == 14) return launch_cfg<Cfg<4, 4, 4, 4, 2, 3>>(a, sc, s);
+  return launch_cfg<Cfg<4, 2, 4, 4, 2, 5, 255, 4>>(a, sc, s);
 }
 
 }  // namespace bk

@@ -13,6 +13,8 @@ ap.add_argument("--kernels", default="auto")
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--full", action="store_true", help="sweep the ghost shell too (66^3 bricks)")
 ap.add_argument("--peak", type=float, default=6650.0)
+ap.add_argument("--variants", default="")
+ap.add_argument("--kls", default="")
 args = ap.parse_args()
 K = {"auto": bk.KERNEL_AUTO, "brick": bk.KERNEL_BRICK, "tiled": bk.KERNEL_TILED}
 bk.load().bk_set_device(0)
@@ -24,7 +26,13 @@ d.storage[0].from_host(h); d.storage[1].from_host(h)
 t = d.grid.dims
 lo, hi = ((0, 0, 0), t) if args.full else ((1, 1, 1), tuple(x - 1 for x in t))
 pts = args.size ** 3
+import itertools
 for name in args.stencils.split(","):
+  for var, kl in itertools.product(args.variants.split(","), args.kls.split(",")):
+    if var:
+        os.environ["BK_STAR_VARIANT"] = var
+    if kl:
+        os.environ["BK_STAR_KL"] = kl
     for kn in args.kernels.split(","):
         d.stencil, d.kernel = bk.STENCILS[name], K[kn]
         for s in range(3):
@@ -37,4 +45,4 @@ for name in args.stencils.split(","):
         e1.record(); e1.sync()
         ms = e0.elapsed_ms(e1) / args.reps
         gbs = 16.0 * pts / ms / 1e6
-        print(f"{name:9s} {kn:6s} {'full' if args.full else 'inner'} {ms:8.4f} ms  {pts/ms/1e6:8.1f} GStencil/s  {gbs:8.1f} GB/s alg  {gbs/args.peak*100:5.1f}% of {args.peak:.0f}", flush=True)
+        print(f"{name:9s} v{var or '0'} kl{kl or '16'} {kn:6s} {'full' if args.full else 'inner'} {ms:8.4f} ms  {pts/ms/1e6:8.1f} GStencil/s  {gbs:8.1f} GB/s alg  {gbs/args.peak*100:5.1f}% of {args.peak:.0f}", flush=True)
