@@ -24,6 +24,7 @@
 #include "bk_common.h"
 #include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 
 namespace {
 
@@ -75,8 +76,10 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 // ---- compile-time geometry --------------------------------------------------------------------------------------
-template <int R_, int YT_, int TI_, int TJ_, int G_, int D_, int MAXREG_ = 255, int NPW_ = 1>
+template <int R_, int YT_, int TI_, int TJ_, int G_, int D_, int MAXREG_ = 255, int NPW_ = 1, bool CUBE_ = false>
 struct Cfg {
+  static constexpr bool CUBE = CUBE_;                 // (2R+1)^3 cube stencil instead of a star
+  using Coef = typename std::conditional<CUBE_, bk::CubeCoef, bk::StarCoef>::type;
   static constexpr int R = R_, YT = YT_, TI = TI_, TJ = TJ_, G = G_, D = D_;
   static constexpr int W = 2 * R + 1;                 // partial outputs in flight per point
   static constexpr int RUP = ((R + G - 1) / G) * G;   // halo planes streamed before/after a segment (multiple of G)
@@ -88,7 +91,8 @@ struct Cfg {
   static constexpr int NCW = NCONS / 32;
   static constexpr int NPW = NPW_;                    // producer warps (bulk-copy issue is instruction bound)
   static constexpr int NT = NCONS + 32 * NPW;
-  static constexpr int NCOPY = TI * TJ + 2 * TJ + 2 * TI;  // copy jobs per stage (j-halo jobs issue G copies)
+  static constexpr int NJH = CUBE ? TI + 2 : TI;      // j-halo columns: a cube stencil also needs the corner bricks
+  static constexpr int NCOPY = TI * TJ + 2 * TJ + 2 * NJH;  // copy jobs per stage (j-halo jobs issue G copies)
   static constexpr int JOBS = (NCOPY + 32 * NPW - 1) / (32 * NPW);
   static constexpr int MAXREG = MAXREG_;              // register cap (chosen so that the intended CTAs/SM fit)
   static constexpr size_t SMEM = (size_t) D * STAGE + 2 * D * 8 + 128;
@@ -99,7 +103,7 @@ struct Cfg {
 };
 
 template <class C>
-__device__ __forceinline__ void star_body(const TiledArgs &a, const StarCoef &cf) {
+__device__ __forceinline__ void march_body(const TiledArgs &a, const typename C::Coef &cf) {
   constexpr int R = C::R, YT = C::YT, TI = C::TI, TJ = C::TJ, G = C::G, D = C::D, W = C::W, RUP = C::RUP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // dynamic shared memory is only guaranteed 16-B aligned: align the ring to 128 B by hand
@@ -141,8 +145,8 @@ __device__ __forceinline__ void star_body(const TiledArgs &a, const StarCoef &cf
         kind[q] = 1, sbi[q] = 1 + job % TI, sbj[q] = 1 + job / TI;
       } else if ((job -= TI * TJ) < 2 * TJ) {
         kind[q] = 1, sbi[q] = (job & 1) ? TI + 1 : 0, sbj[q] = 1 + (job >> 1);
-      } else if ((job -= 2 * TJ) < 2 * TI) {
-        kind[q] = 2 + (job & 1), sbi[q] = 1 + (job >> 1), sbj[q] = (job & 1) ? TJ + 1 : 0;
+      } else if ((job -= 2 * TJ) < 2 * C::NJH) {
+        kind[q] = 2 + (job & 1), sbi[q] = (C::CUBE ? 0 : 1) + (job >> 1), sbj[q] = (job & 1) ? TJ + 1 : 0;
       }
       // both j-halo kinds land in slot row 0: rows [8-R,8) from below (kind 2), rows [0,R) from above (kind 3)
       dsto[q] = C::slotoff(sbi[q], kind[q] >= 2 ? 0 : sbj[q]) + (kind[q] == 2 ? (8 - R) * 64 : 0);
@@ -247,6 +251,21 @@ __device__ __forceinline__ void star_body(const TiledArgs &a, const StarCoef &cf
   int orel = -R - RUP;  // output plane finished by the current iteration, relative to the segment start
   const int nout = nl * 8;
 
+  // plane `orel` of the segment is complete: 128-bit stores straight into the output brick
+  auto store_plane = [&](const double2 (&fin)[YT]) {
+    if (orel >= 0 && orel < nout) {
+      const int oz = orel & 7;
+      if (oz == 0) {
+        outp = a.out + (size_t) id_next * a.out_step + y0 * 8 + c * 2;
+        if (mine && (orel >> 3) + 1 < nl) id_next = __ldg(gcol + ((orel >> 3) + 1) * glayer);
+      }
+      if (mine) {
+#pragma unroll
+        for (int r = 0; r < YT; ++r) *reinterpret_cast<double2 *>(outp + oz * 64 + r * 8) = fin[r];
+      }
+    }
+  };
+
 #pragma unroll 1
   for (int tb = 0; tb < P; tb += W) {
 #pragma unroll
@@ -254,100 +273,140 @@ __device__ __forceinline__ void star_body(const TiledArgs &a, const StarCoef &cf
       if (tb + u < P) {
         if (pl == 0) mbar_wait(bar_full + 8 * st, ph);
         const unsigned char *pb = ring + st * C::STAGE + pl * 512;
-        double2 v[YT];
-#pragma unroll
-        for (int r = 0; r < YT; ++r) v[r] = *reinterpret_cast<const double2 *>(pb + own_off + r * 64);
-
-        // ---- k taps, first half: this plane is the +d neighbour of outputs t-d ------------------------------------
         const int sF = ((u - R) % W + W) % W;  // slot of output t-R: finished by this plane
-#pragma unroll
-        for (int r = 0; r < YT; ++r) {
-          acc[sF][r].x = fma(cf.cp[2][R - 1], v[r].x, acc[sF][r].x);
-          acc[sF][r].y = fma(cf.cp[2][R - 1], v[r].y, acc[sF][r].y);
-        }
-        if (orel >= 0 && orel < nout) {
-          const int oz = orel & 7;
-          if (oz == 0) {
-            outp = a.out + (size_t) id_next * a.out_step + y0 * 8 + c * 2;
-            if (mine && (orel >> 3) + 1 < nl) id_next = __ldg(gcol + ((orel >> 3) + 1) * glayer);
-          }
-          if (mine) {
-#pragma unroll
-            for (int r = 0; r < YT; ++r) *reinterpret_cast<double2 *>(outp + oz * 64 + r * 8) = acc[sF][r];
-          }
-        }
-#pragma unroll
-        for (int d = R - 1; d >= 1; --d) {
-          const int s = ((u - d) % W + W) % W;
-#pragma unroll
-          for (int r = 0; r < YT; ++r) {
-            acc[s][r].x = fma(cf.cp[2][d - 1], v[r].x, acc[s][r].x);
-            acc[s][r].y = fma(cf.cp[2][d - 1], v[r].y, acc[s][r].y);
-          }
-        }
-        // ---- centre + in-plane taps of output t ------------------------------------------------------------------
         const int s0 = u % W;
-        double2 rows[YT + 2 * R];
+        const int sN = (u + R) % W;            // slot of output t+R: first contribution, (re)initialises the slot
+        if constexpr (C::CUBE) {
+          // Sign symmetry of the cube coefficients (c depends on |dx|,|dy|,|dz| only, stencils/mpi125pt.py:13-32):
+          // fold +-dx, then +-dy, then weight the 9 folded values once per |dz| and scatter along k.
+          // 2*(YT+4)/YT + 6 adds, 27 FMA and 3 adds per point instead of 125 FMA.
+          static_assert(!C::CUBE || R == 2, "cube path is written for radius 2");
+          double2 X0[YT + 4], X1[YT + 4], X2[YT + 4];
 #pragma unroll
-        for (int h = 0; h < R; ++h) rows[h] = *reinterpret_cast<const double2 *>(pb + joff[h]);
-#pragma unroll
-        for (int r = 0; r < YT; ++r) rows[R + r] = v[r];
-#pragma unroll
-        for (int h = 0; h < R; ++h) rows[R + YT + h] = *reinterpret_cast<const double2 *>(pb + joff[R + h]);
-#pragma unroll
-        for (int r = 0; r < YT; ++r) {
-          double line[2 * R + 2];  // cells x0-R .. x0+1+R of row r
-          line[R] = v[r].x, line[R + 1] = v[r].y;
-          const unsigned char *pr = pb + own_off + r * 64;
-          if constexpr (R % 2 == 0) {
-#pragma unroll
-            for (int m = 1; m <= R / 2; ++m) {
-              const double2 lft = *reinterpret_cast<const double2 *>(pr + ioffL[m - 1]);
-              const double2 rgt = *reinterpret_cast<const double2 *>(pr + ioffR[m - 1]);
-              line[R - 2 * m] = lft.x, line[R - 2 * m + 1] = lft.y;
-              line[R + 2 * m] = rgt.x, line[R + 2 * m + 1] = rgt.y;
-            }
-          } else {
-#pragma unroll
-            for (int m = 1; m <= R; ++m) {
-              line[R - m] = *reinterpret_cast<const double *>(pr + ioffL[m - 1]);
-              line[R + 1 + m] = *reinterpret_cast<const double *>(pr + ioffR[m - 1]);
-            }
+          for (int rr = 0; rr < YT + 4; ++rr) {
+            const unsigned char *pr = (rr < 2) ? pb + joff[rr] : (rr >= YT + 2) ? pb + joff[rr - YT] : pb + own_off + (rr - 2) * 64;
+            const double2 ctr = *reinterpret_cast<const double2 *>(pr);
+            const double2 lft = *reinterpret_cast<const double2 *>(pr + ioffL[0]);
+            const double2 rgt = *reinterpret_cast<const double2 *>(pr + ioffR[0]);
+            X0[rr] = ctr;
+            X1[rr] = make_double2(lft.y + ctr.y, ctr.x + rgt.x);
+            X2[rr] = make_double2(lft.x + rgt.x, lft.y + rgt.y);
           }
-          double ax = fma(cf.c0, v[r].x, acc[s0][r].x), ay = fma(cf.c0, v[r].y, acc[s0][r].y);
-#pragma unroll
-          for (int d = 1; d <= R; ++d) {
-            ax = fma(cf.cp[0][d - 1], line[R + d], ax);
-            ay = fma(cf.cp[0][d - 1], line[R + 1 + d], ay);
-            ax = fma(cf.cm[0][d - 1], line[R - d], ax);
-            ay = fma(cf.cm[0][d - 1], line[R + 1 - d], ay);
-          }
-#pragma unroll
-          for (int d = 1; d <= R; ++d) {
-            ax = fma(cf.cp[1][d - 1], rows[R + r + d].x, ax);
-            ay = fma(cf.cp[1][d - 1], rows[R + r + d].y, ay);
-            ax = fma(cf.cm[1][d - 1], rows[R + r - d].x, ax);
-            ay = fma(cf.cm[1][d - 1], rows[R + r - d].y, ay);
-          }
-          acc[s0][r].x = ax, acc[s0][r].y = ay;
-        }
-        // ---- k taps, second half: this plane is the -d neighbour of outputs t+d -----------------------------------
-#pragma unroll
-        for (int d = 1; d <= R - 1; ++d) {
-          const int s = (u + d) % W;
 #pragma unroll
           for (int r = 0; r < YT; ++r) {
-            acc[s][r].x = fma(cf.cm[2][d - 1], v[r].x, acc[s][r].x);
-            acc[s][r].y = fma(cf.cm[2][d - 1], v[r].y, acc[s][r].y);
-          }
-        }
-        const int sN = (u + R) % W;  // slot of output t+R: first contribution, (re)initialises the slot
+            const int rr = r + 2;
+            double2 f[3][3];  // [|dy|][|dx|]
+            f[0][0] = X0[rr], f[0][1] = X1[rr], f[0][2] = X2[rr];
+            f[1][0] = make_double2(X0[rr - 1].x + X0[rr + 1].x, X0[rr - 1].y + X0[rr + 1].y);
+            f[1][1] = make_double2(X1[rr - 1].x + X1[rr + 1].x, X1[rr - 1].y + X1[rr + 1].y);
+            f[1][2] = make_double2(X2[rr - 1].x + X2[rr + 1].x, X2[rr - 1].y + X2[rr + 1].y);
+            f[2][0] = make_double2(X0[rr - 2].x + X0[rr + 2].x, X0[rr - 2].y + X0[rr + 2].y);
+            f[2][1] = make_double2(X1[rr - 2].x + X1[rr + 2].x, X1[rr - 2].y + X1[rr + 2].y);
+            f[2][2] = make_double2(X2[rr - 2].x + X2[rr + 2].x, X2[rr - 2].y + X2[rr + 2].y);
+            double2 p0 = acc[s0][r], p1, p2;
+            p1 = make_double2(cf.cc[1][0][0] * f[0][0].x, cf.cc[1][0][0] * f[0][0].y);
+            p2 = make_double2(cf.cc[2][0][0] * f[0][0].x, cf.cc[2][0][0] * f[0][0].y);
 #pragma unroll
-        for (int r = 0; r < YT; ++r) {
-          acc[sN][r].x = cf.cm[2][R - 1] * v[r].x;
-          acc[sN][r].y = cf.cm[2][R - 1] * v[r].y;
-        }
+            for (int ay = 0; ay < 3; ++ay)
+#pragma unroll
+              for (int ax = 0; ax < 3; ++ax) {
+                p0.x = fma(cf.cc[0][ay][ax], f[ay][ax].x, p0.x), p0.y = fma(cf.cc[0][ay][ax], f[ay][ax].y, p0.y);
+                if (ay + ax > 0) {
+                  p1.x = fma(cf.cc[1][ay][ax], f[ay][ax].x, p1.x), p1.y = fma(cf.cc[1][ay][ax], f[ay][ax].y, p1.y);
+                  p2.x = fma(cf.cc[2][ay][ax], f[ay][ax].x, p2.x), p2.y = fma(cf.cc[2][ay][ax], f[ay][ax].y, p2.y);
+                }
+              }
+            const int sm1 = ((u - 1) % W + W) % W, sp1 = (u + 1) % W;
+            acc[sF][r].x += p2.x, acc[sF][r].y += p2.y;
+            acc[sm1][r].x += p1.x, acc[sm1][r].y += p1.y;
+            acc[s0][r] = p0;
+            acc[sp1][r].x += p1.x, acc[sp1][r].y += p1.y;
+            acc[sN][r] = p2;
+          }
+          store_plane(acc[sF]);
+        } else {
+          double2 v[YT];
+#pragma unroll
+          for (int r = 0; r < YT; ++r) v[r] = *reinterpret_cast<const double2 *>(pb + own_off + r * 64);
 
+          // ---- k taps, first half: this plane is the +d neighbour of outputs t-d ------------------------------------
+#pragma unroll
+          for (int r = 0; r < YT; ++r) {
+            acc[sF][r].x = fma(cf.cp[2][R - 1], v[r].x, acc[sF][r].x);
+            acc[sF][r].y = fma(cf.cp[2][R - 1], v[r].y, acc[sF][r].y);
+          }
+          store_plane(acc[sF]);
+#pragma unroll
+          for (int d = R - 1; d >= 1; --d) {
+            const int s = ((u - d) % W + W) % W;
+#pragma unroll
+            for (int r = 0; r < YT; ++r) {
+              acc[s][r].x = fma(cf.cp[2][d - 1], v[r].x, acc[s][r].x);
+              acc[s][r].y = fma(cf.cp[2][d - 1], v[r].y, acc[s][r].y);
+            }
+          }
+          // ---- centre + in-plane taps of output t ------------------------------------------------------------------
+          double2 rows[YT + 2 * R];
+#pragma unroll
+          for (int h = 0; h < R; ++h) rows[h] = *reinterpret_cast<const double2 *>(pb + joff[h]);
+#pragma unroll
+          for (int r = 0; r < YT; ++r) rows[R + r] = v[r];
+#pragma unroll
+          for (int h = 0; h < R; ++h) rows[R + YT + h] = *reinterpret_cast<const double2 *>(pb + joff[R + h]);
+#pragma unroll
+          for (int r = 0; r < YT; ++r) {
+            double line[2 * R + 2];  // cells x0-R .. x0+1+R of row r
+            line[R] = v[r].x, line[R + 1] = v[r].y;
+            const unsigned char *pr = pb + own_off + r * 64;
+            if constexpr (R % 2 == 0) {
+#pragma unroll
+              for (int m = 1; m <= R / 2; ++m) {
+                const double2 lft = *reinterpret_cast<const double2 *>(pr + ioffL[m - 1]);
+                const double2 rgt = *reinterpret_cast<const double2 *>(pr + ioffR[m - 1]);
+                line[R - 2 * m] = lft.x, line[R - 2 * m + 1] = lft.y;
+                line[R + 2 * m] = rgt.x, line[R + 2 * m + 1] = rgt.y;
+              }
+            } else {
+#pragma unroll
+              for (int m = 1; m <= R; ++m) {
+                line[R - m] = *reinterpret_cast<const double *>(pr + ioffL[m - 1]);
+                line[R + 1 + m] = *reinterpret_cast<const double *>(pr + ioffR[m - 1]);
+              }
+            }
+            double ax = fma(cf.c0, v[r].x, acc[s0][r].x), ay = fma(cf.c0, v[r].y, acc[s0][r].y);
+#pragma unroll
+            for (int d = 1; d <= R; ++d) {
+              ax = fma(cf.cp[0][d - 1], line[R + d], ax);
+              ay = fma(cf.cp[0][d - 1], line[R + 1 + d], ay);
+              ax = fma(cf.cm[0][d - 1], line[R - d], ax);
+              ay = fma(cf.cm[0][d - 1], line[R + 1 - d], ay);
+            }
+#pragma unroll
+            for (int d = 1; d <= R; ++d) {
+              ax = fma(cf.cp[1][d - 1], rows[R + r + d].x, ax);
+              ay = fma(cf.cp[1][d - 1], rows[R + r + d].y, ay);
+              ax = fma(cf.cm[1][d - 1], rows[R + r - d].x, ax);
+              ay = fma(cf.cm[1][d - 1], rows[R + r - d].y, ay);
+            }
+            acc[s0][r].x = ax, acc[s0][r].y = ay;
+          }
+          // ---- k taps, second half: this plane is the -d neighbour of outputs t+d -----------------------------------
+#pragma unroll
+          for (int d = 1; d <= R - 1; ++d) {
+            const int s = (u + d) % W;
+#pragma unroll
+            for (int r = 0; r < YT; ++r) {
+              acc[s][r].x = fma(cf.cm[2][d - 1], v[r].x, acc[s][r].x);
+              acc[s][r].y = fma(cf.cm[2][d - 1], v[r].y, acc[s][r].y);
+            }
+          }
+#pragma unroll
+          for (int r = 0; r < YT; ++r) {
+            acc[sN][r].x = cf.cm[2][R - 1] * v[r].x;
+            acc[sN][r].y = cf.cm[2][R - 1] * v[r].y;
+          }
+
+        }
         ++orel;
         if (++pl == G) {
           pl = 0;
@@ -361,19 +420,20 @@ __device__ __forceinline__ void star_body(const TiledArgs &a, const StarCoef &cf
 }
 
 template <class C>
-__global__ void __launch_bounds__(C::NT) k_star(const __grid_constant__ TiledArgs a, const __grid_constant__ StarCoef cf) {
-  star_body<C>(a, cf);
+__global__ void __launch_bounds__(C::NT) k_star(const __grid_constant__ TiledArgs a,
+                                                const __grid_constant__ typename C::Coef cf) {
+  march_body<C>(a, cf);
 }
 // same body under an explicit register cap (so that two CTAs fit one SM)
 template <class C>
 __global__ void __launch_bounds__(C::NT) __maxnreg__(C::MAXREG) k_star_capped(const __grid_constant__ TiledArgs a,
-                                                                               const __grid_constant__ StarCoef cf) {
-  star_body<C>(a, cf);
+                                                                               const __grid_constant__ typename C::Coef cf) {
+  march_body<C>(a, cf);
 }
 
 template <class C>
-int launch_cfg(const TiledArgs &a0, const StarCoef &cf, cudaStream_t s) {
-  void (*kern)(const TiledArgs, const StarCoef);
+int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s) {
+  void (*kern)(const TiledArgs, const typename C::Coef);
   if constexpr (C::MAXREG < 255) kern = k_star_capped<C>; else kern = k_star<C>;
   BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
   if (getenv("BK_DEBUG")) {
@@ -400,12 +460,16 @@ int launch_cfg(const TiledArgs &a0, const StarCoef &cf, cudaStream_t s) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NT, C::SMEM);
     slots = sms * (per_sm > 0 ? per_sm : 1);
   }
+  // cost of a split into nseg segments (unit: planes): every CTA streams 8*layers + ovh planes, CTAs are dealt to the
+  // resident slots dynamically, and the launch ends about 0.7 CTA-times after the slots run out of fresh CTAs
+  // (constants fitted on B200, profiles/r01_segments.md)
+  const double ovh = 3.0 * C::R + 2.0, tiles = (double) a.ntx * nty;
   int best_seg = 1;
-  long best_cost = -1;
+  double best_cost = -1.0;
   for (int nseg = 1; nseg <= nz; ++nseg) {
-    const int kl = (nz + nseg - 1) / nseg;
-    const long ctas = (long) a.ntx * nty * ((nz + kl - 1) / kl);
-    const long cost = ((ctas + slots - 1) / slots) * (kl * 8 + 2 * C::RUP + 24);  // +24: pipeline fill per CTA
+    const int kl = (nz + nseg - 1) / nseg, segs = (nz + kl - 1) / kl;
+    const double work = tiles * (8.0 * nz + ovh * segs);
+    const double cost = work / slots + 0.7 * (8.0 * kl + ovh);
     if (best_cost < 0 || cost < best_cost) best_cost = cost, best_seg = nseg;
   }
   a.kl = (nz + best_seg - 1) / best_seg;
@@ -423,10 +487,6 @@ namespace bk {
 
 int launch_tiled(int stencil, const bk_field_t &f, const unsigned *grid, const unsigned *gdims, const unsigned *lo,
                  const unsigned *hi, const double *coeff, cudaStream_t s) {
-  if (stencil == BK_ST_MPI125PT) return BK_EUNSUPPORTED;  // cube stencil: per-brick family for now
-  StarCoef sc;
-  const int r = star_coef_for(stencil, coeff, &sc);
-  if (r < 0) return BK_EINVAL;
   if (((size_t) f.in | (size_t) f.out) & 15 || (f.in_step & 1) || (f.out_step & 1)) return BK_EUNSUPPORTED;
   TiledArgs a;
   a.in = f.in, a.out = f.out, a.in_step = f.in_step, a.out_step = f.out_step, a.grid = grid;
@@ -435,6 +495,18 @@ int launch_tiled(int stencil, const bk_field_t &f, const unsigned *grid, const u
   a.ntx = a.kl = 0;
   int v = 0;
   if (const char *e = getenv("BK_STAR_VARIANT")) v = atoi(e);  // developer knob: alternative geometries
+  if (stencil == BK_ST_MPI125PT) {
+    CubeCoef cc;
+    if (cube_coef_for(stencil, &cc) < 0) return BK_EINVAL;
+    if (v == 1) return launch_cfg<Cfg<2, 2, 4, 4, 2, 4, 255, 4, true>>(a, cc, s);
+    if (v == 2) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 255, 4, true>>(a, cc, s);
+    if (v == 3) return launch_cfg<Cfg<2, 2, 4, 4, 2, 3, 255, 4, true>>(a, cc, s);
+    if (v == 4) return launch_cfg<Cfg<2, 2, 4, 4, 2, 3, 128, 4, true>>(a, cc, s);
+    return launch_cfg<Cfg<2, 4, 4, 4, 2, 4, 255, 4, true>>(a, cc, s);
+  }
+  StarCoef sc;
+  const int r = star_coef_for(stencil, coeff, &sc);
+  if (r < 0) return BK_EINVAL;
   if (r == 1) {
     if (v == 1) return launch_cfg<Cfg<1, 4, 4, 4, 2, 3>>(a, sc, s);
     if (v == 2) return launch_cfg<Cfg<1, 2, 8, 2, 2, 3>>(a, sc, s);
