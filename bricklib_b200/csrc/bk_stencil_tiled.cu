@@ -279,7 +279,7 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
         if constexpr (C::CUBE) {
           // Sign symmetry of the cube coefficients (c depends on |dx|,|dy|,|dz| only, stencils/mpi125pt.py:13-32):
           // fold +-dx, then +-dy, then weight the 9 folded values once per |dz| and scatter along k.
-          // 2*(YT+4)/YT + 6 adds, 27 FMA and 3 adds per point instead of 125 FMA.
+          // 2*(YT+4)/YT + 6 + 3 adds, 18 FMA and 3 adds per point instead of 125 FMA.
           static_assert(!C::CUBE || R == 2, "cube path is written for radius 2");
           double2 X0[YT + 4], X1[YT + 4], X2[YT + 4];
 #pragma unroll
@@ -303,19 +303,26 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
             f[2][0] = make_double2(X0[rr - 2].x + X0[rr + 2].x, X0[rr - 2].y + X0[rr + 2].y);
             f[2][1] = make_double2(X1[rr - 2].x + X1[rr + 2].x, X1[rr - 2].y + X1[rr + 2].y);
             f[2][2] = make_double2(X2[rr - 2].x + X2[rr + 2].x, X2[rr - 2].y + X2[rr + 2].y);
+            // the coefficient is also symmetric under permutation of (|dx|,|dy|,|dz|): cc[az][ay][ax] == cc[az][ax][ay],
+            // so the mirrored folds share one FMA per |dz| (6 instead of 9)
+            const double2 g[6] = {f[0][0],
+                                  make_double2(f[0][1].x + f[1][0].x, f[0][1].y + f[1][0].y),
+                                  make_double2(f[0][2].x + f[2][0].x, f[0][2].y + f[2][0].y),
+                                  f[1][1],
+                                  make_double2(f[1][2].x + f[2][1].x, f[1][2].y + f[2][1].y),
+                                  f[2][2]};
+            constexpr int GY[6] = {0, 0, 0, 1, 1, 2}, GX[6] = {0, 1, 2, 1, 2, 2};
             double2 p0 = acc[s0][r], p1, p2;
-            p1 = make_double2(cf.cc[1][0][0] * f[0][0].x, cf.cc[1][0][0] * f[0][0].y);
-            p2 = make_double2(cf.cc[2][0][0] * f[0][0].x, cf.cc[2][0][0] * f[0][0].y);
+            p1 = make_double2(cf.cc[1][0][0] * g[0].x, cf.cc[1][0][0] * g[0].y);
+            p2 = make_double2(cf.cc[2][0][0] * g[0].x, cf.cc[2][0][0] * g[0].y);
 #pragma unroll
-            for (int ay = 0; ay < 3; ++ay)
-#pragma unroll
-              for (int ax = 0; ax < 3; ++ax) {
-                p0.x = fma(cf.cc[0][ay][ax], f[ay][ax].x, p0.x), p0.y = fma(cf.cc[0][ay][ax], f[ay][ax].y, p0.y);
-                if (ay + ax > 0) {
-                  p1.x = fma(cf.cc[1][ay][ax], f[ay][ax].x, p1.x), p1.y = fma(cf.cc[1][ay][ax], f[ay][ax].y, p1.y);
-                  p2.x = fma(cf.cc[2][ay][ax], f[ay][ax].x, p2.x), p2.y = fma(cf.cc[2][ay][ax], f[ay][ax].y, p2.y);
-                }
+            for (int q = 0; q < 6; ++q) {
+              p0.x = fma(cf.cc[0][GY[q]][GX[q]], g[q].x, p0.x), p0.y = fma(cf.cc[0][GY[q]][GX[q]], g[q].y, p0.y);
+              if (q > 0) {
+                p1.x = fma(cf.cc[1][GY[q]][GX[q]], g[q].x, p1.x), p1.y = fma(cf.cc[1][GY[q]][GX[q]], g[q].y, p1.y);
+                p2.x = fma(cf.cc[2][GY[q]][GX[q]], g[q].x, p2.x), p2.y = fma(cf.cc[2][GY[q]][GX[q]], g[q].y, p2.y);
               }
+            }
             const int sm1 = ((u - 1) % W + W) % W, sp1 = (u + 1) % W;
             acc[sF][r].x += p2.x, acc[sF][r].y += p2.y;
             acc[sm1][r].x += p1.x, acc[sm1][r].y += p1.y;
@@ -502,7 +509,10 @@ int launch_tiled(int stencil, const bk_field_t &f, const unsigned *grid, const u
     if (v == 2) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 255, 4, true>>(a, cc, s);
     if (v == 3) return launch_cfg<Cfg<2, 2, 4, 4, 2, 3, 255, 4, true>>(a, cc, s);
     if (v == 4) return launch_cfg<Cfg<2, 2, 4, 4, 2, 3, 128, 4, true>>(a, cc, s);
-    return launch_cfg<Cfg<2, 4, 4, 4, 2, 4, 255, 4, true>>(a, cc, s);
+    if (v == 5) return launch_cfg<Cfg<2, 2, 6, 4, 2, 4, 128, 4, true>>(a, cc, s);
+    if (v == 7) return launch_cfg<Cfg<2, 2, 4, 4, 2, 5, 255, 4, true>>(a, cc, s);
+    if (v == 8) return launch_cfg<Cfg<2, 4, 4, 4, 2, 4, 255, 4, true>>(a, cc, s);
+    return launch_cfg<Cfg<2, 2, 6, 4, 2, 3, 128, 4, true>>(a, cc, s);
   }
   StarCoef sc;
   const int r = star_coef_for(stencil, coeff, &sc);
@@ -516,6 +526,9 @@ int launch_tiled(int stencil, const bk_field_t &f, const unsigned *grid, const u
     if (v == 6) return launch_cfg<Cfg<1, 4, 4, 4, 2, 4>>(a, sc, s);
     if (v == 7) return launch_cfg<Cfg<1, 4, 4, 4, 2, 3, 255, 4>>(a, sc, s);
     if (v == 9) return launch_cfg<Cfg<1, 4, 8, 2, 2, 3>>(a, sc, s);
+    if (v == 10) return launch_cfg<Cfg<1, 4, 6, 4, 1, 4, 128, 2>>(a, sc, s);
+    if (v == 11) return launch_cfg<Cfg<1, 4, 4, 4, 1, 5, 128, 2>>(a, sc, s);
+    if (v == 12) return launch_cfg<Cfg<1, 4, 6, 4, 1, 4, 128, 1>>(a, sc, s);
     return launch_cfg<Cfg<1, 4, 4, 4, 2, 3, 255, 2>>(a, sc, s);
   }
   if (r == 2) {
@@ -527,6 +540,8 @@ int launch_tiled(int stencil, const bk_field_t &f, const unsigned *grid, const u
     if (v == 6) return launch_cfg<Cfg<2, 4, 4, 4, 2, 6>>(a, sc, s);
     if (v == 7) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 128, 4>>(a, sc, s);
     if (v == 9) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3>>(a, sc, s);
+    if (v == 10) return launch_cfg<Cfg<2, 4, 6, 4, 1, 4, 128, 2>>(a, sc, s);
+    if (v == 11) return launch_cfg<Cfg<2, 4, 4, 4, 1, 5, 128, 2>>(a, sc, s);
     return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 128, 2>>(a, sc, s);
   }
   if (v == 1) return launch_cfg<Cfg<4, 4, 4, 4, 2, 3, 200>>(a, sc, s);
@@ -541,6 +556,10 @@ int launch_tiled(int stencil, const bk_field_t &f, const unsigned *grid, const u
   if (v == 11) return launch_cfg<Cfg<4, 4, 6, 4, 2, 5, 255, 2>>(a, sc, s);
   if (v == 12) return launch_cfg<Cfg<4, 4, 4, 4, 2, 5, 255, 4>>(a, sc, s);
   if (v == 14) return launch_cfg<Cfg<4, 4, 4, 4, 2, 3>>(a, sc, s);
+  if (v == 15) return launch_cfg<Cfg<4, 2, 4, 4, 2, 5, 255, 2>>(a, sc, s);
+  if (v == 16) return launch_cfg<Cfg<4, 2, 4, 4, 2, 5, 255, 3>>(a, sc, s);
+  if (v == 17) return launch_cfg<Cfg<4, 2, 4, 4, 2, 6, 255, 4>>(a, sc, s);
+  if (v == 18) return launch_cfg<Cfg<4, 2, 6, 4, 2, 4, 128, 4>>(a, sc, s);
   return launch_cfg<Cfg<4, 2, 4, 4, 2, 5, 255, 4>>(a, sc, s);
 }
 
