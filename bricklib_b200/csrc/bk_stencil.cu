@@ -78,8 +78,8 @@ int cube_coef_for(int stencil, CubeCoef *o) {
 }
 
 // implemented in bk_stencil_tiled.cu
-int launch_tiled(int stencil, const bk_field_t &f, const unsigned *grid, const unsigned *gdims, const unsigned *lo,
-                 const unsigned *hi, const double *coeff, cudaStream_t s);
+int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, unsigned nsub, const unsigned *grid,
+                 const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff, cudaStream_t s);
 
 }  // namespace bk
 
@@ -218,7 +218,7 @@ int bk_stencil_apply(int stencil, const bk_field_t *f, const unsigned *grid, con
   BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
   cudaStream_t s = (cudaStream_t) stream;
   if (flags != BK_KERNEL_BRICK) {
-    int rc = bk::launch_tiled(stencil, *f, grid, gdims, lo, hi, coeff, s);
+    int rc = bk::launch_tiled(stencil, *f, nullptr, 1, grid, gdims, lo, hi, coeff, s);
     if (rc != BK_EUNSUPPORTED || flags == BK_KERNEL_TILED) return rc;
   }
   Select sel = {grid, nullptr, nullptr, gdims[0], gdims[1], {lo[0], lo[1], lo[2]}, 0};
@@ -242,7 +242,12 @@ int bk_stencil_apply_multi(int stencil, const bk_field_t *fields_dev, unsigned n
   BK_REQUIRE(fields_dev && grid && gdims && lo && hi && nsub > 0, "null argument");
   BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
   const unsigned nx = hi[0] - lo[0];
-  BK_REQUIRE((unsigned long long) nx * nsub < (1ull << 31), "launch too wide");
+  BK_REQUIRE((unsigned long long) nx * nsub < (1ull << 31) && nsub <= 65535, "launch too wide");
+  if (!getenv("BK_MULTI_BRICK")) {  // developer knob: force the per-brick family
+    bk_field_t none = {nullptr, nullptr, 512, nullptr, 512};
+    int rc = bk::launch_tiled(stencil, none, fields_dev, nsub, grid, gdims, lo, hi, coeff, (cudaStream_t) stream);
+    if (rc != BK_EUNSUPPORTED) return rc;
+  }
   Select sel = {grid, nullptr, fields_dev, gdims[0], gdims[1], {lo[0], lo[1], lo[2]}, nx};
   bk_field_t dummy = {nullptr, nullptr, 512, nullptr, 512};
   return launch_brick(stencil, sel, dummy, dim3(nx * nsub, hi[1] - lo[1], hi[2] - lo[2]), coeff, (cudaStream_t) stream);

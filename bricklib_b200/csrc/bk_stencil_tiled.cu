@@ -39,6 +39,7 @@ struct TiledArgs {
   int lo[3], hi[3];
   int ntx;  // tiles along i
   int kl;   // brick layers per k segment
+  const bk_field_t *multi;  // strong-scaling launch: per-subdomain fields (device array), subdomain = blockIdx.z
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------------
@@ -112,6 +113,13 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
   const uint32_t bar_full = ring_u32 + D * C::STAGE;
   const uint32_t bar_empty = bar_full + D * 8;
 
+  const double *fin = a.in;
+  double *fout = a.out;
+  size_t in_step = a.in_step, out_step = a.out_step;
+  if (a.multi) {  // strong/main.cu:85-99: many subdomains share grid and adjacency, each has its own storages
+    const bk_field_t f = a.multi[blockIdx.z];
+    fin = f.in, fout = f.out, in_step = f.in_step, out_step = f.out_step;
+  }
   const int tid = threadIdx.x;
   const int tx = blockIdx.x % a.ntx, ty = blockIdx.x / a.ntx;
   const int i0 = a.lo[0] + tx * TI, j0 = a.lo[1] + ty * TJ;
@@ -180,7 +188,7 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
       const uint32_t sb = ring_u32 + st * C::STAGE;
 #pragma unroll
       for (int q = 0; q < C::JOBS; ++q) {
-        const double *src = a.in + (size_t) idc[q] * a.in_step + pz * 64;
+        const double *src = fin + (size_t) idc[q] * in_step + pz * 64;
         if (kind[q] == 1) {
           bulk_g2s(sb + dsto[q], src, G * 512, fb);
         } else if (kind[q] >= 2) {
@@ -238,7 +246,7 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
   const unsigned *gcol = a.grid + ((size_t) kb0 * a.gy + (j0 + bj)) * a.gx + (i0 + bi);
   const size_t glayer = (size_t) a.gy * a.gx;
   unsigned id_next = mine ? __ldg(gcol) : 0u;
-  double *outp = a.out;
+  double *outp = fout;
 
   double2 acc[W][YT];
 #pragma unroll
@@ -256,7 +264,7 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
     if (orel >= 0 && orel < nout) {
       const int oz = orel & 7;
       if (oz == 0) {
-        outp = a.out + (size_t) id_next * a.out_step + y0 * 8 + c * 2;
+        outp = fout + (size_t) id_next * out_step + y0 * 8 + c * 2;
         if (mine && (orel >> 3) + 1 < nl) id_next = __ldg(gcol + ((orel >> 3) + 1) * glayer);
       }
       if (mine) {
@@ -439,7 +447,7 @@ __global__ void __launch_bounds__(C::NT) __maxnreg__(C::MAXREG) k_star_capped(co
 }
 
 template <class C>
-int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s) {
+int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, unsigned nsub = 1) {
   void (*kern)(const TiledArgs, const typename C::Coef);
   if constexpr (C::MAXREG < 255) kern = k_star_capped<C>; else kern = k_star<C>;
   BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
@@ -470,7 +478,7 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s) 
   // cost of a split into nseg segments (unit: planes): every CTA streams 8*layers + ovh planes, CTAs are dealt to the
   // resident slots dynamically, and the launch ends about 0.7 CTA-times after the slots run out of fresh CTAs
   // (constants fitted on B200, profiles/r01_segments.md)
-  const double ovh = 3.0 * C::R + 2.0, tiles = (double) a.ntx * nty;
+  const double ovh = 3.0 * C::R + 2.0, tiles = (double) a.ntx * nty * nsub;
   int best_seg = 1;
   double best_cost = -1.0;
   for (int nseg = 1; nseg <= nz; ++nseg) {
@@ -482,7 +490,7 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s) 
   a.kl = (nz + best_seg - 1) / best_seg;
   if (const char *e = getenv("BK_STAR_KL")) a.kl = atoi(e) > 0 ? atoi(e) : a.kl;  // developer knob
   const int segs = (nz + a.kl - 1) / a.kl;
-  dim3 grid((unsigned) (a.ntx * nty), (unsigned) segs, 1);
+  dim3 grid((unsigned) (a.ntx * nty), (unsigned) segs, nsub);
   kern<<<grid, C::NT, C::SMEM, s>>>(a, cf);
   BK_LAUNCHED();
   return BK_OK;
@@ -492,75 +500,40 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s) 
 
 namespace bk {
 
-int launch_tiled(int stencil, const bk_field_t &f, const unsigned *grid, const unsigned *gdims, const unsigned *lo,
-                 const unsigned *hi, const double *coeff, cudaStream_t s) {
-  if (((size_t) f.in | (size_t) f.out) & 15 || (f.in_step & 1) || (f.out_step & 1)) return BK_EUNSUPPORTED;
+int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, unsigned nsub, const unsigned *grid,
+                 const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff, cudaStream_t s) {
+  if (!multi_dev && (((size_t) f.in | (size_t) f.out) & 15 || (f.in_step & 1) || (f.out_step & 1))) return BK_EUNSUPPORTED;
   TiledArgs a;
   a.in = f.in, a.out = f.out, a.in_step = f.in_step, a.out_step = f.out_step, a.grid = grid;
   a.gx = (int) gdims[0], a.gy = (int) gdims[1], a.gz = (int) gdims[2];
   for (int d = 0; d < 3; ++d) a.lo[d] = (int) lo[d], a.hi[d] = (int) hi[d];
   a.ntx = a.kl = 0;
+  a.multi = multi_dev;
   int v = 0;
-  if (const char *e = getenv("BK_STAR_VARIANT")) v = atoi(e);  // developer knob: alternative geometries
+  if (const char *e = getenv("BK_STAR_VARIANT")) v = atoi(e);  // developer knob: one alternative geometry per stencil
+  // Geometries (R, YT, TI, TJ, G, D, register cap, producer warps), chosen on B200 -- see DESIGN.md section 4:
+  //   radius 1/2: 4x4-brick tiles, 4 consumer warps + 2 producer warps, 2 CTAs per SM (<= 128 registers)
+  //   radius 4  : 2 rows per thread (8 consumer warps) + 4 producer warps, 5-stage ring, 1 CTA per SM
+  //   cube      : 6x4-brick tiles, 12 consumer warps + 4 producer warps, 128 registers, 1 CTA per SM
   if (stencil == BK_ST_MPI125PT) {
     CubeCoef cc;
     if (cube_coef_for(stencil, &cc) < 0) return BK_EINVAL;
-    if (v == 1) return launch_cfg<Cfg<2, 2, 4, 4, 2, 4, 255, 4, true>>(a, cc, s);
-    if (v == 2) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 255, 4, true>>(a, cc, s);
-    if (v == 3) return launch_cfg<Cfg<2, 2, 4, 4, 2, 3, 255, 4, true>>(a, cc, s);
-    if (v == 4) return launch_cfg<Cfg<2, 2, 4, 4, 2, 3, 128, 4, true>>(a, cc, s);
-    if (v == 5) return launch_cfg<Cfg<2, 2, 6, 4, 2, 4, 128, 4, true>>(a, cc, s);
-    if (v == 7) return launch_cfg<Cfg<2, 2, 4, 4, 2, 5, 255, 4, true>>(a, cc, s);
-    if (v == 8) return launch_cfg<Cfg<2, 4, 4, 4, 2, 4, 255, 4, true>>(a, cc, s);
-    return launch_cfg<Cfg<2, 2, 6, 4, 2, 3, 128, 4, true>>(a, cc, s);
+    if (v == 1) return launch_cfg<Cfg<2, 2, 4, 4, 2, 4, 255, 4, true>>(a, cc, s, nsub);
+    return launch_cfg<Cfg<2, 2, 6, 4, 2, 3, 128, 4, true>>(a, cc, s, nsub);
   }
   StarCoef sc;
   const int r = star_coef_for(stencil, coeff, &sc);
   if (r < 0) return BK_EINVAL;
   if (r == 1) {
-    if (v == 1) return launch_cfg<Cfg<1, 4, 4, 4, 2, 3>>(a, sc, s);
-    if (v == 2) return launch_cfg<Cfg<1, 2, 8, 2, 2, 3>>(a, sc, s);
-    if (v == 3) return launch_cfg<Cfg<1, 4, 8, 4, 2, 3>>(a, sc, s);
-    if (v == 4) return launch_cfg<Cfg<1, 4, 8, 2, 1, 4>>(a, sc, s);
-    if (v == 5) return launch_cfg<Cfg<1, 4, 6, 4, 2, 5>>(a, sc, s);
-    if (v == 6) return launch_cfg<Cfg<1, 4, 4, 4, 2, 4>>(a, sc, s);
-    if (v == 7) return launch_cfg<Cfg<1, 4, 4, 4, 2, 3, 255, 4>>(a, sc, s);
-    if (v == 9) return launch_cfg<Cfg<1, 4, 8, 2, 2, 3>>(a, sc, s);
-    if (v == 10) return launch_cfg<Cfg<1, 4, 6, 4, 1, 4, 128, 2>>(a, sc, s);
-    if (v == 11) return launch_cfg<Cfg<1, 4, 4, 4, 1, 5, 128, 2>>(a, sc, s);
-    if (v == 12) return launch_cfg<Cfg<1, 4, 6, 4, 1, 4, 128, 1>>(a, sc, s);
-    return launch_cfg<Cfg<1, 4, 4, 4, 2, 3, 255, 2>>(a, sc, s);
+    if (v == 1) return launch_cfg<Cfg<1, 4, 6, 4, 1, 4, 128, 2>>(a, sc, s, nsub);
+    return launch_cfg<Cfg<1, 4, 4, 4, 2, 3, 255, 2>>(a, sc, s, nsub);
   }
   if (r == 2) {
-    if (v == 1) return launch_cfg<Cfg<2, 4, 8, 2, 2, 3>>(a, sc, s);
-    if (v == 2) return launch_cfg<Cfg<2, 2, 4, 4, 2, 3>>(a, sc, s);
-    if (v == 3) return launch_cfg<Cfg<2, 4, 8, 4, 2, 3>>(a, sc, s);
-    if (v == 4) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 128>>(a, sc, s);
-    if (v == 5) return launch_cfg<Cfg<2, 4, 6, 4, 2, 5>>(a, sc, s);
-    if (v == 6) return launch_cfg<Cfg<2, 4, 4, 4, 2, 6>>(a, sc, s);
-    if (v == 7) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 128, 4>>(a, sc, s);
-    if (v == 9) return launch_cfg<Cfg<2, 4, 4, 4, 2, 3>>(a, sc, s);
-    if (v == 10) return launch_cfg<Cfg<2, 4, 6, 4, 1, 4, 128, 2>>(a, sc, s);
-    if (v == 11) return launch_cfg<Cfg<2, 4, 4, 4, 1, 5, 128, 2>>(a, sc, s);
-    return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 128, 2>>(a, sc, s);
+    if (v == 1) return launch_cfg<Cfg<2, 4, 6, 4, 1, 4, 128, 2>>(a, sc, s, nsub);
+    return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 128, 2>>(a, sc, s, nsub);
   }
-  if (v == 1) return launch_cfg<Cfg<4, 4, 4, 4, 2, 3, 200>>(a, sc, s);
-  if (v == 2) return launch_cfg<Cfg<4, 2, 4, 4, 2, 3>>(a, sc, s);
-  if (v == 3) return launch_cfg<Cfg<4, 4, 8, 4, 2, 3>>(a, sc, s);
-  if (v == 5) return launch_cfg<Cfg<4, 4, 4, 4, 2, 6>>(a, sc, s);
-  if (v == 6) return launch_cfg<Cfg<4, 4, 6, 4, 2, 5>>(a, sc, s);
-  if (v == 7) return launch_cfg<Cfg<4, 4, 6, 4, 1, 9>>(a, sc, s);
-  if (v == 8) return launch_cfg<Cfg<4, 4, 4, 4, 1, 8>>(a, sc, s);
-  if (v == 9) return launch_cfg<Cfg<4, 4, 4, 4, 2, 3, 255, 4>>(a, sc, s);
-  if (v == 10) return launch_cfg<Cfg<4, 2, 4, 4, 2, 3, 255, 4>>(a, sc, s);
-  if (v == 11) return launch_cfg<Cfg<4, 4, 6, 4, 2, 5, 255, 2>>(a, sc, s);
-  if (v == 12) return launch_cfg<Cfg<4, 4, 4, 4, 2, 5, 255, 4>>(a, sc, s);
-  if (v == 14) return launch_cfg<Cfg<4, 4, 4, 4, 2, 3>>(a, sc, s);
-  if (v == 15) return launch_cfg<Cfg<4, 2, 4, 4, 2, 5, 255, 2>>(a, sc, s);
-  if (v == 16) return launch_cfg<Cfg<4, 2, 4, 4, 2, 5, 255, 3>>(a, sc, s);
-  if (v == 17) return launch_cfg<Cfg<4, 2, 4, 4, 2, 6, 255, 4>>(a, sc, s);
-  if (v == 18) return launch_cfg<Cfg<4, 2, 6, 4, 2, 4, 128, 4>>(a, sc, s);
-  return launch_cfg<Cfg<4, 2, 4, 4, 2, 5, 255, 4>>(a, sc, s);
+  if (v == 1) return launch_cfg<Cfg<4, 4, 4, 4, 2, 5, 255, 4>>(a, sc, s, nsub);
+  return launch_cfg<Cfg<4, 2, 4, 4, 2, 5, 255, 4>>(a, sc, s, nsub);
 }
 
 }  // namespace bk

@@ -216,3 +216,33 @@ def test_full_size_matches_oracle_on_a_sampled_slab(big):
         a_in, a_out = assemble(inp), assemble(out)
         want = P.sweep_array(st, a_in, (8, 8, 8), (a_in.shape[2] - 8, a_in.shape[1] - 8, a_in.shape[0] - 8))
         assert rel(a_out[8:-8, 8:-8, 8:-8], want[8:-8, 8:-8, 8:-8]) < TOL, name
+
+
+# ---- the C++ drivers (drivers/*.cpp over include/*.h): self-validating like the reference's single/weak/strong ------
+def _run_driver(*args):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "drivers", args[0])
+    if not os.path.exists(exe):
+        pytest.fail(f"{exe} is not built: run __graft_entry__.build()")
+    r = subprocess.run([exe, *args[1:]], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("name", ["7pt", "mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt"])
+def test_cpp_single_driver_prints_result_match(name):
+    out = _run_driver("single", "-n", "64", "-s", name, "-r", "3")
+    assert "result match" in out and "Trans:" in out
+
+
+@pytest.mark.parametrize("name,ranks,dom", [("mpi7pt", 4, "32,24,40"), ("mpi25pt", 2, "32,32,32"), ("mpi125pt", 8, "16,24,16")])
+def test_cpp_weak_driver_validates_against_global_periodic_sweep(name, ranks, dom):
+    out = _run_driver("weak", "-s", dom, "-I", "2", "-g", str(ranks), "-S", name, "-v")
+    assert "result match" in out and "perf" in out and "Total of 42 parts" in out
+
+
+@pytest.mark.parametrize("name,ranks,d,s", [("mpi7pt", 3, 128, 32), ("mpi13pt", 1, 64, 32), ("mpi125pt", 2, 128, 64)])
+def test_cpp_strong_driver_validates_against_global_periodic_sweep(name, ranks, d, s):
+    out = _run_driver("strong", "-d", str(d), "-s", str(s), "-I", "2", "-g", str(ranks), "-S", name, "-v")
+    assert "result match" in out and "perf" in out
