@@ -243,16 +243,23 @@ class ExchangeView:
     Stands in for ExchangeView::exchange / BrickDecomp::exchange (brick-mpi.h:96-123, :466-495).  `peer_ptrs[r]` is the
     device address of rank r's storage as seen from THIS process (own pointer, or a CUDA-IPC mapping)."""
 
+    @staticmethod
+    def plan(decomp, step=BRICK):
+        """the pull plan as pure host data: one (peer rank, src byte offset in the PEER's storage, dst byte offset in
+        MINE, bytes) per ghost region -- ghost[i] <- skin[i] of rank_map[ghost[i].neighbor] (brick-mpi.h:476-485)"""
+        return [(decomp.rank_map[g.neighbor], s.pos * step * 8, g.pos * step * 8, g.len * step * 8)
+                for g, s in zip(decomp.ghost, decomp.skin)]
+
     def __init__(self, decomp, storage, peer_ptrs, my_rank=0):
-        segs = (Seg * len(decomp.ghost))()
+        plan = self.plan(decomp, storage.step)
+        segs = (Seg * len(plan))()
         self.remote_bytes = 0
-        for i, (g, s) in enumerate(zip(decomp.ghost, decomp.skin)):
-            peer = decomp.rank_map[g.neighbor]
-            segs[i].src = peer_ptrs[peer] + s.pos * storage.step * 8
-            segs[i].dst = storage.dat.ptr + g.pos * storage.step * 8
-            segs[i].bytes = g.len * storage.step * 8
+        for i, (peer, src_off, dst_off, nbytes) in enumerate(plan):
+            segs[i].src = peer_ptrs[peer] + src_off
+            segs[i].dst = storage.dat.ptr + dst_off
+            segs[i].bytes = nbytes
             if peer != my_rank:
-                self.remote_bytes += segs[i].bytes
+                self.remote_bytes += nbytes
         h = C.c_void_p()
         check(load().bk_xplan_create(C.byref(h), segs, len(decomp.ghost)))
         self._h = h
