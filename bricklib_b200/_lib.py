@@ -10,6 +10,7 @@ BK_OK = 0
 ST_7PT, ST_MPI7PT, ST_MPI13PT, ST_MPI25PT, ST_MPI125PT = range(5)
 STENCILS = {"7pt": 0, "mpi7pt": 1, "mpi13pt": 2, "mpi25pt": 3, "mpi125pt": 4}
 KERNEL_AUTO, KERNEL_BRICK, KERNEL_TILED = 0, 1, 2
+PART_ALL, PART_READY, PART_REST = 0, 1, 2
 IPC_HANDLE_BYTES = 64
 
 vp, sz, u64 = C.c_void_p, C.c_size_t, C.c_uint64
@@ -50,6 +51,7 @@ SIGNATURES = {
     "bk_memcpy_d2h": (C.c_int, [vp, vp, sz, vp]),
     "bk_memcpy_d2d": (C.c_int, [vp, vp, sz, vp]),
     "bk_stream_create": (C.c_int, [C.POINTER(vp)]),
+    "bk_stream_create_priority": (C.c_int, [C.POINTER(vp), C.c_int]),
     "bk_stream_destroy": (C.c_int, [vp]),
     "bk_stream_sync": (C.c_int, [vp]),
     "bk_device_sync": (C.c_int, []),
@@ -78,6 +80,7 @@ SIGNATURES = {
     "bk_copy_from_brick": (C.c_int, [lp, lp, lp, vp, vp, vp, sz, vp]),
     "bk_compare_brick": (C.c_int, [lp, lp, lp, vp, vp, vp, sz, C.c_double, C.POINTER(C.c_ulonglong), dp, vp]),
     "bk_stencil_apply": (C.c_int, [C.c_int, C.POINTER(Field), vp, up, up, up, dp, C.c_uint, vp]),
+    "bk_stencil_apply_part": (C.c_int, [C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp]),
     "bk_stencil_apply_list": (C.c_int, [C.c_int, C.POINTER(Field), vp, sz, dp, vp]),
     "bk_stencil_apply_multi": (C.c_int, [C.c_int, vp, C.c_uint, vp, up, up, up, dp, vp]),
     "bk_launch_count": (C.c_ulonglong, []),
@@ -86,6 +89,7 @@ SIGNATURES = {
     "bk_xplan_bytes": (sz, [vp]),
     "bk_xplan_run": (C.c_int, [vp, vp]),
     "bk_xplan_run_sync": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, u64, vp]),
+    "bk_xplan_run_gate": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, vp, u64, vp]),
     "bk_flags_signal": (C.c_int, [C.POINTER(vp), C.c_int, u64, vp]),
     "bk_flags_wait": (C.c_int, [C.POINTER(vp), C.c_int, u64, vp]),
     "bk_ipc_export": (C.c_int, [vp, C.c_char_p]),

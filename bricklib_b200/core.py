@@ -175,6 +175,14 @@ def stencil(stencil_id, grid, b_in, b_out, lo=None, hi=None, coeff=None, kernel=
                                   _coeff(coeff), kernel, stream))
 
 
+def stencil_part(stencil_id, grid, b_in, b_out, lo, hi, ready_lo, ready_hi, part, coeff=None, stream=None):
+    """one half of a split sweep (bk_stencil_apply_part): part = PART_READY (CTAs that read only bricks of the ready
+    box) or PART_REST (all the others)"""
+    f = _field(b_in, b_out)
+    check(load().bk_stencil_apply_part(stencil_id, C.byref(f), grid.dev.ptr, _u3(grid.dims), _u3(lo), _u3(hi),
+                                       _coeff(coeff), _u3(ready_lo), _u3(ready_hi), part, stream))
+
+
 def stencil_list(stencil_id, ids_dev, n, b_in, b_out, coeff=None, stream=None):
     f = _field(b_in, b_out)
     check(load().bk_stencil_apply_list(stencil_id, C.byref(f), ids_dev.ptr, n, _coeff(coeff), stream))
@@ -272,6 +280,12 @@ class ExchangeView:
         w = (C.c_void_p * max(1, len(wait_flags)))(*wait_flags)
         s = (C.c_void_p * max(1, len(signal_flags)))(*signal_flags)
         check(load().bk_xplan_run_sync(self._h, w, len(wait_flags), s, len(signal_flags), epoch, stream))
+
+    def exchange_gate(self, wait_flags, signal_flags, gate_ptr, epoch, stream=None):
+        """pull, then the kernel's last CTA stores `epoch` to the local gate and to the peers' done flags"""
+        w = (C.c_void_p * max(1, len(wait_flags)))(*wait_flags)
+        s = (C.c_void_p * max(1, len(signal_flags)))(*signal_flags)
+        check(load().bk_xplan_run_gate(self._h, w, len(wait_flags), s, len(signal_flags), gate_ptr, epoch, stream))
 
     def __del__(self):
         try:

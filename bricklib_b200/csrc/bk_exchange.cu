@@ -17,6 +17,7 @@ struct bk_xplan {
   unsigned long long nchunks = 0;
   size_t bytes = 0;
   uint64_t **flagbuf_dev = nullptr;  // scratch for flag pointer lists (64 wait + 64 signal)
+  unsigned long long *done_dev = nullptr;  // CTAs that finished, summed over all launches of this plan
 };
 
 namespace {
@@ -31,7 +32,8 @@ __device__ __forceinline__ void spin_until(const uint64_t *flag, uint64_t value)
 
 __global__ void __launch_bounds__(kThreads) k_xplan(const bk_seg_t *__restrict__ segs,
                                                    const unsigned long long *__restrict__ first, int nseg,
-                                                   unsigned long long nchunks, uint64_t *const *wait_flags, int nwait) {
+                                                   unsigned long long nchunks, uint64_t *const *wait_flags, int nwait,
+                                                   int nsignal, uint64_t *gate, unsigned long long *done) {
   if (nwait > 0) {
     if (threadIdx.x < nwait) spin_until(wait_flags[threadIdx.x], (uint64_t) (size_t) wait_flags[64]);
     __syncthreads();
@@ -55,6 +57,22 @@ __global__ void __launch_bounds__(kThreads) k_xplan(const bk_seg_t *__restrict__
       for (int u = 0; u < 4; ++u) dst[threadIdx.x + u * kThreads] = v[u];
     } else {
       for (size_t x = threadIdx.x; x < n16; x += kThreads) dst[x] = src[x];
+    }
+  }
+  if (done) {
+    // the last CTA to finish publishes completion: the local gate (read by the gated sweep's producer warps) and the
+    // peers' "done reading your skin" flags.  flag list layout: [65, 65+nsignal) = signal pointers, [64] = epoch
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = ((atomicAdd(done, 1ull) + 1ull) % gridDim.x) == 0ull;
+    __syncthreads();
+    if (last) {
+      const uint64_t epoch = (uint64_t) (size_t) wait_flags[64];
+      __threadfence_system();
+      if (threadIdx.x == 0 && gate) *reinterpret_cast<volatile uint64_t *>(gate) = epoch;
+      if ((int) threadIdx.x < nsignal) *reinterpret_cast<volatile uint64_t *>(wait_flags[65 + threadIdx.x]) = epoch;
+      __threadfence_system();
     }
   }
 }
@@ -83,12 +101,14 @@ int sm_count() {
   return n;
 }
 
-int launch_copy(bk_xplan *p, uint64_t *const *wait_dev, int nwait, cudaStream_t s) {
-  if (p->nchunks == 0 && nwait == 0) return BK_OK;
+int launch_copy(bk_xplan *p, uint64_t *const *wait_dev, int nwait, cudaStream_t s, int nsignal = 0,
+                uint64_t *gate = nullptr, bool publish = false) {
+  if (p->nchunks == 0 && nwait == 0 && !publish) return BK_OK;
   unsigned long long want = p->nchunks ? p->nchunks : 1;
   const unsigned long long cap = (unsigned long long) sm_count() * 8;
   const unsigned grid = (unsigned) (want < cap ? want : cap);
-  k_xplan<<<grid, kThreads, 0, s>>>(p->segs_dev, p->chunk_first_dev, p->nseg, p->nchunks, wait_dev, nwait);
+  k_xplan<<<grid, kThreads, 0, s>>>(p->segs_dev, p->chunk_first_dev, p->nseg, p->nchunks, wait_dev, nwait, nsignal, gate,
+                                    publish ? p->done_dev : nullptr);
   BK_LAUNCHED();
   return BK_OK;
 }
@@ -118,6 +138,8 @@ int bk_xplan_create(bk_xplan_t **out, const bk_seg_t *segs, int nseg) {
   BK_CUDA(cudaMalloc(&p->chunk_first_dev, sizeof(unsigned long long) * (nseg + 1)));
   BK_CUDA(cudaMemcpy(p->chunk_first_dev, first.data(), sizeof(unsigned long long) * (nseg + 1), cudaMemcpyHostToDevice));
   BK_CUDA(cudaMalloc(&p->flagbuf_dev, sizeof(uint64_t *) * 192));
+  BK_CUDA(cudaMalloc(&p->done_dev, sizeof(unsigned long long)));
+  BK_CUDA(cudaMemset(p->done_dev, 0, sizeof(unsigned long long)));
   *out = p;
   return BK_OK;
 }
@@ -127,6 +149,7 @@ int bk_xplan_destroy(bk_xplan_t *p) {
   cudaFree(p->segs_dev);
   cudaFree(p->chunk_first_dev);
   cudaFree(p->flagbuf_dev);
+  cudaFree(p->done_dev);
   delete p;
   return BK_OK;
 }
@@ -156,6 +179,19 @@ int bk_xplan_run_sync(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwai
     BK_LAUNCHED();
   }
   return BK_OK;
+}
+
+int bk_xplan_run_gate(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwait, uint64_t *const *signal_flags,
+                      int nsignal, uint64_t *gate, uint64_t epoch, void *stream) {
+  BK_REQUIRE(p, "null plan");
+  BK_REQUIRE(nwait >= 0 && nwait <= 64 && nsignal >= 0 && nsignal <= 64, "at most 64 flags each");
+  cudaStream_t s = (cudaStream_t) stream;
+  uint64_t *host[130] = {nullptr};
+  for (int i = 0; i < nwait; ++i) host[i] = const_cast<uint64_t *>(wait_flags[i]);
+  host[64] = (uint64_t *) (size_t) epoch;
+  for (int i = 0; i < nsignal; ++i) host[65 + i] = signal_flags[i];
+  BK_CUDA(cudaMemcpyAsync(p->flagbuf_dev, host, sizeof(host), cudaMemcpyHostToDevice, s));
+  return launch_copy(p, p->flagbuf_dev, nwait, s, nsignal, gate, true);
 }
 
 int bk_flags_signal(uint64_t *const *flags, int n, uint64_t value, void *stream) {

@@ -72,6 +72,15 @@ int bk_stream_create(void **stream) {
   *stream = (void *) s;
   return BK_OK;
 }
+int bk_stream_create_priority(void **stream, int high) {
+  BK_REQUIRE(stream, "null");
+  int least = 0, greatest = 0;  // numerically lower = higher priority
+  BK_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+  cudaStream_t s;
+  BK_CUDA(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high ? greatest : least));
+  *stream = (void *) s;
+  return BK_OK;
+}
 int bk_stream_destroy(void *stream) {
   BK_CUDA(cudaStreamDestroy((cudaStream_t) stream));
   return BK_OK;

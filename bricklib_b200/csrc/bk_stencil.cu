@@ -79,7 +79,8 @@ int cube_coef_for(int stencil, CubeCoef *o) {
 
 // implemented in bk_stencil_tiled.cu
 int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, unsigned nsub, const unsigned *grid,
-                 const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff, cudaStream_t s);
+                 const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff, cudaStream_t s,
+                 int part = BK_PART_ALL, const unsigned *ready_lo = nullptr, const unsigned *ready_hi = nullptr);
 
 }  // namespace bk
 
@@ -223,6 +224,20 @@ int bk_stencil_apply(int stencil, const bk_field_t *f, const unsigned *grid, con
   }
   Select sel = {grid, nullptr, nullptr, gdims[0], gdims[1], {lo[0], lo[1], lo[2]}, 0};
   return launch_brick(stencil, sel, *f, dim3(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]), coeff, s);
+}
+
+int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid, const unsigned *gdims,
+                          const unsigned *lo, const unsigned *hi, const double *coeff, const unsigned *ready_lo,
+                          const unsigned *ready_hi, int part, void *stream) {
+  BK_REQUIRE(stencil >= 0 && stencil < BK_ST_COUNT, "unknown stencil id");
+  BK_REQUIRE(f && f->adj && f->in && f->out && grid && gdims && lo && hi && ready_lo && ready_hi, "null argument");
+  BK_REQUIRE(part == BK_PART_READY || part == BK_PART_REST, "part must be BK_PART_READY or BK_PART_REST");
+  BK_REQUIRE(f->in_step >= 512 && f->out_step >= 512, "brick step smaller than a brick");
+  BK_REQUIRE(f->in != f->out, "in-place sweep is not defined");
+  BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
+  // only the marching kernel has the split enumeration; the caller falls back to whole-box launches on EUNSUPPORTED
+  return bk::launch_tiled(stencil, *f, nullptr, 1, grid, gdims, lo, hi, coeff, (cudaStream_t) stream, part, ready_lo,
+                          ready_hi);
 }
 
 int bk_stencil_apply_list(int stencil, const bk_field_t *f, const unsigned *ids, size_t n, const double *coeff,

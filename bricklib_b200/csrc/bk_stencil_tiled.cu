@@ -40,6 +40,14 @@ struct TiledArgs {
   int ntx;  // tiles along i
   int kl;   // brick layers per k segment
   const bk_field_t *multi;  // strong-scaling launch: per-subdomain fields (device array), subdomain = blockIdx.z
+  // CTA enumeration: blockIdx.x runs through up to 6 boxes of the (tile i, tile j, k segment) space in order.  A plain
+  // launch has one box.  A split launch (bk_stencil_apply_part) runs either the CTAs whose whole read footprint lies
+  // inside the caller's "ready" brick box, or all the others -- the first part overlaps the ghost exchange, the second
+  // is enqueued behind it, and both use the tile decomposition of the full box (no thin slab launches).
+  int nbox;
+  struct Box {
+    int lo[3], dim[3], first;
+  } box[6];
 };
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------------
@@ -77,8 +85,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
 }
 
 // ---- compile-time geometry --------------------------------------------------------------------------------------
-template <int R_, int YT_, int TI_, int TJ_, int G_, int D_, int MAXREG_ = 255, int NPW_ = 1, bool CUBE_ = false>
+template <int R_, int YT_, int TI_, int TJ_, int G_, int D_, int MAXREG_ = 255, int NPW_ = 1, bool CUBE_ = false,
+          int CREG_ = 0, int PREG_ = 40, int FLAGS_ = 0>
 struct Cfg {
+  // CREG > 0: register re-balancing between the roles (setmaxnreg, warpgroup granular): the kernel starts with
+  // 65536/NT registers per thread, the producer warpgroup shrinks to PREG and the consumer warpgroups grow to CREG
+  [[maybe_unused]] static constexpr int CREG = CREG_, PREG = PREG_, FLAGS = FLAGS_;
   static constexpr bool CUBE = CUBE_;                 // (2R+1)^3 cube stencil instead of a star
   using Coef = typename std::conditional<CUBE_, bk::CubeCoef, bk::StarCoef>::type;
   static constexpr int R = R_, YT = YT_, TI = TI_, TJ = TJ_, G = G_, D = D_;
@@ -95,9 +107,10 @@ struct Cfg {
   static constexpr int NJH = CUBE ? TI + 2 : TI;      // j-halo columns: a cube stencil also needs the corner bricks
   static constexpr int NCOPY = TI * TJ + 2 * TJ + 2 * NJH;  // copy jobs per stage (j-halo jobs issue G copies)
   static constexpr int JOBS = (NCOPY + 32 * NPW - 1) / (32 * NPW);
-  static constexpr int MAXREG = MAXREG_;              // register cap (chosen so that the intended CTAs/SM fit)
+  [[maybe_unused]] static constexpr int MAXREG = MAXREG_;              // register cap (chosen so that the intended CTAs/SM fit)
   static constexpr size_t SMEM = (size_t) D * STAGE + 2 * D * 8 + 128;
   static_assert(8 % G == 0 && 8 % YT == 0 && TI % 2 == 0 && 2 * R <= 8, "geometry");
+  static_assert(CREG == 0 || (NCW % 4 == 0 && NPW == 4 && NCONS * CREG + 128 * PREG <= 65536), "setmaxnreg needs warpgroups");
   // SW is even, so the bank half of a slot depends on its column only: a quarter warp (4 x-pairs of 2 i-adjacent
   // bricks) reads 8 distinct 16-B bank groups
   __host__ __device__ static constexpr int slotoff(int bi, int bj) { return (bj * SW + bi) * SLOTP; }
@@ -121,9 +134,15 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
     fin = f.in, fout = f.out, in_step = f.in_step, out_step = f.out_step;
   }
   const int tid = threadIdx.x;
-  const int tx = blockIdx.x % a.ntx, ty = blockIdx.x / a.ntx;
+  int bq = 0, brel = (int) blockIdx.x;
+  while (bq + 1 < a.nbox && brel >= a.box[bq + 1].first) ++bq;
+  brel -= a.box[bq].first;
+  const int tx = a.box[bq].lo[0] + brel % a.box[bq].dim[0];
+  brel /= a.box[bq].dim[0];
+  const int ty = a.box[bq].lo[1] + brel % a.box[bq].dim[1];
+  const int tseg = a.box[bq].lo[2] + brel / a.box[bq].dim[1];
   const int i0 = a.lo[0] + tx * TI, j0 = a.lo[1] + ty * TJ;
-  const int kb0 = a.lo[2] + blockIdx.y * a.kl;
+  const int kb0 = a.lo[2] + tseg * a.kl;
   const int nl = min(a.kl, a.hi[2] - kb0);  // brick layers in this segment
   const int P = nl * 8 + 2 * RUP;            // planes streamed; plane t is absolute plane kb0*8 - RUP + t
   const int NS = P / G;
@@ -137,6 +156,12 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
   }
   __syncthreads();
 
+  if constexpr (C::CREG > 0) {
+    if (tid >= C::NCONS)
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::PREG));
+    else
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::CREG));
+  }
   if (tid >= C::NCONS) {
     // ================================================ producer warp ============================================
     // jobs are dealt round-robin over the producer warps, then over lanes
@@ -389,6 +414,27 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
               }
             }
             double ax = fma(cf.c0, v[r].x, acc[s0][r].x), ay = fma(cf.c0, v[r].y, acc[s0][r].y);
+            if constexpr (C::FLAGS & 1) {
+              // shorter dependency chains: the i taps are summed on their own and added at the end
+              double ix = cf.cp[0][0] * line[R + 1], iy = cf.cp[0][0] * line[R + 2];
+              ix = fma(cf.cm[0][0], line[R - 1], ix), iy = fma(cf.cm[0][0], line[R], iy);
+#pragma unroll
+              for (int d = 2; d <= R; ++d) {
+                ix = fma(cf.cp[0][d - 1], line[R + d], ix);
+                iy = fma(cf.cp[0][d - 1], line[R + 1 + d], iy);
+                ix = fma(cf.cm[0][d - 1], line[R - d], ix);
+                iy = fma(cf.cm[0][d - 1], line[R + 1 - d], iy);
+              }
+#pragma unroll
+              for (int d = 1; d <= R; ++d) {
+                ax = fma(cf.cp[1][d - 1], rows[R + r + d].x, ax);
+                ay = fma(cf.cp[1][d - 1], rows[R + r + d].y, ay);
+                ax = fma(cf.cm[1][d - 1], rows[R + r - d].x, ax);
+                ay = fma(cf.cm[1][d - 1], rows[R + r - d].y, ay);
+              }
+              acc[s0][r].x = ax + ix, acc[s0][r].y = ay + iy;
+              continue;
+            }
 #pragma unroll
             for (int d = 1; d <= R; ++d) {
               ax = fma(cf.cp[0][d - 1], line[R + d], ax);
@@ -446,10 +492,18 @@ __global__ void __launch_bounds__(C::NT) __maxnreg__(C::MAXREG) k_star_capped(co
   march_body<C>(a, cf);
 }
 
+// register re-balancing (Cfg::CREG > 0): ptxas needs the register count at entry, i.e. min-blocks in the launch bounds
 template <class C>
-int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, unsigned nsub = 1) {
+__global__ void __launch_bounds__(C::NT, 1) k_star_rebal(const __grid_constant__ TiledArgs a,
+                                                         const __grid_constant__ typename C::Coef cf) {
+  march_body<C>(a, cf);
+}
+
+template <class C>
+int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, unsigned nsub, int part,
+               const int *rdy_lo, const int *rdy_hi) {
   void (*kern)(const TiledArgs, const typename C::Coef);
-  if constexpr (C::MAXREG < 255) kern = k_star_capped<C>; else kern = k_star<C>;
+  if constexpr (C::CREG > 0) kern = k_star_rebal<C>; else if constexpr (C::MAXREG < 255) kern = k_star_capped<C>; else kern = k_star<C>;
   BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
   if (getenv("BK_DEBUG")) {
     cudaFuncAttributes fa;
@@ -490,7 +544,49 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, 
   a.kl = (nz + best_seg - 1) / best_seg;
   if (const char *e = getenv("BK_STAR_KL")) a.kl = atoi(e) > 0 ? atoi(e) : a.kl;  // developer knob
   const int segs = (nz + a.kl - 1) / a.kl;
-  dim3 grid((unsigned) (a.ntx * nty), (unsigned) segs, nsub);
+  // CTA boxes.  "inner" = CTAs whose whole read footprint (tile + 1 brick all round) lies in the ready box
+  int in_lo[3] = {0, 0, 0}, in_hi[3] = {0, 0, 0};
+  const int ext[3] = {a.ntx, nty, segs};
+  if (part != BK_PART_ALL) {
+    const int T[2] = {C::TI, C::TJ};
+    for (int d = 0; d < 2; ++d) {
+      int l = 0, h = ext[d];
+      while (l < h && a.lo[d] + l * T[d] - 1 < rdy_lo[d]) ++l;
+      while (h > l && a.lo[d] + (h - 1) * T[d] + T[d] + 1 > rdy_hi[d]) --h;
+      in_lo[d] = l, in_hi[d] = h;
+    }
+    int l = 0, h = segs;
+    auto seg_end = [&](int q) { return a.lo[2] + (q * a.kl + a.kl < nz ? q * a.kl + a.kl : nz); };
+    while (l < h && a.lo[2] + l * a.kl - 1 < rdy_lo[2]) ++l;
+    while (h > l && seg_end(h - 1) + 1 > rdy_hi[2]) --h;
+    in_lo[2] = l, in_hi[2] = h;
+  }
+  a.nbox = 0;
+  int first = 0;
+  auto add_box = [&](int x0, int x1, int y0, int y1, int z0, int z1) {
+    if (x1 <= x0 || y1 <= y0 || z1 <= z0) return;
+    TiledArgs::Box &b = a.box[a.nbox++];
+    b.lo[0] = x0, b.lo[1] = y0, b.lo[2] = z0, b.dim[0] = x1 - x0, b.dim[1] = y1 - y0, b.dim[2] = z1 - z0;
+    b.first = first;
+    first += b.dim[0] * b.dim[1] * b.dim[2];
+  };
+  const bool has_inner = in_hi[0] > in_lo[0] && in_hi[1] > in_lo[1] && in_hi[2] > in_lo[2];
+  if (part == BK_PART_ALL) {
+    add_box(0, ext[0], 0, ext[1], 0, ext[2]);
+  } else if (part == BK_PART_READY) {
+    if (has_inner) add_box(in_lo[0], in_hi[0], in_lo[1], in_hi[1], in_lo[2], in_hi[2]);
+  } else if (!has_inner) {
+    add_box(0, ext[0], 0, ext[1], 0, ext[2]);
+  } else {
+    add_box(0, ext[0], 0, ext[1], 0, in_lo[2]);                          // segments below / above
+    add_box(0, ext[0], 0, ext[1], in_hi[2], ext[2]);
+    add_box(0, ext[0], 0, in_lo[1], in_lo[2], in_hi[2]);                 // tile rows before / after
+    add_box(0, ext[0], in_hi[1], ext[1], in_lo[2], in_hi[2]);
+    add_box(0, in_lo[0], in_lo[1], in_hi[1], in_lo[2], in_hi[2]);        // tile columns left / right
+    add_box(in_hi[0], ext[0], in_lo[1], in_hi[1], in_lo[2], in_hi[2]);
+  }
+  if (first == 0) return BK_OK;
+  dim3 grid((unsigned) first, 1, nsub);
   kern<<<grid, C::NT, C::SMEM, s>>>(a, cf);
   BK_LAUNCHED();
   return BK_OK;
@@ -501,7 +597,8 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, 
 namespace bk {
 
 int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, unsigned nsub, const unsigned *grid,
-                 const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff, cudaStream_t s) {
+                 const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff, cudaStream_t s,
+                 int part, const unsigned *ready_lo, const unsigned *ready_hi) {
   if (!multi_dev && (((size_t) f.in | (size_t) f.out) & 15 || (f.in_step & 1) || (f.out_step & 1))) return BK_EUNSUPPORTED;
   TiledArgs a;
   a.in = f.in, a.out = f.out, a.in_step = f.in_step, a.out_step = f.out_step, a.grid = grid;
@@ -509,31 +606,37 @@ int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, 
   for (int d = 0; d < 3; ++d) a.lo[d] = (int) lo[d], a.hi[d] = (int) hi[d];
   a.ntx = a.kl = 0;
   a.multi = multi_dev;
+  a.nbox = 0;
+  int rdy_lo[3] = {0, 0, 0}, rdy_hi[3] = {0, 0, 0};
+  if (part != BK_PART_ALL)
+    for (int d = 0; d < 3; ++d) rdy_lo[d] = (int) ready_lo[d], rdy_hi[d] = (int) ready_hi[d];
   int v = 0;
   if (const char *e = getenv("BK_STAR_VARIANT")) v = atoi(e);  // developer knob: one alternative geometry per stencil
   // Geometries (R, YT, TI, TJ, G, D, register cap, producer warps), chosen on B200 -- see DESIGN.md section 4:
   //   radius 1/2: 4x4-brick tiles, 4 consumer warps + 2 producer warps, 2 CTAs per SM (<= 128 registers)
-  //   radius 4  : 2 rows per thread (8 consumer warps) + 4 producer warps, 5-stage ring, 1 CTA per SM
-  //   cube      : 6x4-brick tiles, 12 consumer warps + 4 producer warps, 128 registers, 1 CTA per SM
+  //   radius 4  : 6x4-brick tiles, 2 rows per thread (12 consumer warps at 152 registers) + 4 producer warps (40
+  //               registers, setmaxnreg), 3-stage ring (130 KB: leaves L1 for the id/adjacency reads), 1 CTA per SM
+  //   cube      : same shape: 6x4-brick tiles, 12 consumer warps (152 registers) + 4 producer warps, 1 CTA per SM
   if (stencil == BK_ST_MPI125PT) {
     CubeCoef cc;
     if (cube_coef_for(stencil, &cc) < 0) return BK_EINVAL;
-    if (v == 1) return launch_cfg<Cfg<2, 2, 4, 4, 2, 4, 255, 4, true>>(a, cc, s, nsub);
-    return launch_cfg<Cfg<2, 2, 6, 4, 2, 3, 128, 4, true>>(a, cc, s, nsub);
+    if (v == 1) return launch_cfg<Cfg<2, 2, 6, 4, 2, 3, 128, 4, true>>(a, cc, s, nsub, part, rdy_lo, rdy_hi);
+    return launch_cfg<Cfg<2, 2, 6, 4, 2, 3, 255, 4, true, 152, 40>>(a, cc, s, nsub, part, rdy_lo, rdy_hi);
   }
   StarCoef sc;
   const int r = star_coef_for(stencil, coeff, &sc);
   if (r < 0) return BK_EINVAL;
   if (r == 1) {
-    if (v == 1) return launch_cfg<Cfg<1, 4, 6, 4, 1, 4, 128, 2>>(a, sc, s, nsub);
-    return launch_cfg<Cfg<1, 4, 4, 4, 2, 3, 255, 2>>(a, sc, s, nsub);
+    if (v == 1) return launch_cfg<Cfg<1, 4, 6, 4, 1, 4, 128, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+    return launch_cfg<Cfg<1, 4, 4, 4, 2, 3, 255, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
   }
   if (r == 2) {
-    if (v == 1) return launch_cfg<Cfg<2, 4, 6, 4, 1, 4, 128, 2>>(a, sc, s, nsub);
-    return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 128, 2>>(a, sc, s, nsub);
+    if (v == 1) return launch_cfg<Cfg<2, 4, 6, 4, 1, 4, 128, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+    return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 128, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
   }
-  if (v == 1) return launch_cfg<Cfg<4, 4, 4, 4, 2, 5, 255, 4>>(a, sc, s, nsub);
-  return launch_cfg<Cfg<4, 2, 4, 4, 2, 5, 255, 4>>(a, sc, s, nsub);
+  if (v == 1) return launch_cfg<Cfg<4, 2, 4, 4, 2, 5, 255, 4>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+  if (v == 2) return launch_cfg<Cfg<4, 4, 8, 4, 2, 4, 255, 4, false, 232, 40>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+  return launch_cfg<Cfg<4, 2, 6, 4, 2, 3, 255, 4, false, 152, 40>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
 }
 
 }  // namespace bk

@@ -4,9 +4,10 @@ Per exchange period:  ghost <- neighbours' skin  (one fused pull kernel over the
 reached through CUDA-IPC mappings over NVLink; self-neighbours are ordinary device copies in the same kernel), then
 ST_ITER sweeps ping-ponging in -> out -> in.  The last sweep of a period skips the ghost shell (weak/main.cpp:209).
 
-Overlap (25-point stencil, ST_ITER = 2, matters most): the inner bricks [2,n-2)^3 never read ghost bricks, so their
-first sweep runs on the compute stream WHILE the pull kernel runs on the comm stream; the six boundary slabs follow
-once the pull has finished.
+Overlap: the first sweep of a period is split in two launches over the SAME tile decomposition of the whole grid
+(bk_stencil_apply_part): the CTAs that read only the subdomain's own bricks start at once on the compute stream, the
+CTAs that touch the ghost shell run on the high-priority exchange stream right behind the pull kernel.  Both halves
+run concurrently; later sweeps wait for both.  Stream-ordered only: nothing spins on the device for the sweep.
 """
 import ctypes as C
 
@@ -74,7 +75,7 @@ class WeakDomain:
 
     def enable_overlap(self):
         s = C.c_void_p()
-        check(load().bk_stream_create(C.byref(s)))
+        check(load().bk_stream_create_priority(C.byref(s), 1))
         self.comm_stream = s
         self.ev_comm, self.ev_comp = core.Event(), core.Event()
 
@@ -105,17 +106,20 @@ class WeakDomain:
     def _sweep(self, src, dst, lo, hi, stream):
         core.stencil(self.stencil, self.grid, self.bricks[src], self.bricks[dst], lo, hi, None, self.kernel, stream)
 
-    def _exchange(self, stream):
-        if self.hs is None or not self.peers:
+    def _exchange(self, stream, fused_signal=False):
+        hs, e = self.hs, self.epoch
+        if hs is None or not self.peers:
             self.view.exchange(stream)
             return
-        hs, e = self.hs, self.epoch
         # tell every peer my skin is final, pull theirs once they say the same, then tell them I am done reading
         sig = (C.c_void_p * len(self.peers))(*[hs.ready_flag_on(p, self.rank) for p in self.peers])
         check(load().bk_flags_signal(sig, len(self.peers), e, stream))
         waits = [hs.ready_flag_on(self.rank, p) for p in self.peers]
         dones = [hs.done_flag_on(p, self.rank) for p in self.peers]
-        self.view.exchange_sync(waits, dones, e, stream)
+        if fused_signal:   # the pull kernel's last CTA raises the done flags itself
+            self.view.exchange_gate(waits, dones, None, e, stream)
+        else:
+            self.view.exchange_sync(waits, dones, e, stream)
 
     def _wait_peers_done(self, stream):
         if self.hs is None or not self.peers:
@@ -141,21 +145,25 @@ class WeakDomain:
             cs = self.comm_stream
             self.ev_comp.record(stream)
             check(load().bk_stream_wait_event(cs, self.ev_comp.h))  # previous period's sweeps wrote the skin
-            self._exchange(cs)
-            self.ev_comm.record(cs)
+            self._exchange(cs, fused_signal=True)
             g = GZ // 8
-            in_lo, in_hi = (2 * g,) * 3, tuple(x - 2 * g for x in t)
-            self._sweep(0, 1, in_lo, in_hi, stream)  # inner bricks: no ghost input, overlaps the pull
+            own_lo, own_hi = (g,) * 3, tuple(x - g for x in t)      # bricks that are final without the exchange
+            split = self.kernel != _lib.KERNEL_BRICK and self.st_iter > 1
+            if split:
+                try:
+                    core.stencil_part(self.stencil, self.grid, self.bricks[0], self.bricks[1], full_lo, full_hi, own_lo,
+                                      own_hi, _lib.PART_READY, None, stream)
+                    core.stencil_part(self.stencil, self.grid, self.bricks[0], self.bricks[1], full_lo, full_hi, own_lo,
+                                      own_hi, _lib.PART_REST, None, cs)
+                except _lib.BrickError:
+                    split = False
+            self.ev_comm.record(cs)
             check(load().bk_stream_wait_event(stream, self.ev_comm.h))
-            first_hi = t if self.st_iter > 1 else tuple(x - g for x in t)
-            first_lo = (0, 0, 0) if self.st_iter > 1 else (g,) * 3
-            for lo, hi in shell_boxes(first_lo, first_hi, in_lo, in_hi):
-                self._sweep(0, 1, lo, hi, stream)
-            for s in range(1, self.st_iter):
+            for s in range(0 if not split else 1, self.st_iter):
                 last = s == self.st_iter - 1
                 if s == 1:
                     self._wait_peers_done(stream)
-                lo, hi = ((g,) * 3, tuple(x - g for x in t)) if last else (full_lo, full_hi)
+                lo, hi = (own_lo, own_hi) if last else (full_lo, full_hi)
                 self._sweep(s % 2, 1 - s % 2, lo, hi, stream)
         return load().bk_launch_count() - n0
 

@@ -57,6 +57,7 @@ int bk_memcpy_h2d(void *dev, const void *host, size_t bytes, void *stream);
 int bk_memcpy_d2h(void *host, const void *dev, size_t bytes, void *stream);
 int bk_memcpy_d2d(void *dst, const void *src, size_t bytes, void *stream);
 int bk_stream_create(void **stream);
+int bk_stream_create_priority(void **stream, int high); /* high != 0: the device's highest priority (exchange stream) */
 int bk_stream_destroy(void *stream);
 int bk_stream_sync(void *stream);
 int bk_device_sync(void);
@@ -132,6 +133,19 @@ typedef struct {
  * single/cpu.cpp:11-17), ignored (may be NULL) otherwise.  Asynchronous on `stream`. */
 int bk_stencil_apply(int stencil, const bk_field_t *f, const unsigned *grid_dev, const unsigned *gdims,
                      const unsigned *lo, const unsigned *hi, const double *coeff_host, unsigned flags, void *stream);
+/* Split sweep for overlapping the ghost exchange (replaces the blocking exchange-then-compute order of
+ * weak/main.cu:251-282).  The bricks inside the half-open box [ready_lo,ready_hi) are final already (the subdomain's own
+ * bricks); the others (the ghost shell) are final once the exchange has finished.  part = BK_PART_READY launches the
+ * CTAs of the box's tile decomposition that read only ready bricks, BK_PART_REST all the other CTAs; together they
+ * cover [lo,hi) exactly once, with the same tiles as a whole-box launch (no thin slab launches).  Enqueue READY on the
+ * compute stream at once and REST on a stream that waits for the exchange.  BK_EUNSUPPORTED when the storage layout
+ * rules out the marching kernel (use bk_stencil_apply after the exchange instead). */
+#define BK_PART_ALL 0
+#define BK_PART_READY 1
+#define BK_PART_REST 2
+int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid_dev, const unsigned *gdims,
+                          const unsigned *lo, const unsigned *hi, const double *coeff_host, const unsigned *ready_lo,
+                          const unsigned *ready_hi, int part, void *stream);
 /* same over an explicit list of brick ids (inner / skin / ghost lists for overlap; any adjacency-defined set) */
 int bk_stencil_apply_list(int stencil, const bk_field_t *f, const unsigned *ids_dev, size_t n,
                           const double *coeff_host, void *stream);
@@ -161,6 +175,10 @@ size_t bk_xplan_bytes(const bk_xplan_t *plan);
 int bk_xplan_run(bk_xplan_t *plan, void *stream);
 int bk_xplan_run_sync(bk_xplan_t *plan, const uint64_t *const *wait_flags, int nwait, uint64_t *const *signal_flags,
                       int nsignal, uint64_t epoch, void *stream);
+/* same, but the LAST CTA of the pull kernel itself publishes completion: it stores epoch to the signal flags and to
+ * `gate` (optional extra flag in local device memory) -- no separate signal launch. */
+int bk_xplan_run_gate(bk_xplan_t *plan, const uint64_t *const *wait_flags, int nwait, uint64_t *const *signal_flags,
+                      int nsignal, uint64_t *gate, uint64_t epoch, void *stream);
 /* tiny kernels for the handshake on a stream: store `value` to n flags / spin until n flags >= value */
 int bk_flags_signal(uint64_t *const *flags, int n, uint64_t value, void *stream);
 int bk_flags_wait(const uint64_t *const *flags, int n, uint64_t value, void *stream);
