@@ -120,27 +120,16 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
   ExchangeView ev = bDecomp.exchangeView(bStorage_dev, S.storage_ptr);
 
   void *comm_stream, *evDone, *evX, *c0, *c1, *x0, *x1;
-  bkCheck(bk_stream_create(&comm_stream));
+  bkCheck(bk_stream_create_priority(&comm_stream, 1));
   for (void **e : {&evDone, &evX, &c0, &c1, &x0, &x1}) bkCheck(bk_event_create(e));
   const std::vector<long> full_lo = {0, 0, 0}, full_hi = strideb;
   const long g = GZ / TILE;
-  const std::vector<long> in_lo = {2 * g, 2 * g, 2 * g}, in_hi = {strideb[0] - 2 * g, strideb[1] - 2 * g, strideb[2] - 2 * g};
   const std::vector<long> skip_lo = {g, g, g}, skip_hi = {strideb[0] - g, strideb[1] - g, strideb[2] - g};
   double calctime = 0, calltime = 0, waittime = 0;
 
   auto sweep = [&](int s, const std::vector<long> &lo, const std::vector<long> &hi) {
     brickStencil(st->id, grid_dev, strideb, (s % 2) ? bOut_dev : bIn_dev, (s % 2) ? bIn_dev : bOut_dev, lo, hi, nullptr, nullptr);
   };
-  // six slabs of [lo,hi) minus [in_lo,in_hi)
-  auto shell = [&](int s, const std::vector<long> &lo, const std::vector<long> &hi) {
-    if (in_lo[2] > lo[2]) sweep(s, lo, {hi[0], hi[1], in_lo[2]});
-    if (hi[2] > in_hi[2]) sweep(s, {lo[0], lo[1], in_hi[2]}, hi);
-    if (in_lo[1] > lo[1]) sweep(s, {lo[0], lo[1], in_lo[2]}, {hi[0], in_lo[1], in_hi[2]});
-    if (hi[1] > in_hi[1]) sweep(s, {lo[0], in_hi[1], in_lo[2]}, {hi[0], hi[1], in_hi[2]});
-    if (in_lo[0] > lo[0]) sweep(s, {lo[0], in_lo[1], in_lo[2]}, {in_lo[0], in_hi[1], in_hi[2]});
-    if (hi[0] > in_hi[0]) sweep(s, {in_hi[0], in_lo[1], in_lo[2]}, {hi[0], in_hi[1], in_hi[2]});
-  };
-
   auto brick_func = [&]() {
     // every rank's previous sweeps are complete before anyone pulls
     bkCheck(bk_event_record(evDone, nullptr));
@@ -153,10 +142,20 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     ev.exchange(comm_stream);
     bkCheck(bk_event_record(evX, comm_stream));
     bkCheck(bk_event_record(c0, nullptr));
+    // sweep 0 in two launches over the same tiles: CTAs that read only my own bricks overlap the pull (compute
+    // stream), the CTAs that touch the ghost shell follow the pull on the high-priority exchange stream
     const bool single_sweep = st->st_iter == 1;
-    sweep(0, in_lo, in_hi);  // inner bricks read no ghost brick: overlaps the pull
-    bkCheck(bk_stream_wait_event(nullptr, evX));
-    shell(0, single_sweep ? skip_lo : full_lo, single_sweep ? skip_hi : full_hi);
+    const std::vector<long> &lo0 = single_sweep ? skip_lo : full_lo, &hi0 = single_sweep ? skip_hi : full_hi;
+    if (brickStencilPart(st->id, grid_dev, strideb, bIn_dev, bOut_dev, lo0, hi0, skip_lo, skip_hi, BK_PART_READY, nullptr,
+                         nullptr)) {
+      brickStencilPart(st->id, grid_dev, strideb, bIn_dev, bOut_dev, lo0, hi0, skip_lo, skip_hi, BK_PART_REST, nullptr,
+                       comm_stream);
+      bkCheck(bk_event_record(evX, comm_stream));
+      bkCheck(bk_stream_wait_event(nullptr, evX));
+    } else {
+      bkCheck(bk_stream_wait_event(nullptr, evX));
+      sweep(0, lo0, hi0);
+    }
     calltime += omp_get_wtime() - t0;
     // sweep 1 overwrites storage 0, whose skin the neighbours are pulling: wait until every pull has finished
     bkCheck(bk_event_sync(evX));

@@ -142,6 +142,23 @@ void brickStencil(int stencil, const unsigned *grid_dev, const std::vector<long>
   const unsigned h[3] = {(unsigned) hi[0], (unsigned) hi[1], (unsigned) hi[2]};
   bkCheck(bk_stencil_apply(stencil, &f, grid_dev, g, l, h, coeff, kernel, stream));
 }
+/// One half of a split sweep over [lo,hi) (bk_stencil_apply_part): `part` = BK_PART_READY launches the CTAs that read only
+/// bricks of [ready_lo,ready_hi) (final before the ghost exchange), BK_PART_REST all the others.  Returns false when the
+/// storage layout rules the marching kernel out (then sweep the whole box after the exchange instead).
+template <typename T>
+bool brickStencilPart(int stencil, const unsigned *grid_dev, const std::vector<long> &gdims, T &bIn, T &bOut,
+                      const std::vector<long> &lo, const std::vector<long> &hi, const std::vector<long> &ready_lo,
+                      const std::vector<long> &ready_hi, int part, const bElem *coeff = nullptr, void *stream = nullptr) {
+  bk_field_t f = {&bIn.bInfo->adj[0][0], bIn.dat, bIn.step, bOut.dat, bOut.step};
+  unsigned g[3], l[3], h[3], rl[3], rh[3];
+  for (int d = 0; d < 3; ++d)
+    g[d] = (unsigned) gdims[d], l[d] = (unsigned) lo[d], h[d] = (unsigned) hi[d], rl[d] = (unsigned) ready_lo[d],
+    rh[d] = (unsigned) ready_hi[d];
+  const int rc = bk_stencil_apply_part(stencil, &f, grid_dev, g, l, h, coeff, rl, rh, part, stream);
+  if (rc == BK_EUNSUPPORTED) return false;
+  bkCheck(rc);
+  return true;
+}
 template <typename T>
 void brickStencil(int stencil, const unsigned *grid_dev, const std::vector<long> &gdims, T &bIn, T &bOut,
                   const bElem *coeff = nullptr, void *stream = nullptr) {
