@@ -161,19 +161,41 @@ def time_periods(bk, d, steps, warmup, dist):
 
 
 def time_sweeps(bk, d, reps):
-    """the dominant kernel alone: `reps` full-interior sweeps between two events on the launching stream"""
+    """the dominant kernel alone: `reps` launches over the interior between two events on the launching stream.
+    Returns (seconds per launch, time steps one launch advances)."""
     t = d.grid.dims
     lo, hi = (1, 1, 1), tuple(x - 1 for x in t)
+    steps = d.steps_per_pass()
+
+    def one(s):
+        if steps == 1:
+            d._sweep(s % 2, 1 - s % 2, lo, hi, None)
+        else:
+            bk.stencil_advance(d.stencil, steps, d.grid, d.bricks[s % 2], d.bricks[1 - s % 2], lo, hi)
+
     for s in range(3):
-        d._sweep(s % 2, 1 - s % 2, lo, hi, None)
+        one(s)
     bk.device_sync()
     ev0, ev1 = bk.Event(), bk.Event()
     ev0.record()
     for s in range(reps):
-        d._sweep(s % 2, 1 - s % 2, lo, hi, None)
+        one(s)
     ev1.record()
     ev1.sync()
-    return ev0.elapsed_ms(ev1) / 1e3 / reps
+    return ev0.elapsed_ms(ev1) / 1e3 / reps, steps
+
+
+def roofline_of(pts, launch_s, steps, peak, peak_src, traffic):
+    """HBM roofline of one launch of the sweep kernel.  A launch reads and writes every interior point once whatever
+    the number of time steps it fuses, so its compulsory traffic is 16 B x points; the single-sweep algorithmic figure
+    of SURVEY 8(d) (16 B per point PER STEP) is reported next to it as `frac_of_single_sweep_roofline`."""
+    achieved = 16.0 * pts / launch_s / 1e9
+    kern = "k_star2 (two time steps per pass)" if steps == 2 else "k_star (one sweep)"
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "kernel": f"{kern}: one launch = 512^3 interior points x 16 B compulsory, {steps} step(s)",
+            "kernel_ms": launch_s * 1e3, "steps_per_launch": steps, "peak_source": peak_src,
+            "GStencil/s_kernel": pts * steps / launch_s / 1e9,
+            "frac_of_single_sweep_roofline": 16.0 * pts * steps / launch_s / 1e9 / peak}
 
 
 def e2e_periods(bk, doms, steps):
@@ -282,6 +304,7 @@ def main():
     ap.add_argument("--stencil", default="mpi7pt", choices=["mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt"])
     ap.add_argument("--size", type=int, default=512, help="cells per axis per GPU")
     ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="one sweep per pass (no temporal blocking)")
     ap.add_argument("--no-extras", action="store_true", help="skip other stencils / e2e / cpu baseline")
     ap.add_argument("--kernel", default="auto", choices=["auto", "brick", "tiled"])
     args = ap.parse_args()
@@ -311,6 +334,87 @@ def main():
         wire_peers(bk, dm, dist, rank, world)
         if not args.no_overlap:
             dm.enable_overlap()
+        if args.no_fuse:
+            dm.fuse = 1
+        rng = np.random.default_rng(0x5EED + rank)
+        host = rng.random(dm.decomp.nbricks * 512)
+        host[:512] = 0.0
+        dm.storage[0].from_host(host)
+        return dm
+
+    d = make_domain()
+
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+    sec, launches = time_periods(bk, d, args.steps, args.warmup, dist)
+    clocks = sampler.stop() if rank == 0 else None
+    it = d.st_iter
+    value = pts * it * n * args.steps / sec / 1e9
+
+    peak, peak_src = measured_peak()
+    sweep_s, sweep_steps = time_sweeps(bk, d, 20)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
+            args.stencil + ("_fused2" if sweep_steps == 2 else ""))
+    except Exception:
+        pass
+
+    line = {
+        "impl": "reference", "metric": "GStencil/s", "value": gst, "unit": "GStencil/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"weak {args.stencil} {size}^3 per rank, 8^3 bricks, 1 exchange + {it} sweeps per step",
+                   "ranks": 1, "note": "reference CPU path (OpenMP + generated %s code), single process" % isa},
+        "cpu_baseline": {"value": gst, "unit": "GStencil/s", "cores": cores, "kind": kind,
+                         "sample": f"{args.steps} periods of {size}^3 after 1 warm-up"},
+        "e2e": {"value": gst, "unit": "GStencil/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--stencil", default="mpi7pt", choices=["mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt"])
+    ap.add_argument("--size", type=int, default=512, help="cells per axis per GPU")
+    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="one sweep per pass (no temporal blocking)")
+    ap.add_argument("--no-extras", action="store_true", help="skip other stencils / e2e / cpu baseline")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "brick", "tiled"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import bricklib_b200 as bk
+    rank, world, dist = dist_setup(args.gpus)
+    if world == 1:
+        bk._lib.check(bk.load().bk_set_device(0))
+    n = world
+    cart = CART.get(n)
+    if cart is None:
+        raise SystemExit("supported GPU counts: 1, 2, 4, 8")
+    coo = [(a, b, c) for a in range(cart[0]) for b in range(cart[1]) for c in range(cart[2])][rank]
+    kernel = {"auto": bk.KERNEL_AUTO, "brick": bk.KERNEL_BRICK, "tiled": bk.KERNEL_TILED}[args.kernel]
+    st = bk.STENCILS[args.stencil]
+    size = args.size
+    dom = (size,) * 3
+    pts = size ** 3
+
+    def make_domain():
+        dm = bk.WeakDomain(dom, st, cart, coo, rank, kernel)
+        wire_peers(bk, dm, dist, rank, world)
+        if not args.no_overlap:
+            dm.enable_overlap()
+        if args.no_fuse:
+            dm.fuse = 1
         rng = np.random.default_rng(0x5EED + rank)
         host = rng.random(dm.decomp.nbricks * 512)
         host[:512] = 0.0
@@ -342,12 +446,10 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"weak {args.stencil} {size}^3 per GPU, 8^3 bricks, 1 exchange + {it} sweeps per step",
                    "process_grid": "x".join(map(str, cart)), "exchange_MB_per_gpu_per_step": d.view.bytes / 1e6,
-                   "overlap": not args.no_overlap, "kernel": args.kernel,
+                   "overlap": not args.no_overlap, "kernel": args.kernel, "steps_per_pass": d.steps_per_pass(),
                    "l2": f"inputs larger than L2: {2 * d.storage[0].dat.nbytes / 1e9:.2f} GB streamed per sweep"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "stencil sweep, one launch = 512^3 interior points x 16 B",
-                     "kernel_ms": sweep_s * 1e3, "peak_source": peak_src},
+        "roofline": roofline_of(pts, sweep_s, sweep_steps, peak, peak_src, traffic),
         "clocks": clocks,
     }
 
@@ -358,11 +460,11 @@ def main():
                 continue
             d.stencil, d.st_iter = sid, bk.load().bk_stencil_st_iter(sid)
             s2, _ = time_periods(bk, d, max(3, args.steps // 4), 3, None)
-            k2 = time_sweeps(bk, d, 10)
+            k2, ks = time_sweeps(bk, d, 10)
             others[name] = {"GStencil/s": pts * d.st_iter * max(3, args.steps // 4) / s2 / 1e9,
-                            "sweep_ms": k2 * 1e3, "algorithmic_GB/s": 16.0 * pts / k2 / 1e9,
+                            "sweep_ms": k2 * 1e3, "steps_per_launch": ks, "hbm_GB/s": 16.0 * pts / k2 / 1e9,
                             "frac_of_hbm_peak": 16.0 * pts / k2 / 1e9 / peak,
-                            "GFLOP/s": (2 * bk.load().bk_stencil_points(sid) - 1) * pts / k2 / 1e9}
+                            "GFLOP/s": (2 * bk.load().bk_stencil_points(sid) - 1) * pts * ks / k2 / 1e9}
         d.stencil, d.st_iter = st, it
         line["others"] = others
         e2e_s, bi, bo = e2e_periods(bk, [d, make_domain()], 8)

@@ -7,6 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbrick_b200.so")
 
 BK_OK = 0
+BK_EUNSUPPORTED = -4
 ST_7PT, ST_MPI7PT, ST_MPI13PT, ST_MPI25PT, ST_MPI125PT = range(5)
 STENCILS = {"7pt": 0, "mpi7pt": 1, "mpi13pt": 2, "mpi25pt": 3, "mpi125pt": 4}
 KERNEL_AUTO, KERNEL_BRICK, KERNEL_TILED = 0, 1, 2
@@ -40,6 +41,7 @@ SIGNATURES = {
     "bk_stencil_radius": (C.c_int, [C.c_int]),
     "bk_stencil_st_iter": (C.c_int, [C.c_int]),
     "bk_stencil_points": (C.c_int, [C.c_int]),
+    "bk_stencil_fused_steps": (C.c_int, [C.c_int]),
     "bk_device_count": (C.c_int, [ip]),
     "bk_set_device": (C.c_int, [C.c_int]),
     "bk_dev_alloc": (C.c_int, [C.POINTER(vp), sz]),
@@ -81,6 +83,7 @@ SIGNATURES = {
     "bk_compare_brick": (C.c_int, [lp, lp, lp, vp, vp, vp, sz, C.c_double, C.POINTER(C.c_ulonglong), dp, vp]),
     "bk_stencil_apply": (C.c_int, [C.c_int, C.POINTER(Field), vp, up, up, up, dp, C.c_uint, vp]),
     "bk_stencil_apply_part": (C.c_int, [C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp]),
+    "bk_stencil_advance": (C.c_int, [C.c_int, C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp]),
     "bk_stencil_apply_list": (C.c_int, [C.c_int, C.POINTER(Field), vp, sz, dp, vp]),
     "bk_stencil_apply_multi": (C.c_int, [C.c_int, vp, C.c_uint, vp, up, up, up, dp, vp]),
     "bk_launch_count": (C.c_ulonglong, []),

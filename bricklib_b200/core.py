@@ -183,6 +183,25 @@ def stencil_part(stencil_id, grid, b_in, b_out, lo, hi, ready_lo, ready_hi, part
                                        _coeff(coeff), _u3(ready_lo), _u3(ready_hi), part, stream))
 
 
+def stencil_advance(stencil_id, steps, grid, b_in, b_out, lo=None, hi=None, ready=None, part=_lib.PART_ALL, coeff=None,
+                    stream=None):
+    """`steps` (1 or 2) time steps in one pass (bk_stencil_advance); ready = (ready_lo, ready_hi) for split launches.
+    Raises Unsupported when there is no fused kernel for this stencil/layout."""
+    lo = (0, 0, 0) if lo is None else lo
+    hi = grid.dims if hi is None else hi
+    f = _field(b_in, b_out)
+    rl, rh = (_u3(ready[0]), _u3(ready[1])) if ready else (None, None)
+    rc = load().bk_stencil_advance(stencil_id, steps, C.byref(f), grid.dev.ptr, _u3(grid.dims), _u3(lo), _u3(hi),
+                                   _coeff(coeff), rl, rh, part, stream)
+    if rc == _lib.BK_EUNSUPPORTED:
+        raise Unsupported(f"no {steps}-step kernel for stencil {stencil_id}")
+    check(rc)
+
+
+class Unsupported(_lib.BrickError):
+    pass
+
+
 def stencil_list(stencil_id, ids_dev, n, b_in, b_out, coeff=None, stream=None):
     f = _field(b_in, b_out)
     check(load().bk_stencil_apply_list(stencil_id, C.byref(f), ids_dev.ptr, n, _coeff(coeff), stream))

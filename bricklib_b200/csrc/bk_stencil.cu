@@ -80,7 +80,8 @@ int cube_coef_for(int stencil, CubeCoef *o) {
 // implemented in bk_stencil_tiled.cu
 int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, unsigned nsub, const unsigned *grid,
                  const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff, cudaStream_t s,
-                 int part = BK_PART_ALL, const unsigned *ready_lo = nullptr, const unsigned *ready_hi = nullptr);
+                 int part = BK_PART_ALL, const unsigned *ready_lo = nullptr, const unsigned *ready_hi = nullptr,
+                 int steps = 1);
 
 }  // namespace bk
 
@@ -205,6 +206,10 @@ int bk_stencil_st_iter(int s) {  // stencils/fake.h:39-344: ghost depth 8 cells 
   static const int it[BK_ST_COUNT] = {8, 8, 4, 2, 4};
   return (s < 0 || s >= BK_ST_COUNT) ? BK_EINVAL : it[s];
 }
+int bk_stencil_fused_steps(int s) {  // time steps per pass that pay off (the radius-2 fused kernel exists but is slower)
+  static const int f[BK_ST_COUNT] = {2, 2, 1, 1, 1};
+  return (s < 0 || s >= BK_ST_COUNT) ? BK_EINVAL : f[s];
+}
 int bk_stencil_points(int s) {
   static const int p[BK_ST_COUNT] = {7, 7, 13, 25, 125};
   return (s < 0 || s >= BK_ST_COUNT) ? BK_EINVAL : p[s];
@@ -238,6 +243,20 @@ int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid
   // only the marching kernel has the split enumeration; the caller falls back to whole-box launches on EUNSUPPORTED
   return bk::launch_tiled(stencil, *f, nullptr, 1, grid, gdims, lo, hi, coeff, (cudaStream_t) stream, part, ready_lo,
                           ready_hi);
+}
+
+int bk_stencil_advance(int stencil, int steps, const bk_field_t *f, const unsigned *grid, const unsigned *gdims,
+                       const unsigned *lo, const unsigned *hi, const double *coeff, const unsigned *ready_lo,
+                       const unsigned *ready_hi, int part, void *stream) {
+  BK_REQUIRE(stencil >= 0 && stencil < BK_ST_COUNT, "unknown stencil id");
+  BK_REQUIRE(steps == 1 || steps == 2, "steps must be 1 or 2");
+  BK_REQUIRE(f && f->adj && f->in && f->out && grid && gdims && lo && hi, "null argument");
+  BK_REQUIRE(part == BK_PART_ALL || (ready_lo && ready_hi && (part == BK_PART_READY || part == BK_PART_REST)), "bad part");
+  BK_REQUIRE(f->in_step >= 512 && f->out_step >= 512, "brick step smaller than a brick");
+  BK_REQUIRE(f->in != f->out, "in-place sweep is not defined");
+  BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
+  return bk::launch_tiled(stencil, *f, nullptr, 1, grid, gdims, lo, hi, coeff, (cudaStream_t) stream, part, ready_lo,
+                          ready_hi, steps);
 }
 
 int bk_stencil_apply_list(int stencil, const bk_field_t *f, const unsigned *ids, size_t n, const double *coeff,

@@ -25,6 +25,13 @@
 #include <cstdint>
 #include <cstdlib>
 #include <type_traits>
+#include <algorithm>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <queue>
+#include <tuple>
+#include <vector>
 
 namespace {
 
@@ -109,6 +116,8 @@ struct Cfg {
   static constexpr int JOBS = (NCOPY + 32 * NPW - 1) / (32 * NPW);
   [[maybe_unused]] static constexpr int MAXREG = MAXREG_;              // register cap (chosen so that the intended CTAs/SM fit)
   static constexpr size_t SMEM = (size_t) D * STAGE + 2 * D * 8 + 128;
+  static constexpr int OVH = 2 * RUP + 2;             // cost-model overhead planes per segment (halo planes + fill)
+  static constexpr bool FUSED = false;
   static_assert(8 % G == 0 && 8 % YT == 0 && TI % 2 == 0 && 2 * R <= 8, "geometry");
   static_assert(CREG == 0 || (NCW % 4 == 0 && NPW == 4 && NCONS * CREG + 128 * PREG <= 65536), "setmaxnreg needs warpgroups");
   // SW is even, so the bank half of a slot depends on its column only: a quarter warp (4 x-pairs of 2 i-adjacent
@@ -233,6 +242,7 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
   const int c = tid & 3;                 // x-pair inside the brick row: cells x0 = 2c, 2c+1
   const int e = (tid >> 2) & 1;          // brick parity inside a pair of i-adjacent bricks
   int rest = tid >> 3;
+  const bool swp = (R % 2 == 1) && (rest & 1);  // odd row group of the half warp (see the i-halo loads)
   const int y0 = (rest % (8 / YT)) * YT;  // first of my YT rows
   rest /= (8 / YT);
   const int bi = (rest % (TI / 2)) * 2 + e, bj = rest / (TI / 2);
@@ -264,6 +274,10 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
     } else {  // cell x0-m / x0+1+m
       ioffL[m - 1] = -8 * m + ((2 * c - m < 0) ? dl + 64 : 0);
       ioffR[m - 1] = 8 * (1 + m) + ((2 * c + 1 + m > 7) ? dr - 64 : 0);
+      if (swp) {
+        const int t = ioffL[m - 1];
+        ioffL[m - 1] = ioffR[m - 1], ioffR[m - 1] = t;
+      }
     }
   }
 
@@ -408,9 +422,11 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
               }
             } else {
 #pragma unroll
-              for (int m = 1; m <= R; ++m) {
-                line[R - m] = *reinterpret_cast<const double *>(pr + ioffL[m - 1]);
-                line[R + 1 + m] = *reinterpret_cast<const double *>(pr + ioffR[m - 1]);
+              for (int m = 1; m <= R; ++m) {  // odd row groups load right first: a half warp then covers all 32 banks
+                const double q0 = *reinterpret_cast<const double *>(pr + ioffL[m - 1]);
+                const double q1 = *reinterpret_cast<const double *>(pr + ioffR[m - 1]);
+                line[R - m] = swp ? q1 : q0;
+                line[R + 1 + m] = swp ? q0 : q1;
               }
             }
             double ax = fma(cf.c0, v[r].x, acc[s0][r].x), ay = fma(cf.c0, v[r].y, acc[s0][r].y);
@@ -492,6 +508,407 @@ __global__ void __launch_bounds__(C::NT) __maxnreg__(C::MAXREG) k_star_capped(co
   march_body<C>(a, cf);
 }
 
+// ==================================================================================================================
+// Two time steps per pass (temporal blocking) for the star stencils.
+//
+// The reference exchanges ghost zones once per ST_ITER sweeps and recomputes the ghost shell in between
+// (weak/main.cu:246-287): between two exchanges consecutive sweeps have no outside dependency, so two of them can be
+// applied in ONE pass over HBM.  The CTA streams input planes exactly as above (ring of D one-plane stages, halo depth
+// 2R), stage A turns input plane t into intermediate plane t-R (own tile plus an R-wide strip around it) and writes it
+// to a 2-plane ring in shared memory, stage B turns that intermediate plane into output plane t-2R with the same
+// register scatter along k.  The intermediate field never touches HBM: 16 B of traffic per point per TWO steps.
+// Semantics = bk_stencil_apply over the whole grid followed by bk_stencil_apply over [lo,hi): the intermediate is
+// computed at every in-grid cell the second step reads and is zero outside the grid (the null brick).
+template <int R_, int YT_, int TI_, int TJ_, int D_, int NPW_, int MINB_ = 1, int CREG_ = 0, int PREG_ = 40, bool LAG_ = false>
+struct FCfg {
+  static constexpr bool LAG = LAG_;                    // stage B runs one plane behind stage A (independent work between barriers)
+  static constexpr int MINB = MINB_;                   // CTAs per SM the register allocation must allow
+  static constexpr int CREG = CREG_, PREG = PREG_;     // setmaxnreg re-balancing as in Cfg (0 = off)
+  static constexpr bool CUBE = false, FUSED = true;
+  using Coef = bk::StarCoef;
+  static constexpr int R = R_, YT = YT_, TI = TI_, TJ = TJ_, D = D_;
+  static constexpr int W = 2 * R + 1;
+  static constexpr int H = 2 * R;                      // halo depth of the loads: two steps
+  static constexpr int SW = TI + 2, SH = TJ + 1;
+  static constexpr int SLOTP = 512 + 64;               // one plane per stage; same bank skew as Cfg
+  static constexpr int STAGE = ((SH * SW * SLOTP + 127) / 128) * 128;
+  static constexpr int NCONS = TI * TJ * 32 / YT, NCW = NCONS / 32, NPW = NPW_, NT = NCONS + 32 * NPW;
+  static constexpr int NCOPY = TI * TJ + 2 * TJ + 2 * (TI + 2);   // own, i-halo bricks, j-halo rows incl. corner columns
+  static constexpr int JOBS = (NCOPY + 32 * NPW - 1) / (32 * NPW);
+  static constexpr int NSTRIP = 16 * R * (TI + TJ);    // intermediate points outside the tile, one per thread
+  static constexpr int M = LAG ? 3 : 2;                // intermediate planes in flight
+  static constexpr size_t SMEM = (size_t) (D + M) * STAGE + 2 * D * 8 + 128;
+  static constexpr int OVH = 2 * H + 3;                // cost-model overhead planes per segment
+  [[maybe_unused]] static constexpr int MAXREG = 255;
+  static_assert(NSTRIP <= NCONS && 8 % YT == 0 && TI % 2 == 0 && 2 * H <= 8, "geometry");
+  static_assert(CREG == 0 || (NCW % 4 == 0 && NPW % 4 == 0 && NCONS * CREG + 32 * NPW * PREG <= 65536), "setmaxnreg");
+  __host__ __device__ static constexpr int slotoff(int bi, int bj) { return (bj * SW + bi) * SLOTP; }
+  // byte offset of the cell at tile-relative (X,Y), X in [-8, 8TI+8), Y in [-H, 8TJ+H): rows below/above the tile live in
+  // slot row 0 (rows [8-H,8) and [0,H))
+  __device__ static int cell(int X, int Y) {
+    const int sx = (X + 8) >> 3, cx = (X + 8) & 7;
+    int sy, ry;
+    if (Y < 0) sy = 0, ry = 8 + Y;
+    else if (Y >= 8 * TJ) sy = 0, ry = Y - 8 * TJ;
+    else sy = 1 + (Y >> 3), ry = Y & 7;
+    return slotoff(sx, sy) + ry * 64 + cx * 8;
+  }
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::NT, C::MINB) k_star2(const __grid_constant__ TiledArgs a, const __grid_constant__ bk::StarCoef cf) {
+  constexpr int R = C::R, YT = C::YT, TI = C::TI, TJ = C::TJ, D = C::D, W = C::W, H = C::H;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char *ring = smem_raw + ((128 - (smem_u32(smem_raw) & 127)) & 127);
+  unsigned char *mid = ring + D * C::STAGE;  // M intermediate planes, same slot layout as an input stage
+  const uint32_t ring_u32 = smem_u32(ring);
+  const uint32_t bar_full = ring_u32 + (D + C::M) * C::STAGE;
+  const uint32_t bar_empty = bar_full + D * 8;
+
+  const double *fin = a.in;
+  double *fout = a.out;
+  size_t in_step = a.in_step, out_step = a.out_step;
+  if (a.multi) {
+    const bk_field_t f = a.multi[blockIdx.z];
+    fin = f.in, fout = f.out, in_step = f.in_step, out_step = f.out_step;
+  }
+  const int tid = threadIdx.x;
+  int bq = 0, brel = (int) blockIdx.x;
+  while (bq + 1 < a.nbox && brel >= a.box[bq + 1].first) ++bq;
+  brel -= a.box[bq].first;
+  const int tx = a.box[bq].lo[0] + brel % a.box[bq].dim[0];
+  brel /= a.box[bq].dim[0];
+  const int ty = a.box[bq].lo[1] + brel % a.box[bq].dim[1];
+  const int tseg = a.box[bq].lo[2] + brel / a.box[bq].dim[1];
+  const int i0 = a.lo[0] + tx * TI, j0 = a.lo[1] + ty * TJ;
+  const int kb0 = a.lo[2] + tseg * a.kl;
+  const int nl = min(a.kl, a.hi[2] - kb0);
+  const int nout = nl * 8;
+  const int P = nout + 2 * H;  // input planes streamed: relative planes -H .. nout+H-1
+
+  if (tid == 0) {
+    for (int s = 0; s < D; ++s) {
+      mbar_init(bar_full + 8 * s, 32 * C::NPW);
+      mbar_init(bar_empty + 8 * s, 1);  // one consumer arrives after the consumers' plane barrier
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if constexpr (C::CREG > 0) {
+    if (tid >= C::NCONS)
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(C::PREG));
+    else
+      asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(C::CREG));
+  }
+  if (tid >= C::NCONS) {
+    // ================================================ producer warps ===========================================
+    // (a bulk copy takes its operands from uniform registers: the per-lane copies of a warp are issued one after the
+    // other, ~35 cycles each, so the copy rate scales with the number of producer WARPS)
+    const int pw = (tid - C::NCONS) >> 5, lane = tid & 31;
+    int sbi[C::JOBS], sbj[C::JOBS], kind[C::JOBS];
+    uint32_t dsto[C::JOBS];
+    unsigned idn[C::JOBS], idc[C::JOBS];
+#pragma unroll
+    for (int q = 0; q < C::JOBS; ++q) {
+      int job = pw + C::NPW * (lane + 32 * q);
+      kind[q] = 0;
+      sbi[q] = sbj[q] = 0;
+      if (job < TI * TJ) {
+        kind[q] = 1, sbi[q] = 1 + job % TI, sbj[q] = 1 + job / TI;
+      } else if ((job -= TI * TJ) < 2 * TJ) {
+        kind[q] = 1, sbi[q] = (job & 1) ? TI + 1 : 0, sbj[q] = 1 + (job >> 1);
+      } else if ((job -= 2 * TJ) < 2 * (TI + 2)) {
+        kind[q] = 2 + (job & 1), sbi[q] = job >> 1, sbj[q] = (job & 1) ? TJ + 1 : 0;
+      }
+      dsto[q] = C::slotoff(sbi[q], kind[q] >= 2 ? 0 : sbj[q]) + (kind[q] == 2 ? (8 - H) * 64 : 0);
+    }
+    auto brick_id = [&](int q, int kb) -> unsigned {
+      const int gi = i0 + sbi[q] - 1, gj = j0 + sbj[q] - 1;
+      if (kind[q] == 0 || gi < 0 || gi >= a.gx || gj < 0 || gj >= a.gy || kb < 0 || kb >= a.gz) return 0u;
+      return __ldg(a.grid + ((size_t) kb * a.gy + gj) * a.gx + gi);
+    };
+    const int z_first = kb0 * 8 - H;
+    int kb = (z_first >= 0) ? z_first / 8 : -((7 - z_first) / 8);
+    int pz = z_first - kb * 8;
+#pragma unroll
+    for (int q = 0; q < C::JOBS; ++q) idn[q] = brick_id(q, kb);
+    int st = 0;
+    uint32_t ph = 0;
+    bool fresh = true;
+    uint32_t bytes = 0;
+#pragma unroll
+    for (int q = 0; q < C::JOBS; ++q) bytes += kind[q] == 0 ? 0 : kind[q] == 1 ? 512 : H * 64;
+    for (int n = 0; n < P; ++n) {
+      if (fresh) {
+#pragma unroll
+        for (int q = 0; q < C::JOBS; ++q) idc[q] = idn[q], idn[q] = brick_id(q, kb + 1);
+        fresh = false;
+      }
+      if (n >= D) mbar_wait(bar_empty + 8 * st, ph ^ 1);
+      const uint32_t fb = bar_full + 8 * st;
+      mbar_expect_tx(fb, bytes);
+      const uint32_t sb = ring_u32 + st * C::STAGE;
+#pragma unroll
+      for (int q = 0; q < C::JOBS; ++q) {
+        const double *src = fin + (size_t) idc[q] * in_step + pz * 64;
+        if (kind[q] == 1) bulk_g2s(sb + dsto[q], src, 512, fb);
+        else if (kind[q] >= 2) bulk_g2s(sb + dsto[q], src + (kind[q] == 2 ? (8 - H) * 8 : 0), H * 64, fb);
+      }
+      if (++pz == 8) pz = 0, ++kb, fresh = true;
+      if (++st == D) st = 0, ph ^= 1;
+    }
+    return;
+  }
+
+  // ================================================== consumers ================================================
+  const int c = tid & 3, e = (tid >> 2) & 1;
+  int rest = tid >> 3;
+  const bool swp = (R % 2 == 1) && (rest & 1);  // odd row group of the half warp (see the i-halo loads)
+  const int y0 = (rest % (8 / YT)) * YT;
+  rest /= (8 / YT);
+  const int bi = (rest % (TI / 2)) * 2 + e, bj = rest / (TI / 2);
+  const int own_slot = C::slotoff(bi + 1, bj + 1);
+  const int own_off = own_slot + y0 * 64 + c * 16;
+  int joff[2 * R];
+#pragma unroll
+  for (int h = 0; h < 2 * R; ++h) {
+    const int ya = (h < R) ? y0 - R + h : y0 + YT + (h - R);
+    int base;
+    if (ya < 0) base = C::slotoff(bi + 1, bj) + (8 + ya) * 64;
+    else if (ya >= 8) base = C::slotoff(bi + 1, (bj == TJ - 1) ? 0 : bj + 2) + (ya - 8) * 64;
+    else base = own_slot + ya * 64;
+    joff[h] = base + c * 16;
+  }
+  const int dl = C::slotoff(bi, bj + 1) - own_slot, dr = C::slotoff(bi + 2, bj + 1) - own_slot;
+  constexpr int NI = (R % 2 == 0) ? R / 2 : R;
+  int ioffL[NI], ioffR[NI];
+#pragma unroll
+  for (int m = 1; m <= NI; ++m) {
+    if (R % 2 == 0) {
+      ioffL[m - 1] = -16 * m + ((c - m < 0) ? dl + 64 : 0);
+      ioffR[m - 1] = 16 * m + ((c + m > 3) ? dr - 64 : 0);
+    } else {
+      ioffL[m - 1] = -8 * m + ((2 * c - m < 0) ? dl + 64 : 0);
+      ioffR[m - 1] = 8 * (1 + m) + ((2 * c + 1 + m > 7) ? dr - 64 : 0);
+      if (swp) {
+        const int t = ioffL[m - 1];
+        ioffL[m - 1] = ioffR[m - 1], ioffR[m - 1] = t;
+      }
+    }
+  }
+  // my strip point (intermediate cell outside the tile that the second step reads), if any
+  // every warp takes an equal share of the strip: NI lanes on the two i-strip columns (a column maps to two bank groups
+  // only, so few lanes per instruction), NJ lanes on the j-strip rows
+  constexpr int SNI = 2 * R * 8 * TJ / C::NCW, SNJ = 2 * R * 8 * TI / C::NCW;
+  static_assert(SNI * C::NCW == 2 * R * 8 * TJ && SNJ * C::NCW == 2 * R * 8 * TI && SNI % 2 == 0 && SNI + SNJ <= 32, "strip split");
+  const int wrp = tid >> 5, ln = tid & 31;
+  const bool has_strip = ln < SNI + SNJ;
+  int sX = 0, sY = 0;
+  if (ln < SNI) {
+    const int side = ln >= SNI / 2, idx = wrp * (SNI / 2) + (ln - side * (SNI / 2));  // idx in [0, R*8TJ)
+    sY = idx % (8 * TJ);
+    sX = side ? 8 * TI + idx / (8 * TJ) : -1 - idx / (8 * TJ);
+  } else if (has_strip) {
+    const int q = wrp * SNJ + (ln - SNI), side = q / (R * 8 * TI), rem = q % (R * 8 * TI);
+    sX = rem % (8 * TI);
+    sY = side ? 8 * TJ + rem / (8 * TI) : -1 - rem / (8 * TI);
+  }
+  const int soff = C::cell(sX, sY);
+  int sxm[R], sxp[R], sym[R], syp[R];
+#pragma unroll
+  for (int d = 1; d <= R; ++d) {
+    sxm[d - 1] = C::cell(sX - d, sY), sxp[d - 1] = C::cell(sX + d, sY);
+    sym[d - 1] = C::cell(sX, sY - d), syp[d - 1] = C::cell(sX, sY + d);
+  }
+  bool strip_in;  // is my strip point's brick column inside the grid?
+  {
+    const int gi = i0 + ((sX + 8) >> 3) - 1, gj = j0 + (sY < 0 ? -1 : sY >= 8 * TJ ? TJ : (sY >> 3));
+    strip_in = has_strip && gi >= 0 && gi < a.gx && gj >= 0 && gj < a.gy;
+  }
+  const bool own_in = (i0 + bi < a.gx) && (j0 + bj < a.gy);
+  const bool mine = (i0 + bi < a.hi[0]) && (j0 + bj < a.hi[1]);
+  const unsigned *gcol = a.grid + ((size_t) kb0 * a.gy + (j0 + bj)) * a.gx + (i0 + bi);
+  const size_t glayer = (size_t) a.gy * a.gx;
+  unsigned id_next = mine ? __ldg(gcol) : 0u;
+  double *outp = fout;
+
+  double2 accA[W][YT], accB[W][YT];
+  double accS[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    accS[w] = 0.0;
+#pragma unroll
+    for (int r = 0; r < YT; ++r) accA[w][r] = accB[w][r] = make_double2(0.0, 0.0);
+  }
+
+  // one plane of the star update on my patch: `pb` = plane base, slot u%W of `acc` belongs to this plane's own output;
+  // on return slot (u-R)%W holds the plane this input completes (output index t-R)
+  auto star_plane = [&](const unsigned char *pb, double2 (&acc)[W][YT], const int u) {
+    const int sF = ((u - R) % W + W) % W, s0 = u % W, sN = (u + R) % W;
+    double2 v[YT];
+#pragma unroll
+    for (int r = 0; r < YT; ++r) v[r] = *reinterpret_cast<const double2 *>(pb + own_off + r * 64);
+#pragma unroll
+    for (int r = 0; r < YT; ++r) {
+      acc[sF][r].x = fma(cf.cp[2][R - 1], v[r].x, acc[sF][r].x);
+      acc[sF][r].y = fma(cf.cp[2][R - 1], v[r].y, acc[sF][r].y);
+    }
+#pragma unroll
+    for (int d = R - 1; d >= 1; --d) {
+      const int s = ((u - d) % W + W) % W;
+#pragma unroll
+      for (int r = 0; r < YT; ++r) {
+        acc[s][r].x = fma(cf.cp[2][d - 1], v[r].x, acc[s][r].x);
+        acc[s][r].y = fma(cf.cp[2][d - 1], v[r].y, acc[s][r].y);
+      }
+    }
+    double2 rows[YT + 2 * R];
+#pragma unroll
+    for (int h = 0; h < R; ++h) rows[h] = *reinterpret_cast<const double2 *>(pb + joff[h]);
+#pragma unroll
+    for (int r = 0; r < YT; ++r) rows[R + r] = v[r];
+#pragma unroll
+    for (int h = 0; h < R; ++h) rows[R + YT + h] = *reinterpret_cast<const double2 *>(pb + joff[R + h]);
+#pragma unroll
+    for (int r = 0; r < YT; ++r) {
+      double line[2 * R + 2];
+      line[R] = v[r].x, line[R + 1] = v[r].y;
+      const unsigned char *pr = pb + own_off + r * 64;
+      if constexpr (R % 2 == 0) {
+#pragma unroll
+        for (int m = 1; m <= R / 2; ++m) {
+          const double2 lft = *reinterpret_cast<const double2 *>(pr + ioffL[m - 1]);
+          const double2 rgt = *reinterpret_cast<const double2 *>(pr + ioffR[m - 1]);
+          line[R - 2 * m] = lft.x, line[R - 2 * m + 1] = lft.y;
+          line[R + 2 * m] = rgt.x, line[R + 2 * m + 1] = rgt.y;
+        }
+      } else {
+#pragma unroll
+        for (int m = 1; m <= R; ++m) {  // odd row groups load right first: a half warp then covers all 32 banks
+          const double q0 = *reinterpret_cast<const double *>(pr + ioffL[m - 1]);
+          const double q1 = *reinterpret_cast<const double *>(pr + ioffR[m - 1]);
+          line[R - m] = swp ? q1 : q0;
+          line[R + 1 + m] = swp ? q0 : q1;
+        }
+      }
+      double ax = fma(cf.c0, v[r].x, acc[s0][r].x), ay = fma(cf.c0, v[r].y, acc[s0][r].y);
+#pragma unroll
+      for (int d = 1; d <= R; ++d) {
+        ax = fma(cf.cp[0][d - 1], line[R + d], ax);
+        ay = fma(cf.cp[0][d - 1], line[R + 1 + d], ay);
+        ax = fma(cf.cm[0][d - 1], line[R - d], ax);
+        ay = fma(cf.cm[0][d - 1], line[R + 1 - d], ay);
+      }
+#pragma unroll
+      for (int d = 1; d <= R; ++d) {
+        ax = fma(cf.cp[1][d - 1], rows[R + r + d].x, ax);
+        ay = fma(cf.cp[1][d - 1], rows[R + r + d].y, ay);
+        ax = fma(cf.cm[1][d - 1], rows[R + r - d].x, ax);
+        ay = fma(cf.cm[1][d - 1], rows[R + r - d].y, ay);
+      }
+      acc[s0][r].x = ax, acc[s0][r].y = ay;
+    }
+#pragma unroll
+    for (int d = 1; d <= R - 1; ++d) {
+      const int s = (u + d) % W;
+#pragma unroll
+      for (int r = 0; r < YT; ++r) {
+        acc[s][r].x = fma(cf.cm[2][d - 1], v[r].x, acc[s][r].x);
+        acc[s][r].y = fma(cf.cm[2][d - 1], v[r].y, acc[s][r].y);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < YT; ++r) {
+      acc[sN][r].x = cf.cm[2][R - 1] * v[r].x;
+      acc[sN][r].y = cf.cm[2][R - 1] * v[r].y;
+    }
+  };
+
+  int st = 0, msl = 0, mprev = C::M - 1;
+  uint32_t ph = 0;
+  const int zabs0 = kb0 * 8, zmax = a.gz * 8;
+  // iteration n: stage B consumes intermediate plane n-1 (written in the previous iteration, published by the plane
+  // barrier) while stage A produces intermediate plane n from input plane n -- the two are independent, so their
+  // shared-memory latencies overlap; one CTA barrier per plane
+#pragma unroll 1
+  for (int tb = 0; tb <= P; tb += W) {
+#pragma unroll
+    for (int u = 0; u < W; ++u) {
+      const int n = tb + u;
+      if (n <= P) {
+        auto stage_b = [&](const int nb, const int slot, const int uB) {  // intermediate plane nb-H-R -> output nb-2H
+          const unsigned char *pmB = mid + slot * C::STAGE;
+          const int orel = nb - 2 * H;
+          star_plane(pmB, accB, uB);
+          if (orel >= 0) {
+            const int sF = ((uB - R) % W + W) % W;
+            const int oz = orel & 7;
+            if (oz == 0) {
+              outp = fout + (size_t) id_next * out_step + y0 * 8 + c * 2;
+              if (mine && (orel >> 3) + 1 < nl) id_next = __ldg(gcol + ((orel >> 3) + 1) * glayer);
+            }
+            if (mine) {
+#pragma unroll
+              for (int r = 0; r < YT; ++r) *reinterpret_cast<double2 *>(outp + oz * 64 + r * 8) = accB[sF][r];
+            }
+          }
+        };
+        if (C::LAG && n - 1 >= H) stage_b(n - 1, mprev, u % W);  // (n - 1 - H) mod W with H = W - 1
+        // ---- stage A: input plane n-H completes intermediate plane n-H-R ------------------------------------------
+        if (n < P) {
+          mbar_wait(bar_full + 8 * st, ph);
+          const unsigned char *pbA = ring + st * C::STAGE;
+          unsigned char *pm = mid + msl * C::STAGE;
+          const int zm = zabs0 + n - H - R;
+          const bool zin = zm >= 0 && zm < zmax;
+          star_plane(pbA, accA, u);
+          {
+            const int sF = ((u - R) % W + W) % W;
+            const bool ok = zin && own_in;
+#pragma unroll
+            for (int r = 0; r < YT; ++r)
+              *reinterpret_cast<double2 *>(pm + own_off + r * 64) = ok ? accA[sF][r] : make_double2(0.0, 0.0);
+          }
+          if (has_strip) {
+            const int sF = ((u - R) % W + W) % W, s0 = u % W, sN = (u + R) % W;
+            const double sv = *reinterpret_cast<const double *>(pbA + soff);
+            accS[sF] = fma(cf.cp[2][R - 1], sv, accS[sF]);
+            *reinterpret_cast<double *>(pm + soff) = (zin && strip_in) ? accS[sF] : 0.0;
+#pragma unroll
+            for (int d = R - 1; d >= 1; --d)
+              accS[((u - d) % W + W) % W] = fma(cf.cp[2][d - 1], sv, accS[((u - d) % W + W) % W]);
+            double t = fma(cf.c0, sv, accS[s0]);
+#pragma unroll
+            for (int d = 1; d <= R; ++d) {
+              t = fma(cf.cp[0][d - 1], *reinterpret_cast<const double *>(pbA + sxp[d - 1]), t);
+              t = fma(cf.cm[0][d - 1], *reinterpret_cast<const double *>(pbA + sxm[d - 1]), t);
+            }
+#pragma unroll
+            for (int d = 1; d <= R; ++d) {
+              t = fma(cf.cp[1][d - 1], *reinterpret_cast<const double *>(pbA + syp[d - 1]), t);
+              t = fma(cf.cm[1][d - 1], *reinterpret_cast<const double *>(pbA + sym[d - 1]), t);
+            }
+            accS[s0] = t;
+#pragma unroll
+            for (int d = 1; d <= R - 1; ++d) accS[(u + d) % W] = fma(cf.cm[2][d - 1], sv, accS[(u + d) % W]);
+            accS[sN] = cf.cm[2][R - 1] * sv;
+          }
+        }
+        // every consumer has read the input stage / the previous intermediate plane and written its part of the new one
+        asm volatile("bar.sync 1, %0;" ::"n"(C::NCONS) : "memory");
+        if (n < P) {
+          if (tid == 0) mbar_arrive(bar_empty + 8 * st);
+          if (++st == D) st = 0, ph ^= 1;
+          if (!C::LAG && n >= H) stage_b(n, msl, (u + 1) % W);  // (n - H) mod W
+        }
+        mprev = msl;
+        msl = (msl == C::M - 1) ? 0 : msl + 1;
+      }
+    }
+  }
+}
+
 // register re-balancing (Cfg::CREG > 0): ptxas needs the register count at entry, i.e. min-blocks in the launch bounds
 template <class C>
 __global__ void __launch_bounds__(C::NT, 1) k_star_rebal(const __grid_constant__ TiledArgs a,
@@ -499,19 +916,67 @@ __global__ void __launch_bounds__(C::NT, 1) k_star_rebal(const __grid_constant__
   march_body<C>(a, cf);
 }
 
+// Brick layers per k segment.  Every CTA streams 8*layers + ovh planes (ovh = halo planes + pipeline fill) and CTAs are
+// dealt to the `slots` resident CTA slots in blockIdx order (all tiles of segment 0, then segment 1, ...; the last
+// segment may be shorter).  Long segments amortise ovh, short ones fill the last wave: the launch is list-scheduled
+// here for every candidate length and the shortest makespan wins (model checked against profiles/r01_segments.md and
+// the fused-kernel sweeps).  Results are cached per (tiles, layers, slots, ovh).
+int pick_segment_layers(long tiles, int nz, int slots, int ovh) {
+  static std::mutex mu;
+  static std::map<std::tuple<long, int, int, int>, int> cache;
+  const auto key = std::make_tuple(tiles, nz, slots, ovh);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  int best_kl = nz;
+  double best = -1.0;
+  int last_segs = -1;
+  for (int kl = nz; kl >= 1; --kl) {
+    const int segs = (nz + kl - 1) / kl;
+    if (segs == last_segs) continue;  // same segment count with a longer segment: never better
+    last_segs = segs;
+    if ((double) tiles * segs > 64.0 * slots && best >= 0) break;  // far too many tiny CTAs
+    const int kl_min = (nz + segs - 1) / segs;                     // most even split for this segment count
+    std::priority_queue<double, std::vector<double>, std::greater<double>> free_at;
+    for (int i = 0; i < slots; ++i) free_at.push(0.0);
+    double makespan = 0.0;
+    for (int q = 0; q < segs; ++q) {
+      const int len = std::min(kl_min, nz - q * kl_min);
+      const double d = 8.0 * len + ovh;
+      for (long t = 0; t < tiles; ++t) {
+        const double start = free_at.top();
+        free_at.pop();
+        free_at.push(start + d);
+        makespan = std::max(makespan, start + d);
+      }
+    }
+    // CTAs of one wave do not finish together on real hardware: charge a fraction of a CTA time for the ragged tail
+    const double cost = makespan + 0.15 * (8.0 * kl_min + ovh);
+    if (best < 0 || cost < best) best = cost, best_kl = kl_min;
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  cache[key] = best_kl;
+  return best_kl;
+}
+
 template <class C>
 int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, unsigned nsub, int part,
                const int *rdy_lo, const int *rdy_hi) {
   void (*kern)(const TiledArgs, const typename C::Coef);
-  if constexpr (C::CREG > 0) kern = k_star_rebal<C>; else if constexpr (C::MAXREG < 255) kern = k_star_capped<C>; else kern = k_star<C>;
+  if constexpr (C::FUSED) kern = k_star2<C>;
+  else if constexpr (C::CREG > 0) kern = k_star_rebal<C>;
+  else if constexpr (C::MAXREG < 255) kern = k_star_capped<C>;
+  else kern = k_star<C>;
   BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
   if (getenv("BK_DEBUG")) {
     cudaFuncAttributes fa;
     int nb = -1;
     cudaFuncGetAttributes(&fa, kern);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::NT, C::SMEM);
-    fprintf(stderr, "[bk] k_star R=%d YT=%d tile=%dx%d G=%d D=%d: %d thr, %d regs, %zu B smem, %zu B local, %d CTA/SM\n", C::R,
-            C::YT, C::TI, C::TJ, C::G, C::D, C::NT, fa.numRegs, C::SMEM, fa.localSizeBytes, nb);
+    fprintf(stderr, "[bk] %s R=%d YT=%d tile=%dx%d D=%d: %d thr, %d regs, %zu B smem, %zu B local, %d CTA/SM\n",
+            C::FUSED ? "k_star2" : "k_star", C::R, C::YT, C::TI, C::TJ, C::D, C::NT, fa.numRegs, C::SMEM, fa.localSizeBytes, nb);
   }
   TiledArgs a = a0;
   const int nx = a.hi[0] - a.lo[0], ny = a.hi[1] - a.lo[1], nz = a.hi[2] - a.lo[2];
@@ -529,19 +994,7 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, 
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NT, C::SMEM);
     slots = sms * (per_sm > 0 ? per_sm : 1);
   }
-  // cost of a split into nseg segments (unit: planes): every CTA streams 8*layers + ovh planes, CTAs are dealt to the
-  // resident slots dynamically, and the launch ends about 0.7 CTA-times after the slots run out of fresh CTAs
-  // (constants fitted on B200, profiles/r01_segments.md)
-  const double ovh = 3.0 * C::R + 2.0, tiles = (double) a.ntx * nty * nsub;
-  int best_seg = 1;
-  double best_cost = -1.0;
-  for (int nseg = 1; nseg <= nz; ++nseg) {
-    const int kl = (nz + nseg - 1) / nseg, segs = (nz + kl - 1) / kl;
-    const double work = tiles * (8.0 * nz + ovh * segs);
-    const double cost = work / slots + 0.7 * (8.0 * kl + ovh);
-    if (best_cost < 0 || cost < best_cost) best_cost = cost, best_seg = nseg;
-  }
-  a.kl = (nz + best_seg - 1) / best_seg;
+  a.kl = pick_segment_layers((long) a.ntx * nty * nsub, nz, slots, C::OVH);
   if (const char *e = getenv("BK_STAR_KL")) a.kl = atoi(e) > 0 ? atoi(e) : a.kl;  // developer knob
   const int segs = (nz + a.kl - 1) / a.kl;
   // CTA boxes.  "inner" = CTAs whose whole read footprint (tile + 1 brick all round) lies in the ready box
@@ -598,8 +1051,9 @@ namespace bk {
 
 int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, unsigned nsub, const unsigned *grid,
                  const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff, cudaStream_t s,
-                 int part, const unsigned *ready_lo, const unsigned *ready_hi) {
+                 int part, const unsigned *ready_lo, const unsigned *ready_hi, int steps) {
   if (!multi_dev && (((size_t) f.in | (size_t) f.out) & 15 || (f.in_step & 1) || (f.out_step & 1))) return BK_EUNSUPPORTED;
+  if (steps == 2 && bk_stencil_radius(stencil) > 2) return BK_EUNSUPPORTED;
   TiledArgs a;
   a.in = f.in, a.out = f.out, a.in_step = f.in_step, a.out_step = f.out_step, a.grid = grid;
   a.gx = (int) gdims[0], a.gy = (int) gdims[1], a.gz = (int) gdims[2];
@@ -626,6 +1080,17 @@ int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, 
   StarCoef sc;
   const int r = star_coef_for(stencil, coeff, &sc);
   if (r < 0) return BK_EINVAL;
+  if (steps == 2) {  // two time steps per pass: (R, YT, TI, TJ, D, producer warps)
+    if (r == 1) {
+      if (v == 1) return launch_cfg<FCfg<1, 4, 8, 4, 4, 4>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+      if (v == 2) return launch_cfg<FCfg<1, 2, 4, 4, 3, 2, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+      if (v == 3) return launch_cfg<FCfg<1, 4, 8, 4, 4, 4, 1, 0, 40, true>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+      if (v == 4) return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2, 0, 40, true>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+      return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+    }
+    if (r == 2) return launch_cfg<FCfg<2, 2, 4, 4, 4, 4>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+    return BK_EUNSUPPORTED;
+  }
   if (r == 1) {
     if (v == 1) return launch_cfg<Cfg<1, 4, 6, 4, 1, 4, 128, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
     return launch_cfg<Cfg<1, 4, 4, 4, 2, 3, 255, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);

@@ -64,6 +64,7 @@ class WeakDomain:
         self.epoch = 0
         self.comm_stream = None
         self.ev_comm = self.ev_comp = None
+        self.fuse = 2        # time steps per pass where a fused kernel exists (7/13-point); 1 = one sweep per pass
 
     # ---- wiring -------------------------------------------------------------------------------------------------
     def connect(self, peer_storage_ptrs=None, handshake=None):
@@ -128,44 +129,70 @@ class WeakDomain:
         check(load().bk_flags_wait(w, len(self.peers), self.epoch, stream))
 
     def period(self, stream=None):
-        """one exchange + ST_ITER sweeps; returns the number of kernel launches issued"""
+        """one exchange + ST_ITER time steps; returns the number of kernel launches issued.
+
+        The steps are issued as passes of `self.fuse` (1 or 2) time steps each (bk_stencil_advance); the first pass is
+        split into a READY half on the compute stream and a REST half behind the pull when overlap is enabled."""
         n0 = load().bk_launch_count()
         self.epoch += 1
         t = self.grid.dims
-        full_lo, full_hi = (0, 0, 0), t
-        if self.comm_stream is None:
-            self._exchange(stream)
-            for s in range(self.st_iter):
-                last = s == self.st_iter - 1
-                if s == 1:
-                    self._wait_peers_done(stream)  # sweep 1 rewrites storage[0], whose skin peers were reading
-                lo, hi = ((1, 1, 1), tuple(x - 1 for x in t)) if last else (full_lo, full_hi)
-                self._sweep(s % 2, 1 - s % 2, lo, hi, stream)
-        else:
-            cs = self.comm_stream
+        g = GZ // 8
+        full = ((0, 0, 0), t)
+        own = ((g,) * 3, tuple(x - g for x in t))        # bricks that are final without the exchange
+        fuse = self.steps_per_pass()
+        cs = self.comm_stream
+        overlap = cs is not None and self.kernel != _lib.KERNEL_BRICK
+        if cs is not None:
             self.ev_comp.record(stream)
             check(load().bk_stream_wait_event(cs, self.ev_comp.h))  # previous period's sweeps wrote the skin
-            self._exchange(cs, fused_signal=True)
-            g = GZ // 8
-            own_lo, own_hi = (g,) * 3, tuple(x - g for x in t)      # bricks that are final without the exchange
-            split = self.kernel != _lib.KERNEL_BRICK and self.st_iter > 1
-            if split:
+        self._exchange(cs if cs is not None else stream, fused_signal=cs is not None)
+        done, p = 0, 0
+        while done < self.st_iter:
+            src, dst = p % 2, 1 - p % 2
+            last = done + fuse >= self.st_iter
+            lo, hi = own if last else full
+            if p == 1:
+                self._wait_peers_done(stream)  # pass 1 rewrites storage[0], whose skin the peers were reading
+            if p == 0 and overlap and not last:
                 try:
-                    core.stencil_part(self.stencil, self.grid, self.bricks[0], self.bricks[1], full_lo, full_hi, own_lo,
-                                      own_hi, _lib.PART_READY, None, stream)
-                    core.stencil_part(self.stencil, self.grid, self.bricks[0], self.bricks[1], full_lo, full_hi, own_lo,
-                                      own_hi, _lib.PART_REST, None, cs)
-                except _lib.BrickError:
-                    split = False
-            self.ev_comm.record(cs)
-            check(load().bk_stream_wait_event(stream, self.ev_comm.h))
-            for s in range(0 if not split else 1, self.st_iter):
-                last = s == self.st_iter - 1
-                if s == 1:
-                    self._wait_peers_done(stream)
-                lo, hi = (own_lo, own_hi) if last else (full_lo, full_hi)
-                self._sweep(s % 2, 1 - s % 2, lo, hi, stream)
+                    self._advance(fuse, src, dst, lo, hi, own, _lib.PART_READY, stream)
+                    self._advance(fuse, src, dst, lo, hi, own, _lib.PART_REST, cs)
+                    self.ev_comm.record(cs)
+                    check(load().bk_stream_wait_event(stream, self.ev_comm.h))
+                    done, p = done + fuse, p + 1
+                    continue
+                except core.Unsupported:
+                    if fuse == 2:
+                        fuse = 1
+                        continue
+                    overlap = False
+            if p == 0 and cs is not None:
+                self.ev_comm.record(cs)
+                check(load().bk_stream_wait_event(stream, self.ev_comm.h))
+            try:
+                self._advance(fuse, src, dst, lo, hi, None, _lib.PART_ALL, stream)
+            except core.Unsupported:
+                if fuse == 1:
+                    raise
+                fuse = 1
+                continue
+            done, p = done + fuse, p + 1
+        assert p % 2 == 0 or self.st_iter % 2 == 1, "result must end in storage[0]"
         return load().bk_launch_count() - n0
+
+    def steps_per_pass(self):
+        """time steps one launch advances: 2 where the fused kernel pays off (7-point), else 1"""
+        fuse = min(max(1, self.fuse), load().bk_stencil_fused_steps(self.stencil))
+        if self.kernel == _lib.KERNEL_BRICK or self.st_iter % fuse:
+            fuse = 1
+        return fuse
+
+    def _advance(self, steps, src, dst, lo, hi, ready, part, stream):
+        if steps == 1 and part == _lib.PART_ALL:
+            self._sweep(src, dst, lo, hi, stream)
+        else:
+            core.stencil_advance(self.stencil, steps, self.grid, self.bricks[src], self.bricks[dst], lo, hi, ready, part,
+                                 None, stream)
 
 
 def shell_boxes(lo, hi, in_lo, in_hi):

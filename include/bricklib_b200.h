@@ -44,6 +44,8 @@ const char *bk_last_error(void);
 int bk_stencil_radius(int stencil);  /* 1,1,2,4,2 */
 int bk_stencil_st_iter(int stencil); /* sweeps per ghost exchange: 8,8,4,2,4 (= ghost depth 8 / radius) */
 int bk_stencil_points(int stencil);  /* 7,7,13,25,125 */
+int bk_stencil_fused_steps(int stencil); /* `steps` of bk_stencil_advance that is fastest: 2,2,1,1,1 (radius 2 can fuse, but its
+                                            two-step kernel is slower than two sweeps) */
 
 /* ---- device plumbing (stands in for include/brick-gpu.h:43-103 movBrickInfo/movBrickStorage, cudaarray.h:11-31) - */
 int bk_device_count(int *n);
@@ -146,6 +148,17 @@ int bk_stencil_apply(int stencil, const bk_field_t *f, const unsigned *grid_dev,
 int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid_dev, const unsigned *gdims,
                           const unsigned *lo, const unsigned *hi, const double *coeff_host, const unsigned *ready_lo,
                           const unsigned *ready_hi, int part, void *stream);
+/* `steps` time steps in ONE pass over HBM (temporal blocking; steps = 1 or 2).  Between two ghost exchanges the
+ * reference applies ST_ITER sweeps that depend on nothing outside the subdomain's (ghost-inclusive) grid
+ * (weak/main.cu:275-285), so consecutive sweeps can be fused.  steps = 2 is equivalent to
+ *     bk_stencil_apply(stencil, {in -> tmp}, whole grid);  bk_stencil_apply(stencil, {tmp -> out}, [lo,hi));
+ * except that tmp lives in shared memory: the intermediate is evaluated at every in-grid cell the second step reads and
+ * is zero outside the grid (the null brick).  HBM traffic: 16 B per point per `steps` steps.  part/ready_* as in
+ * bk_stencil_apply_part (BK_PART_ALL: ready_* may be NULL).  BK_EUNSUPPORTED for stencils or layouts without a fused
+ * kernel (radius 4, cube): the caller then issues single steps. */
+int bk_stencil_advance(int stencil, int steps, const bk_field_t *f, const unsigned *grid_dev, const unsigned *gdims,
+                       const unsigned *lo, const unsigned *hi, const double *coeff_host, const unsigned *ready_lo,
+                       const unsigned *ready_hi, int part, void *stream);
 /* same over an explicit list of brick ids (inner / skin / ghost lists for overlap; any adjacency-defined set) */
 int bk_stencil_apply_list(int stencil, const bk_field_t *f, const unsigned *ids_dev, size_t n,
                           const double *coeff_host, void *stream);

@@ -95,6 +95,78 @@ def test_list_launch_equals_box_launch():
         assert np.array_equal(s_a.to_host(), s_b.to_host())
 
 
+@pytest.mark.parametrize("dom", [(40, 24, 32), (64, 64, 64), (16, 16, 16), (104, 40, 16)])
+@pytest.mark.parametrize("st", [1, 2])
+def test_two_steps_per_pass_equal_two_sweeps(dom, st):
+    """bk_stencil_advance(steps=2) == sweep over the whole grid, then sweep over the box (intermediate in shared memory);
+    boxes: whole grid, interior, and an off-centre box; also the READY/REST split must cover the box exactly once"""
+    rng = np.random.default_rng(5)
+    d = bk.BrickDecomp(dom, 8)
+    info = d.getBrickInfo()
+    grid = bk.DeviceGrid(d.grid)
+    s_in, s_tmp, s_ref, s_got = (info.allocate(512) for _ in range(4))
+    h = rng.random(d.nbricks * 512)
+    h[:512] = 0.0
+    s_in.from_host(h)
+    b_in, b_tmp, b_ref, b_got = (bk.Brick(info, s) for s in (s_in, s_tmp, s_ref, s_got))
+    t = grid.dims
+    boxes = [((0, 0, 0), t), ((1, 1, 1), tuple(x - 1 for x in t)), ((1, 0, 1), (t[0], t[1] - 1, t[2]))]
+    for lo, hi in boxes:
+        if any(a >= b for a, b in zip(lo, hi)):
+            continue
+        bk.stencil(st, grid, b_in, b_tmp, kernel=bk.KERNEL_TILED)
+        s_ref.dat.zero()
+        bk.stencil(st, grid, b_tmp, b_ref, lo, hi, kernel=bk.KERNEL_TILED)
+        s_got.dat.zero()
+        bk.stencil_advance(st, 2, grid, b_in, b_got, lo, hi)
+        bk.device_sync()
+        want, got = s_ref.to_host(), s_got.to_host()
+        assert rel(got, want) < 1e-14, (lo, hi)
+        assert np.array_equal(got == 0.0, want == 0.0), "bricks outside the box must stay untouched"
+        own = ((1, 1, 1), tuple(x - 1 for x in t))
+        s_got.dat.zero()
+        bk.stencil_advance(st, 2, grid, b_in, b_got, lo, hi, own, bk.PART_READY)
+        bk.device_sync()
+        part1 = s_got.to_host()
+        s_got.dat.zero()
+        bk.stencil_advance(st, 2, grid, b_in, b_got, lo, hi, own, bk.PART_REST)
+        bk.device_sync()
+        part2 = s_got.to_host()
+        assert not np.any((part1 != 0.0) & (part2 != 0.0)), "READY and REST overlap"
+        assert rel(part1 + part2, want) < 1e-14
+
+
+def test_two_steps_unsupported_for_radius4_and_cube():
+    d = bk.BrickDecomp((16, 16, 16), 8)
+    info = d.getBrickInfo()
+    grid = bk.DeviceGrid(d.grid)
+    a, b = bk.Brick(info, info.allocate(512)), bk.Brick(info, info.allocate(512))
+    for st in (3, 4):
+        with pytest.raises(bk.Unsupported):
+            bk.stencil_advance(st, 2, grid, a, b)
+
+
+@pytest.mark.parametrize("fuse", [1, 2])
+@pytest.mark.parametrize("overlap", [False, True])
+def test_weak_period_fused_passes_against_reference_fixture(golden_dir, fuse, overlap):
+    z = np.load(os.path.join(golden_dir, "weak_steps.npz"))
+    dom = (24, 16, 32)
+    for name, st in bk.STENCILS.items():
+        if st == 0:
+            continue
+        d = bk.WeakDomain(dom, st)
+        d.fuse = fuse
+        d.connect()
+        d.load_interior(z["in_c111"])
+        if overlap:
+            d.enable_overlap()
+        launches = [d.period() for _ in range(2)]
+        bk.device_sync()
+        assert rel(d.read_interior(0), z["out_c111_" + name]) < TOL, name
+        if fuse == 2 and st == 1 and not overlap:
+            assert launches[0] == 1 + oracle.ST_ITER[st] // 2, "exchange + one launch per two steps"
+
+
 class CudaBackend:
     """oracle.schedule backend protocol, implemented with the product (one WeakDomain per emulated rank)."""
 

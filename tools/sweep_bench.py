@@ -15,6 +15,7 @@ ap.add_argument("--full", action="store_true", help="sweep the ghost shell too (
 ap.add_argument("--peak", type=float, default=6650.0)
 ap.add_argument("--variants", default="")
 ap.add_argument("--kls", default="")
+ap.add_argument("--steps", type=int, default=1, help="time steps per pass (2 = fused kernel)")
 args = ap.parse_args()
 K = {"auto": bk.KERNEL_AUTO, "brick": bk.KERNEL_BRICK, "tiled": bk.KERNEL_TILED}
 bk.load().bk_set_device(0)
@@ -35,14 +36,20 @@ for name in args.stencils.split(","):
         os.environ["BK_STAR_KL"] = kl
     for kn in args.kernels.split(","):
         d.stencil, d.kernel = bk.STENCILS[name], K[kn]
+        def sweep(a, b):
+            if args.steps == 1:
+                d._sweep(a, b, lo, hi, None)
+            else:
+                bk.stencil_advance(d.stencil, args.steps, d.grid, d.bricks[a], d.bricks[b], lo, hi)
         for s in range(3):
-            d._sweep(s % 2, 1 - s % 2, lo, hi, None)
+            sweep(s % 2, 1 - s % 2)
         bk.device_sync()
         e0, e1 = bk.Event(), bk.Event()
         e0.record()
         for s in range(args.reps):
-            d._sweep(s % 2, 1 - s % 2, lo, hi, None)
+            sweep(s % 2, 1 - s % 2)
         e1.record(); e1.sync()
         ms = e0.elapsed_ms(e1) / args.reps
         gbs = 16.0 * pts / ms / 1e6
+        ms /= args.steps
         print(f"{name:9s} v{var or '0'} kl{kl or '16'} {kn:6s} {'full' if args.full else 'inner'} {ms:8.4f} ms  {pts/ms/1e6:8.1f} GStencil/s  {gbs:8.1f} GB/s alg  {gbs/args.peak*100:5.1f}% of {args.peak:.0f}", flush=True)
