@@ -362,85 +362,6 @@ def main():
         pass
 
     line = {
-        "impl": "reference", "metric": "GStencil/s", "value": gst, "unit": "GStencil/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"weak {args.stencil} {size}^3 per rank, 8^3 bricks, 1 exchange + {it} sweeps per step",
-                   "ranks": 1, "note": "reference CPU path (OpenMP + generated %s code), single process" % isa},
-        "cpu_baseline": {"value": gst, "unit": "GStencil/s", "cores": cores, "kind": kind,
-                         "sample": f"{args.steps} periods of {size}^3 after 1 warm-up"},
-        "e2e": {"value": gst, "unit": "GStencil/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }
-    print(json.dumps(line))
-
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--stencil", default="mpi7pt", choices=["mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt"])
-    ap.add_argument("--size", type=int, default=512, help="cells per axis per GPU")
-    ap.add_argument("--no-overlap", action="store_true")
-    ap.add_argument("--no-fuse", action="store_true", help="one sweep per pass (no temporal blocking)")
-    ap.add_argument("--no-extras", action="store_true", help="skip other stencils / e2e / cpu baseline")
-    ap.add_argument("--kernel", default="auto", choices=["auto", "brick", "tiled"])
-    args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
-
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
-
-    import bricklib_b200 as bk
-    rank, world, dist = dist_setup(args.gpus)
-    if world == 1:
-        bk._lib.check(bk.load().bk_set_device(0))
-    n = world
-    cart = CART.get(n)
-    if cart is None:
-        raise SystemExit("supported GPU counts: 1, 2, 4, 8")
-    coo = [(a, b, c) for a in range(cart[0]) for b in range(cart[1]) for c in range(cart[2])][rank]
-    kernel = {"auto": bk.KERNEL_AUTO, "brick": bk.KERNEL_BRICK, "tiled": bk.KERNEL_TILED}[args.kernel]
-    st = bk.STENCILS[args.stencil]
-    size = args.size
-    dom = (size,) * 3
-    pts = size ** 3
-
-    def make_domain():
-        dm = bk.WeakDomain(dom, st, cart, coo, rank, kernel)
-        wire_peers(bk, dm, dist, rank, world)
-        if not args.no_overlap:
-            dm.enable_overlap()
-        if args.no_fuse:
-            dm.fuse = 1
-        rng = np.random.default_rng(0x5EED + rank)
-        host = rng.random(dm.decomp.nbricks * 512)
-        host[:512] = 0.0
-        dm.storage[0].from_host(host)
-        return dm
-
-    d = make_domain()
-
-    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
-    if rank == 0:
-        sampler.start()
-    sec, launches = time_periods(bk, d, args.steps, args.warmup, dist)
-    clocks = sampler.stop() if rank == 0 else None
-    it = d.st_iter
-    value = pts * it * n * args.steps / sec / 1e9
-
-    peak, peak_src = measured_peak()
-    sweep_s = time_sweeps(bk, d, 20)
-    achieved = 16.0 * pts / sweep_s / 1e9
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.stencil)
-    except Exception:
-        pass
-
-    line = {
         "metric": "GStencil/s", "value": value, "unit": "GStencil/s", "n_gpus": n, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",

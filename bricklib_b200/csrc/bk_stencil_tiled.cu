@@ -1053,7 +1053,7 @@ int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, 
                  const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff, cudaStream_t s,
                  int part, const unsigned *ready_lo, const unsigned *ready_hi, int steps) {
   if (!multi_dev && (((size_t) f.in | (size_t) f.out) & 15 || (f.in_step & 1) || (f.out_step & 1))) return BK_EUNSUPPORTED;
-  if (steps == 2 && bk_stencil_radius(stencil) > 2) return BK_EUNSUPPORTED;
+  if (steps == 2 && (bk_stencil_radius(stencil) > 2 || stencil == BK_ST_MPI125PT)) return BK_EUNSUPPORTED;
   TiledArgs a;
   a.in = f.in, a.out = f.out, a.in_step = f.in_step, a.out_step = f.out_step, a.grid = grid;
   a.gx = (int) gdims[0], a.gy = (int) gdims[1], a.gz = (int) gdims[2];

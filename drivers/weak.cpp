@@ -49,6 +49,7 @@ struct Shared {
   std::vector<unsigned> dom = {64, 64, 64};
   const StencilDef *st = nullptr;
   bool validate = false;
+  bool no_fuse = false;  // -F: one sweep per pass (no temporal blocking)
   std::vector<bElem *> storage_ptr;  // rank -> device address of storage[0]
   std::vector<double> calc, call, wait, total;
   std::vector<bElem *> result;       // rank -> host copy of the interior after the run (validation)
@@ -127,8 +128,17 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
   const std::vector<long> skip_lo = {g, g, g}, skip_hi = {strideb[0] - g, strideb[1] - g, strideb[2] - g};
   double calctime = 0, calltime = 0, waittime = 0;
 
-  auto sweep = [&](int s, const std::vector<long> &lo, const std::vector<long> &hi) {
-    brickStencil(st->id, grid_dev, strideb, (s % 2) ? bOut_dev : bIn_dev, (s % 2) ? bIn_dev : bOut_dev, lo, hi, nullptr, nullptr);
+  // time steps per pass: two where the fused kernel pays off (7-point), -F forces one sweep per pass
+  int fuse = S.no_fuse ? 1 : bk_stencil_fused_steps(st->id);
+  if (fuse < 1 || st->st_iter % fuse) fuse = 1;
+  const int npass = st->st_iter / fuse;
+  // pass p reads storage p%2 and writes the other one; the last pass of a period skips the ghost shell
+  auto pass = [&](int p, int part, void *stream) -> bool {
+    const bool last = p == npass - 1;
+    auto &src = (p % 2) ? bOut_dev : bIn_dev;
+    auto &dst = (p % 2) ? bIn_dev : bOut_dev;
+    return brickAdvance(st->id, fuse, grid_dev, strideb, src, dst, last ? skip_lo : full_lo, last ? skip_hi : full_hi,
+                        skip_lo, skip_hi, part, nullptr, stream);
   };
   auto brick_func = [&]() {
     // every rank's previous sweeps are complete before anyone pulls
@@ -142,30 +152,26 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     ev.exchange(comm_stream);
     bkCheck(bk_event_record(evX, comm_stream));
     bkCheck(bk_event_record(c0, nullptr));
-    // sweep 0 in two launches over the same tiles: CTAs that read only my own bricks overlap the pull (compute
+    // pass 0 in two launches over the same tiles: CTAs that read only my own bricks overlap the pull (compute
     // stream), the CTAs that touch the ghost shell follow the pull on the high-priority exchange stream
-    const bool single_sweep = st->st_iter == 1;
-    const std::vector<long> &lo0 = single_sweep ? skip_lo : full_lo, &hi0 = single_sweep ? skip_hi : full_hi;
-    if (brickStencilPart(st->id, grid_dev, strideb, bIn_dev, bOut_dev, lo0, hi0, skip_lo, skip_hi, BK_PART_READY, nullptr,
-                         nullptr)) {
-      brickStencilPart(st->id, grid_dev, strideb, bIn_dev, bOut_dev, lo0, hi0, skip_lo, skip_hi, BK_PART_REST, nullptr,
-                       comm_stream);
+    if (pass(0, BK_PART_READY, nullptr)) {
+      pass(0, BK_PART_REST, comm_stream);
       bkCheck(bk_event_record(evX, comm_stream));
       bkCheck(bk_stream_wait_event(nullptr, evX));
     } else {
+      if (fuse != 1) throw std::runtime_error("fused pass unavailable for this storage layout: rerun with -F");
       bkCheck(bk_stream_wait_event(nullptr, evX));
-      sweep(0, lo0, hi0);
+      brickStencil(st->id, grid_dev, strideb, bIn_dev, bOut_dev, npass == 1 ? skip_lo : full_lo,
+                   npass == 1 ? skip_hi : full_hi, nullptr, nullptr);
     }
     calltime += omp_get_wtime() - t0;
-    // sweep 1 overwrites storage 0, whose skin the neighbours are pulling: wait until every pull has finished
+    // pass 1 overwrites storage 0, whose skin the neighbours are pulling: wait until every pull has finished
     bkCheck(bk_event_sync(evX));
     t0 = omp_get_wtime();
     bar.wait();
     waittime += omp_get_wtime() - t0;
-    for (int s = 1; s < st->st_iter; ++s) {
-      const bool last = s == st->st_iter - 1;
-      sweep(s, last ? skip_lo : full_lo, last ? skip_hi : full_hi);
-    }
+    for (int p = 1; p < npass; ++p)
+      if (!pass(p, BK_PART_ALL, nullptr)) throw std::runtime_error("pass unavailable");
     bkCheck(bk_event_record(c1, nullptr));
     bkCheck(bk_event_sync(c1));
     float ms = 0;
@@ -189,7 +195,7 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     bElem *arr_dev = nullptr, *zero = zeroArray(stride);
     copyToDevice(stride, arr_dev, zero);
     copyFromBrickDevice({(long) dom[0], (long) dom[1], (long) dom[2]}, {PADDING, PADDING, PADDING}, {GZ, GZ, GZ}, arr_dev,
-                        grid_dev, (st->st_iter % 2) ? bOut_dev : bIn_dev);
+                        grid_dev, (npass % 2) ? bOut_dev : bIn_dev);
     copyFromDevice(stride, zero, arr_dev);
     bk_dev_free(arr_dev);
     S.result[rank] = zero;
@@ -225,7 +231,7 @@ int main(int argc, char **argv) {
   int c, sel = 0;
   bool bin = false;
   if (const char *e = getenv("BRICK_RANKS")) S.size = atoi(e);
-  while ((c = getopt(argc, argv, "d:s:I:g:S:vbh")) != -1) switch (c) {
+  while ((c = getopt(argc, argv, "d:s:I:g:S:vbhF")) != -1) switch (c) {
       case 'b': bin = true; break;
       case 'd': parseTuple(optarg, S.dom), sel = sel ? -2 : 1; break;
       case 's': parseTuple(optarg, S.dom), sel = sel ? -2 : 2; break;
@@ -233,6 +239,7 @@ int main(int argc, char **argv) {
       case 'g': S.size = std::stoi(optarg); break;
       case 'S': sname = optarg; break;
       case 'v': S.validate = true; break;
+      case 'F': S.no_fuse = true; break;
       default:
         printf("Program options\n  -h: help\n  -b: process grid of powers of two\n  -d i,j,k: overall domain size\n"
                "  -s i,j,k: per-GPU domain size\n  -I n: exchange periods (default 100)\n  -g n: GPUs = ranks (default 1)\n"

@@ -159,6 +159,24 @@ bool brickStencilPart(int stencil, const unsigned *grid_dev, const std::vector<l
   bkCheck(rc);
   return true;
 }
+/// `steps` (1 or 2) time steps in one pass over HBM (bk_stencil_advance): bOut = stencil^steps(bIn) on [lo,hi), every
+/// intermediate evaluated over the whole grid in shared memory.  part/ready_* as in brickStencilPart (BK_PART_ALL: the
+/// ready box is ignored).  Returns false when no fused kernel exists for this stencil / storage layout.
+template <typename T>
+bool brickAdvance(int stencil, int steps, const unsigned *grid_dev, const std::vector<long> &gdims, T &bIn, T &bOut,
+                  const std::vector<long> &lo, const std::vector<long> &hi, const std::vector<long> &ready_lo,
+                  const std::vector<long> &ready_hi, int part = BK_PART_ALL, const bElem *coeff = nullptr,
+                  void *stream = nullptr) {
+  bk_field_t f = {&bIn.bInfo->adj[0][0], bIn.dat, bIn.step, bOut.dat, bOut.step};
+  unsigned g[3], l[3], h[3], rl[3], rh[3];
+  for (int d = 0; d < 3; ++d)
+    g[d] = (unsigned) gdims[d], l[d] = (unsigned) lo[d], h[d] = (unsigned) hi[d], rl[d] = (unsigned) ready_lo[d],
+    rh[d] = (unsigned) ready_hi[d];
+  const int rc = bk_stencil_advance(stencil, steps, &f, grid_dev, g, l, h, coeff, rl, rh, part, stream);
+  if (rc == BK_EUNSUPPORTED) return false;
+  bkCheck(rc);
+  return true;
+}
 template <typename T>
 void brickStencil(int stencil, const unsigned *grid_dev, const std::vector<long> &gdims, T &bIn, T &bOut,
                   const bElem *coeff = nullptr, void *stream = nullptr) {
