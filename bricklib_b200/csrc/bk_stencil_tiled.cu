@@ -743,12 +743,10 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_star2(const __grid_constant_
   }
 
   // one plane of the star update on my patch: `pb` = plane base, slot u%W of `acc` belongs to this plane's own output;
-  // on return slot (u-R)%W holds the plane this input completes (output index t-R)
-  auto star_plane = [&](const unsigned char *pb, double2 (&acc)[W][YT], const int u) {
+  // `v` = my own cells of the plane (stage A loads them, stage B takes them from stage A's registers); on return slot
+  // (u-R)%W holds the plane this input completes (output index t-R)
+  auto star_plane = [&](const unsigned char *pb, double2 (&acc)[W][YT], const int u, const double2 (&v)[YT]) {
     const int sF = ((u - R) % W + W) % W, s0 = u % W, sN = (u + R) % W;
-    double2 v[YT];
-#pragma unroll
-    for (int r = 0; r < YT; ++r) v[r] = *reinterpret_cast<const double2 *>(pb + own_off + r * 64);
 #pragma unroll
     for (int r = 0; r < YT; ++r) {
       acc[sF][r].x = fma(cf.cp[2][R - 1], v[r].x, acc[sF][r].x);
@@ -837,10 +835,15 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_star2(const __grid_constant_
     for (int u = 0; u < W; ++u) {
       const int n = tb + u;
       if (n <= P) {
+        double2 vmid[YT];  // my own cells of the intermediate plane produced in this iteration
         auto stage_b = [&](const int nb, const int slot, const int uB) {  // intermediate plane nb-H-R -> output nb-2H
           const unsigned char *pmB = mid + slot * C::STAGE;
           const int orel = nb - 2 * H;
-          star_plane(pmB, accB, uB);
+          if constexpr (C::LAG) {
+#pragma unroll
+            for (int r = 0; r < YT; ++r) vmid[r] = *reinterpret_cast<const double2 *>(pmB + own_off + r * 64);
+          }
+          star_plane(pmB, accB, uB, vmid);
           if (orel >= 0) {
             const int sF = ((uB - R) % W + W) % W;
             const int oz = orel & 7;
@@ -862,13 +865,18 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_star2(const __grid_constant_
           unsigned char *pm = mid + msl * C::STAGE;
           const int zm = zabs0 + n - H - R;
           const bool zin = zm >= 0 && zm < zmax;
-          star_plane(pbA, accA, u);
           {
+            double2 vin[YT];
+#pragma unroll
+            for (int r = 0; r < YT; ++r) vin[r] = *reinterpret_cast<const double2 *>(pbA + own_off + r * 64);
+            star_plane(pbA, accA, u, vin);
             const int sF = ((u - R) % W + W) % W;
             const bool ok = zin && own_in;
 #pragma unroll
-            for (int r = 0; r < YT; ++r)
-              *reinterpret_cast<double2 *>(pm + own_off + r * 64) = ok ? accA[sF][r] : make_double2(0.0, 0.0);
+            for (int r = 0; r < YT; ++r) {
+              vmid[r] = ok ? accA[sF][r] : make_double2(0.0, 0.0);
+              *reinterpret_cast<double2 *>(pm + own_off + r * 64) = vmid[r];
+            }
           }
           if (has_strip) {
             const int sF = ((u - R) % W + W) % W, s0 = u % W, sN = (u + R) % W;
