@@ -307,6 +307,9 @@ def main():
     ap.add_argument("--no-fuse", action="store_true", help="one sweep per pass (no temporal blocking)")
     ap.add_argument("--no-extras", action="store_true", help="skip other stencils / e2e / cpu baseline")
     ap.add_argument("--kernel", default="auto", choices=["auto", "brick", "tiled"])
+    ap.add_argument("--transport", default="kernel", choices=["kernel", "ce"],
+                    help="ghost exchange as one pull kernel over NVLink peer mappings (default, faster) or on the copy engines")
+    ap.add_argument("--thin", action="store_true", help="split sweeps with thin ghost-dependent k segments (BK_PART_THIN)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -336,6 +339,7 @@ def main():
             dm.enable_overlap()
         if args.no_fuse:
             dm.fuse = 1
+        dm.transport, dm.thin = args.transport, args.thin
         rng = np.random.default_rng(0x5EED + rank)
         host = rng.random(dm.decomp.nbricks * 512)
         host[:512] = 0.0
@@ -367,7 +371,9 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"weak {args.stencil} {size}^3 per GPU, 8^3 bricks, 1 exchange + {it} sweeps per step",
                    "process_grid": "x".join(map(str, cart)), "exchange_MB_per_gpu_per_step": d.view.bytes / 1e6,
-                   "overlap": not args.no_overlap, "kernel": args.kernel, "steps_per_pass": d.steps_per_pass(),
+                   "overlap": not args.no_overlap, "kernel": args.kernel,
+                   "exchange_transport": "copy engines (faces) + narrow pull kernel (edges, corners) over NVLink peer mappings"
+                   if d._remote() else "one pull kernel over NVLink peer mappings (CUDA IPC)", "steps_per_pass": d.steps_per_pass(),
                    "l2": f"inputs larger than L2: {2 * d.storage[0].dat.nbytes / 1e9:.2f} GB streamed per sweep"},
         "gpu_launches": launches,
         "roofline": roofline_of(pts, sweep_s, sweep_steps, peak, peak_src, traffic),

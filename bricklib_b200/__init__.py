@@ -4,7 +4,7 @@ The product is libbrick_b200.so (CUDA kernels for sm_100a behind the C ABI in in
 the thin host-side mirror of the reference interface used by tests/, bench.py and the weak-scaling loop; the C++
 template surface lives in include/*.h and the drivers in drivers/.
 """
-from ._lib import (BK_OK, KERNEL_AUTO, KERNEL_BRICK, KERNEL_TILED, PART_ALL, PART_READY, PART_REST, STENCILS,  # noqa: F401
+from ._lib import (BK_OK, KERNEL_AUTO, KERNEL_BRICK, KERNEL_TILED, PART_ALL, PART_READY, PART_REST, PART_THIN, STENCILS,  # noqa: F401
                    BrickError, load)
 from .core import (BRICK, Brick, BrickDecomp, BrickInfo, BrickStorage, DeviceBuffer, DeviceGrid, Event,  # noqa: F401
                    ExchangeView, compareBrick, copyFromBrick, copyToBrick, device_sync, init_grid, stencil,

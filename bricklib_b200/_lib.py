@@ -11,7 +11,7 @@ BK_EUNSUPPORTED = -4
 ST_7PT, ST_MPI7PT, ST_MPI13PT, ST_MPI25PT, ST_MPI125PT = range(5)
 STENCILS = {"7pt": 0, "mpi7pt": 1, "mpi13pt": 2, "mpi25pt": 3, "mpi125pt": 4}
 KERNEL_AUTO, KERNEL_BRICK, KERNEL_TILED = 0, 1, 2
-PART_ALL, PART_READY, PART_REST = 0, 1, 2
+PART_ALL, PART_READY, PART_REST, PART_THIN = 0, 1, 2, 4
 IPC_HANDLE_BYTES = 64
 
 vp, sz, u64 = C.c_void_p, C.c_size_t, C.c_uint64
@@ -93,6 +93,7 @@ SIGNATURES = {
     "bk_xplan_run": (C.c_int, [vp, vp]),
     "bk_xplan_run_sync": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, u64, vp]),
     "bk_xplan_run_gate": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, vp, u64, vp]),
+    "bk_xplan_run_ce": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, u64, vp]),
     "bk_flags_signal": (C.c_int, [C.POINTER(vp), C.c_int, u64, vp]),
     "bk_flags_wait": (C.c_int, [C.POINTER(vp), C.c_int, u64, vp]),
     "bk_ipc_export": (C.c_int, [vp, C.c_char_p]),

@@ -306,6 +306,12 @@ class ExchangeView:
         s = (C.c_void_p * max(1, len(signal_flags)))(*signal_flags)
         check(load().bk_xplan_run_gate(self._h, w, len(wait_flags), s, len(signal_flags), gate_ptr, epoch, stream))
 
+    def exchange_ce(self, wait_flags=(), signal_flags=(), epoch=0, stream=None):
+        """the same plan on the copy engines (no SM taken from the sweeps); flags as in exchange_sync"""
+        w = (C.c_void_p * max(1, len(wait_flags)))(*wait_flags)
+        s = (C.c_void_p * max(1, len(signal_flags)))(*signal_flags)
+        check(load().bk_xplan_run_ce(self._h, w, len(wait_flags), s, len(signal_flags), epoch, stream))
+
     def __del__(self):
         try:
             load().bk_xplan_destroy(self._h)

@@ -8,6 +8,8 @@
 // A source pointer may live in a peer GPU (CUDA IPC / peer access): the loads then cross NVLink, which makes this a
 // PULL exchange -- no pack, no unpack, no staging buffer.  The optional flags implement the cross-process handshake.
 #include "bk_common.h"
+#include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 struct bk_xplan {
@@ -18,11 +20,23 @@ struct bk_xplan {
   size_t bytes = 0;
   uint64_t **flagbuf_dev = nullptr;  // scratch for flag pointer lists (64 wait + 64 signal)
   unsigned long long *done_dev = nullptr;  // CTAs that finished, summed over all launches of this plan
+  // copy-engine transport (bk_xplan_run_ce): the segments as host data, dealt largest-first to a few lanes
+  std::vector<bk_seg_t> segs_host;
+  std::vector<int> lane_of;                // segment -> lane, in issue order `order`
+  std::vector<int> order;
+  cudaStream_t lanes[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[4] = {nullptr, nullptr, nullptr, nullptr};
+  int nlanes = 0;
+  bk_seg_t *small_segs_dev = nullptr;              // segments below kCeMinBytes: moved by a narrow pull kernel
+  unsigned long long *small_first_dev = nullptr;
+  int small_nseg = 0;
+  unsigned long long small_nchunks = 0;
 };
 
 namespace {
 
 constexpr unsigned kChunkBytes = 16384;
+constexpr size_t kCeMinBytes = 1u << 20;  // copy-engine transport: smaller segments are cheaper through the kernel
 constexpr int kThreads = 256;
 
 __device__ __forceinline__ void spin_until(const uint64_t *flag, uint64_t value) {
@@ -128,6 +142,7 @@ int bk_xplan_create(bk_xplan_t **out, const bk_seg_t *segs, int nseg) {
     total += segs[i].bytes;
   }
   bk_xplan *p = new bk_xplan();
+  p->segs_host.assign(segs, segs + nseg);
   p->nseg = nseg;
   p->nchunks = first[nseg];
   p->bytes = total;
@@ -150,6 +165,13 @@ int bk_xplan_destroy(bk_xplan_t *p) {
   cudaFree(p->chunk_first_dev);
   cudaFree(p->flagbuf_dev);
   cudaFree(p->done_dev);
+  cudaFree(p->small_segs_dev);
+  cudaFree(p->small_first_dev);
+  for (int l = 0; l < p->nlanes; ++l) {
+    cudaStreamDestroy(p->lanes[l]);
+    cudaEventDestroy(p->ev_join[l]);
+  }
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   delete p;
   return BK_OK;
 }
@@ -192,6 +214,90 @@ int bk_xplan_run_gate(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwai
   for (int i = 0; i < nsignal; ++i) host[65 + i] = signal_flags[i];
   BK_CUDA(cudaMemcpyAsync(p->flagbuf_dev, host, sizeof(host), cudaMemcpyHostToDevice, s));
   return launch_copy(p, p->flagbuf_dev, nwait, s, nsignal, gate, true);
+}
+
+// The same plan with the big segments on the COPY ENGINES: no SM is taken from the sweep kernels, which matters because
+// the marching kernels allocate the whole register file of an SM (a pull CTA cannot co-reside with them: a kernel-driven
+// exchange and the sweep time-share SMs instead of overlapping).  On `stream`: a NARROW pull kernel (<= 32 CTAs) waits
+// for the peers' ready flags and moves the small segments (edges, corners: a few MB, not worth 36 API calls); then the
+// big segments (the six faces) fan out over a few lane streams as one cudaMemcpyAsync each (peer sources cross NVLink
+// through the IPC / peer mappings); join; one tiny kernel raises the done flags.
+int bk_xplan_run_ce(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwait, uint64_t *const *signal_flags,
+                    int nsignal, uint64_t epoch, void *stream) {
+  BK_REQUIRE(p, "null plan");
+  BK_REQUIRE(nwait >= 0 && nwait <= 64 && nsignal >= 0 && nsignal <= 64, "at most 64 flags each");
+  cudaStream_t s = (cudaStream_t) stream;
+  if (p->nlanes == 0) {
+    int lo = 0, hi = 0;
+    BK_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    for (int l = 0; l < 4; ++l) {
+      BK_CUDA(cudaStreamCreateWithPriority(&p->lanes[l], cudaStreamNonBlocking, hi));
+      BK_CUDA(cudaEventCreateWithFlags(&p->ev_join[l], cudaEventDisableTiming));
+    }
+    BK_CUDA(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    std::vector<bk_seg_t> small;
+    size_t ce_min = kCeMinBytes;
+    if (const char *e = getenv("BK_CE_MIN_BYTES")) ce_min = (size_t) atoll(e);  // tests: exercise both halves on small domains
+    for (int i = 0; i < p->nseg; ++i) {
+      if (p->segs_host[i].bytes >= ce_min) p->order.push_back(i);
+      else if (p->segs_host[i].bytes) small.push_back(p->segs_host[i]);
+    }
+    std::stable_sort(p->order.begin(), p->order.end(),
+                     [&](int a, int b) { return p->segs_host[a].bytes > p->segs_host[b].bytes; });
+    size_t load[4] = {0, 0, 0, 0};
+    p->lane_of.assign(p->nseg, 0);
+    for (int i : p->order) {
+      int best = 0;
+      for (int l = 1; l < 4; ++l)
+        if (load[l] < load[best]) best = l;
+      p->lane_of[i] = best;
+      load[best] += p->segs_host[i].bytes;
+    }
+    std::vector<unsigned long long> first(small.size() + 1, 0);
+    for (size_t i = 0; i < small.size(); ++i) first[i + 1] = first[i] + (small[i].bytes + kChunkBytes - 1) / kChunkBytes;
+    p->small_nseg = (int) small.size();
+    p->small_nchunks = first[small.size()];
+    if (!small.empty()) {
+      BK_CUDA(cudaMalloc(&p->small_segs_dev, sizeof(bk_seg_t) * small.size()));
+      BK_CUDA(cudaMemcpy(p->small_segs_dev, small.data(), sizeof(bk_seg_t) * small.size(), cudaMemcpyHostToDevice));
+    }
+    BK_CUDA(cudaMalloc(&p->small_first_dev, sizeof(unsigned long long) * first.size()));
+    BK_CUDA(cudaMemcpy(p->small_first_dev, first.data(), sizeof(unsigned long long) * first.size(), cudaMemcpyHostToDevice));
+    p->nlanes = 4;
+  }
+  uint64_t *host[130] = {nullptr};
+  for (int i = 0; i < nwait; ++i) host[i] = const_cast<uint64_t *>(wait_flags[i]);
+  host[64] = (uint64_t *) (size_t) epoch;
+  for (int i = 0; i < nsignal; ++i) host[65 + i] = signal_flags[i];
+  if (nwait > 0 || nsignal > 0)
+    BK_CUDA(cudaMemcpyAsync(p->flagbuf_dev, host, sizeof(host), cudaMemcpyHostToDevice, s));
+  if (p->small_nchunks > 0 || nwait > 0) {
+    const unsigned grid = (unsigned) std::max(1ull, std::min(p->small_nchunks, 32ull));
+    k_xplan<<<grid, kThreads, 0, s>>>(p->small_segs_dev, p->small_first_dev, p->small_nseg, p->small_nchunks,
+                                      p->flagbuf_dev, nwait, 0, nullptr, nullptr);
+    BK_LAUNCHED();
+  }
+  if (!p->order.empty()) {
+    BK_CUDA(cudaEventRecord(p->ev_fork, s));
+    bool used[4] = {false, false, false, false};
+    for (int i : p->order) {
+      const bk_seg_t &g = p->segs_host[i];
+      const int l = p->lane_of[i];
+      if (!used[l]) BK_CUDA(cudaStreamWaitEvent(p->lanes[l], p->ev_fork, 0));
+      used[l] = true;
+      BK_CUDA(cudaMemcpyAsync(g.dst, g.src, g.bytes, cudaMemcpyDefault, p->lanes[l]));
+    }
+    for (int l = 0; l < 4; ++l)
+      if (used[l]) {
+        BK_CUDA(cudaEventRecord(p->ev_join[l], p->lanes[l]));
+        BK_CUDA(cudaStreamWaitEvent(s, p->ev_join[l], 0));
+      }
+  }
+  if (nsignal > 0) {
+    k_signal<<<1, 64, 0, s>>>(p->flagbuf_dev + 65, nsignal, epoch);
+    BK_LAUNCHED();
+  }
+  return BK_OK;
 }
 
 int bk_flags_signal(uint64_t *const *flags, int n, uint64_t value, void *stream) {

@@ -236,7 +236,8 @@ int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid
                           const unsigned *ready_hi, int part, void *stream) {
   BK_REQUIRE(stencil >= 0 && stencil < BK_ST_COUNT, "unknown stencil id");
   BK_REQUIRE(f && f->adj && f->in && f->out && grid && gdims && lo && hi && ready_lo && ready_hi, "null argument");
-  BK_REQUIRE(part == BK_PART_READY || part == BK_PART_REST, "part must be BK_PART_READY or BK_PART_REST");
+  BK_REQUIRE((part & ~BK_PART_THIN) == BK_PART_READY || (part & ~BK_PART_THIN) == BK_PART_REST,
+             "part must be BK_PART_READY or BK_PART_REST (optionally | BK_PART_THIN)");
   BK_REQUIRE(f->in_step >= 512 && f->out_step >= 512, "brick step smaller than a brick");
   BK_REQUIRE(f->in != f->out, "in-place sweep is not defined");
   BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
@@ -251,7 +252,9 @@ int bk_stencil_advance(int stencil, int steps, const bk_field_t *f, const unsign
   BK_REQUIRE(stencil >= 0 && stencil < BK_ST_COUNT, "unknown stencil id");
   BK_REQUIRE(steps == 1 || steps == 2, "steps must be 1 or 2");
   BK_REQUIRE(f && f->adj && f->in && f->out && grid && gdims && lo && hi, "null argument");
-  BK_REQUIRE(part == BK_PART_ALL || (ready_lo && ready_hi && (part == BK_PART_READY || part == BK_PART_REST)), "bad part");
+  BK_REQUIRE(part == BK_PART_ALL ||
+                 (ready_lo && ready_hi && ((part & ~BK_PART_THIN) == BK_PART_READY || (part & ~BK_PART_THIN) == BK_PART_REST)),
+             "bad part");
   BK_REQUIRE(f->in_step >= 512 && f->out_step >= 512, "brick step smaller than a brick");
   BK_REQUIRE(f->in != f->out, "in-place sweep is not defined");
   BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");

@@ -46,6 +46,7 @@ struct TiledArgs {
   int lo[3], hi[3];
   int ntx;  // tiles along i
   int kl;   // brick layers per k segment
+  int kh, kt;  // split launches: thin head / tail segments (layers) that keep the ghost-dependent CTAs few; else 0
   const bk_field_t *multi;  // strong-scaling launch: per-subdomain fields (device array), subdomain = blockIdx.z
   // CTA enumeration: blockIdx.x runs through up to 6 boxes of the (tile i, tile j, k segment) space in order.  A plain
   // launch has one box.  A split launch (bk_stencil_apply_part) runs either the CTAs whose whole read footprint lies
@@ -56,6 +57,24 @@ struct TiledArgs {
     int lo[3], dim[3], first;
   } box[6];
 };
+
+// k range of segment `q`: [head of kh layers] [uniform segments of kl layers] [tail of kt layers]
+__host__ __device__ __forceinline__ void seg_range(const TiledArgs &a, int q, int &kb0, int &nl) {
+  const int nz = a.hi[2] - a.lo[2], mid = nz - a.kh - a.kt;
+  if (a.kh > 0) {
+    if (q == 0) {
+      kb0 = a.lo[2], nl = a.kh;
+      return;
+    }
+    --q;
+  }
+  if (q * a.kl < mid) {
+    kb0 = a.lo[2] + a.kh + q * a.kl;
+    nl = min(a.kl, mid - q * a.kl);
+  } else {
+    kb0 = a.hi[2] - a.kt, nl = a.kt;
+  }
+}
 
 // ---- PTX helpers ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -151,8 +170,8 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
   const int ty = a.box[bq].lo[1] + brel % a.box[bq].dim[1];
   const int tseg = a.box[bq].lo[2] + brel / a.box[bq].dim[1];
   const int i0 = a.lo[0] + tx * TI, j0 = a.lo[1] + ty * TJ;
-  const int kb0 = a.lo[2] + tseg * a.kl;
-  const int nl = min(a.kl, a.hi[2] - kb0);  // brick layers in this segment
+  int kb0, nl;  // first brick layer and number of layers of this segment
+  seg_range(a, tseg, kb0, nl);
   const int P = nl * 8 + 2 * RUP;            // planes streamed; plane t is absolute plane kb0*8 - RUP + t
   const int NS = P / G;
 
@@ -581,8 +600,8 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_star2(const __grid_constant_
   const int ty = a.box[bq].lo[1] + brel % a.box[bq].dim[1];
   const int tseg = a.box[bq].lo[2] + brel / a.box[bq].dim[1];
   const int i0 = a.lo[0] + tx * TI, j0 = a.lo[1] + ty * TJ;
-  const int kb0 = a.lo[2] + tseg * a.kl;
-  const int nl = min(a.kl, a.hi[2] - kb0);
+  int kb0, nl;
+  seg_range(a, tseg, kb0, nl);
   const int nout = nl * 8;
   const int P = nout + 2 * H;  // input planes streamed: relative planes -H .. nout+H-1
 
@@ -1002,9 +1021,20 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, 
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NT, C::SMEM);
     slots = sms * (per_sm > 0 ? per_sm : 1);
   }
-  a.kl = pick_segment_layers((long) a.ntx * nty * nsub, nz, slots, C::OVH);
+  // split launches: the layers whose CTAs read not-yet-ready bricks get thin segments of their own, so that the READY
+  // part (which overlaps the exchange) is as large as possible
+  a.kh = a.kt = 0;
+  const bool thin = (part & BK_PART_THIN) != 0;
+  part &= ~BK_PART_THIN;
+  if (part != BK_PART_ALL && thin) {
+    a.kh = std::max(0, std::min(nz, rdy_lo[2] + 1 - a.lo[2]));
+    a.kt = std::max(0, std::min(nz - a.kh, a.hi[2] - (rdy_hi[2] - 1)));
+    if (nz - a.kh - a.kt <= 0) a.kh = a.kt = 0;
+  }
+  const int nmid = nz - a.kh - a.kt;
+  a.kl = pick_segment_layers((long) a.ntx * nty * nsub, nmid, slots, C::OVH);
   if (const char *e = getenv("BK_STAR_KL")) a.kl = atoi(e) > 0 ? atoi(e) : a.kl;  // developer knob
-  const int segs = (nz + a.kl - 1) / a.kl;
+  const int segs = (nmid + a.kl - 1) / a.kl + (a.kh > 0) + (a.kt > 0);
   // CTA boxes.  "inner" = CTAs whose whole read footprint (tile + 1 brick all round) lies in the ready box
   int in_lo[3] = {0, 0, 0}, in_hi[3] = {0, 0, 0};
   const int ext[3] = {a.ntx, nty, segs};
@@ -1017,8 +1047,9 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, 
       in_lo[d] = l, in_hi[d] = h;
     }
     int l = 0, h = segs;
-    auto seg_end = [&](int q) { return a.lo[2] + (q * a.kl + a.kl < nz ? q * a.kl + a.kl : nz); };
-    while (l < h && a.lo[2] + l * a.kl - 1 < rdy_lo[2]) ++l;
+    auto seg_lo = [&](int q) { int b, n; seg_range(a, q, b, n); return b; };
+    auto seg_end = [&](int q) { int b, n; seg_range(a, q, b, n); return b + n; };
+    while (l < h && seg_lo(l) - 1 < rdy_lo[2]) ++l;
     while (h > l && seg_end(h - 1) + 1 > rdy_hi[2]) --h;
     in_lo[2] = l, in_hi[2] = h;
   }
@@ -1039,12 +1070,13 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, 
   } else if (!has_inner) {
     add_box(0, ext[0], 0, ext[1], 0, ext[2]);
   } else {
-    add_box(0, ext[0], 0, ext[1], 0, in_lo[2]);                          // segments below / above
-    add_box(0, ext[0], 0, ext[1], in_hi[2], ext[2]);
+    // long CTAs first (blockIdx order = dispatch order): the thin head / tail segments then fill the ragged end
     add_box(0, ext[0], 0, in_lo[1], in_lo[2], in_hi[2]);                 // tile rows before / after
     add_box(0, ext[0], in_hi[1], ext[1], in_lo[2], in_hi[2]);
     add_box(0, in_lo[0], in_lo[1], in_hi[1], in_lo[2], in_hi[2]);        // tile columns left / right
     add_box(in_hi[0], ext[0], in_lo[1], in_hi[1], in_lo[2], in_hi[2]);
+    add_box(0, ext[0], 0, ext[1], 0, in_lo[2]);                          // segments below / above
+    add_box(0, ext[0], 0, ext[1], in_hi[2], ext[2]);
   }
   if (first == 0) return BK_OK;
   dim3 grid((unsigned) first, 1, nsub);
@@ -1066,7 +1098,7 @@ int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, 
   a.in = f.in, a.out = f.out, a.in_step = f.in_step, a.out_step = f.out_step, a.grid = grid;
   a.gx = (int) gdims[0], a.gy = (int) gdims[1], a.gz = (int) gdims[2];
   for (int d = 0; d < 3; ++d) a.lo[d] = (int) lo[d], a.hi[d] = (int) hi[d];
-  a.ntx = a.kl = 0;
+  a.ntx = a.kl = a.kh = a.kt = 0;
   a.multi = multi_dev;
   a.nbox = 0;
   int rdy_lo[3] = {0, 0, 0}, rdy_hi[3] = {0, 0, 0};

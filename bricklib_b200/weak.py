@@ -64,6 +64,14 @@ class WeakDomain:
         self.epoch = 0
         self.comm_stream = None
         self.ev_comm = self.ev_comp = None
+        # "ce": ghost ranges move on the copy engines (no SM taken from the sweeps -- the marching kernels fill an SM's
+        # register file, so a pull kernel would time-share SMs with them); "kernel": one pull kernel (k_xplan)
+        # ghost transport: "kernel" = one pull kernel over NVLink peer mappings (k_xplan; the default -- measured faster at
+        # every N), "ce" = faces on the copy engines + narrow kernel for edges/corners (bk_xplan_run_ce; takes no SM, but
+        # 104 MB from 7 peers took 0.55 ms at N=8 against ~0.15 ms for the kernel: profiles/r01c_multi_gpu.md)
+        self.transport = "kernel"
+        self.thin = False    # split sweeps: thin k segments for the ghost-dependent layers (BK_PART_THIN)
+        self.trace = None    # developer aid: a list collects (label, Event) marks of one period (tools/period_trace.py)
         self.fuse = 2        # time steps per pass where a fused kernel exists (7/13-point); 1 = one sweep per pass
 
     # ---- wiring -------------------------------------------------------------------------------------------------
@@ -109,24 +117,40 @@ class WeakDomain:
 
     def _exchange(self, stream, fused_signal=False):
         hs, e = self.hs, self.epoch
+        ce = self._remote() and fused_signal      # only next to overlapped sweeps; else the kernel is faster
         if hs is None or not self.peers:
-            self.view.exchange(stream)
+            if ce:
+                self.view.exchange_ce(stream=stream)
+            else:
+                self.view.exchange(stream)
             return
         # tell every peer my skin is final, pull theirs once they say the same, then tell them I am done reading
         sig = (C.c_void_p * len(self.peers))(*[hs.ready_flag_on(p, self.rank) for p in self.peers])
         check(load().bk_flags_signal(sig, len(self.peers), e, stream))
         waits = [hs.ready_flag_on(self.rank, p) for p in self.peers]
         dones = [hs.done_flag_on(p, self.rank) for p in self.peers]
-        if fused_signal:   # the pull kernel's last CTA raises the done flags itself
+        if ce:
+            self.view.exchange_ce(waits, dones, e, stream)
+        elif fused_signal:   # the pull kernel's last CTA raises the done flags itself
             self.view.exchange_gate(waits, dones, None, e, stream)
         else:
             self.view.exchange_sync(waits, dones, e, stream)
+
+    def _remote(self):
+        """does the exchange run on the copy engines (and the split sweep with thin ghost-dependent segments)?"""
+        return self.transport == "ce"
 
     def _wait_peers_done(self, stream):
         if self.hs is None or not self.peers:
             return
         w = (C.c_void_p * len(self.peers))(*[self.hs.done_flag_on(self.rank, p) for p in self.peers])
         check(load().bk_flags_wait(w, len(self.peers), self.epoch, stream))
+
+    def _mark(self, label, stream):
+        if self.trace is not None:
+            ev = core.Event()
+            ev.record(stream)
+            self.trace.append((label, ev))
 
     def period(self, stream=None):
         """one exchange + ST_ITER time steps; returns the number of kernel launches issued.
@@ -142,10 +166,12 @@ class WeakDomain:
         fuse = self.steps_per_pass()
         cs = self.comm_stream
         overlap = cs is not None and self.kernel != _lib.KERNEL_BRICK
+        self._mark("start", stream)
         if cs is not None:
             self.ev_comp.record(stream)
             check(load().bk_stream_wait_event(cs, self.ev_comp.h))  # previous period's sweeps wrote the skin
         self._exchange(cs if cs is not None else stream, fused_signal=cs is not None)
+        self._mark("exchange done", cs if cs is not None else stream)
         done, p = 0, 0
         while done < self.st_iter:
             src, dst = p % 2, 1 - p % 2
@@ -155,8 +181,11 @@ class WeakDomain:
                 self._wait_peers_done(stream)  # pass 1 rewrites storage[0], whose skin the peers were reading
             if p == 0 and overlap and not last:
                 try:
-                    self._advance(fuse, src, dst, lo, hi, own, _lib.PART_READY, stream)
-                    self._advance(fuse, src, dst, lo, hi, own, _lib.PART_REST, cs)
+                    thin = _lib.PART_THIN if (self.thin or self._remote()) else 0
+                    self._advance(fuse, src, dst, lo, hi, own, _lib.PART_READY | thin, stream)
+                    self._mark("pass 0 READY done", stream)
+                    self._advance(fuse, src, dst, lo, hi, own, _lib.PART_REST | thin, cs)
+                    self._mark("pass 0 REST done", cs)
                     self.ev_comm.record(cs)
                     check(load().bk_stream_wait_event(stream, self.ev_comm.h))
                     done, p = done + fuse, p + 1
@@ -176,6 +205,7 @@ class WeakDomain:
                     raise
                 fuse = 1
                 continue
+            self._mark(f"pass {p} done", stream)
             done, p = done + fuse, p + 1
         assert p % 2 == 0 or self.st_iter % 2 == 1, "result must end in storage[0]"
         return load().bk_launch_count() - n0

@@ -145,6 +145,10 @@ int bk_stencil_apply(int stencil, const bk_field_t *f, const unsigned *grid_dev,
 #define BK_PART_ALL 0
 #define BK_PART_READY 1
 #define BK_PART_REST 2
+/* OR-ed into READY / REST (both launches of a split must agree): the brick layers whose CTAs read not-yet-ready bricks
+ * get thin k segments of their own, which raises the READY share of the sweep from ~45 % to ~70 % at 512^3 at the price
+ * of a few per cent more halo planes.  Worth it when the exchange is slow (crosses NVLink), not for self-exchanges. */
+#define BK_PART_THIN 4
 int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid_dev, const unsigned *gdims,
                           const unsigned *lo, const unsigned *hi, const double *coeff_host, const unsigned *ready_lo,
                           const unsigned *ready_hi, int part, void *stream);
@@ -192,6 +196,12 @@ int bk_xplan_run_sync(bk_xplan_t *plan, const uint64_t *const *wait_flags, int n
  * `gate` (optional extra flag in local device memory) -- no separate signal launch. */
 int bk_xplan_run_gate(bk_xplan_t *plan, const uint64_t *const *wait_flags, int nwait, uint64_t *const *signal_flags,
                       int nsignal, uint64_t *gate, uint64_t epoch, void *stream);
+/* the same plan executed by the COPY ENGINES (one cudaMemcpyAsync per segment on a few internal lane streams, forked
+ * from and joined to `stream`), bracketed by the flag wait / flag signal kernels.  Takes no SM from the sweep kernels --
+ * they allocate an SM's whole register file, so a pull KERNEL cannot co-reside with them and the exchange would
+ * time-share the SMs instead of overlapping.  Same handshake semantics as bk_xplan_run_sync. */
+int bk_xplan_run_ce(bk_xplan_t *plan, const uint64_t *const *wait_flags, int nwait, uint64_t *const *signal_flags,
+                    int nsignal, uint64_t epoch, void *stream);
 /* tiny kernels for the handshake on a stream: store `value` to n flags / spin until n flags >= value */
 int bk_flags_signal(uint64_t *const *flags, int n, uint64_t value, void *stream);
 int bk_flags_wait(const uint64_t *const *flags, int n, uint64_t value, void *stream);

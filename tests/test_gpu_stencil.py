@@ -124,12 +124,49 @@ def test_two_steps_per_pass_equal_two_sweeps(dom, st):
         assert rel(got, want) < 1e-14, (lo, hi)
         assert np.array_equal(got == 0.0, want == 0.0), "bricks outside the box must stay untouched"
         own = ((1, 1, 1), tuple(x - 1 for x in t))
+        for thin in (0, bk.PART_THIN):  # uniform k segments / thin segments for the ghost-dependent layers
+            s_got.dat.zero()
+            bk.stencil_advance(st, 2, grid, b_in, b_got, lo, hi, own, bk.PART_READY | thin)
+            bk.device_sync()
+            part1 = s_got.to_host()
+            s_got.dat.zero()
+            bk.stencil_advance(st, 2, grid, b_in, b_got, lo, hi, own, bk.PART_REST | thin)
+            bk.device_sync()
+            part2 = s_got.to_host()
+            assert not np.any((part1 != 0.0) & (part2 != 0.0)), "READY and REST overlap"
+            assert rel(part1 + part2, want) < 1e-14
+
+
+@pytest.mark.parametrize("st", [1, 2, 3, 4])
+@pytest.mark.parametrize("dom", [(64, 64, 64), (40, 24, 104)])
+def test_split_sweep_covers_the_box_exactly_once(dom, st):
+    """bk_stencil_advance(steps=1, READY) + (REST) == one whole-box sweep, with and without thin k segments; the READY
+    part must not depend on ghost bricks (it is computed here with the ghost shell poisoned)"""
+    rng = np.random.default_rng(9)
+    d = bk.BrickDecomp(dom, 8)
+    info = d.getBrickInfo()
+    grid = bk.DeviceGrid(d.grid)
+    s_in, s_poison, s_ref, s_got = (info.allocate(512) for _ in range(4))
+    h = rng.random(d.nbricks * 512)
+    h[:512] = 0.0
+    s_in.from_host(h)
+    hp = h.copy()
+    hp[d.sep_pos[1] * 512:] = np.nan      # ghost bricks
+    s_poison.from_host(hp)
+    b_in, b_poison, b_ref, b_got = (bk.Brick(info, s) for s in (s_in, s_poison, s_ref, s_got))
+    t = grid.dims
+    own = ((1, 1, 1), tuple(x - 1 for x in t))
+    bk.stencil(st, grid, b_in, b_ref, kernel=bk.KERNEL_TILED)
+    bk.device_sync()
+    want = s_ref.to_host()
+    for thin in (0, bk.PART_THIN):
         s_got.dat.zero()
-        bk.stencil_advance(st, 2, grid, b_in, b_got, lo, hi, own, bk.PART_READY)
+        bk.stencil_advance(st, 1, grid, b_poison, b_got, (0, 0, 0), t, own, bk.PART_READY | thin)
         bk.device_sync()
         part1 = s_got.to_host()
+        assert not np.isnan(part1).any(), "READY read a ghost brick"
         s_got.dat.zero()
-        bk.stencil_advance(st, 2, grid, b_in, b_got, lo, hi, own, bk.PART_REST)
+        bk.stencil_advance(st, 1, grid, b_in, b_got, (0, 0, 0), t, own, bk.PART_REST | thin)
         bk.device_sync()
         part2 = s_got.to_host()
         assert not np.any((part1 != 0.0) & (part2 != 0.0)), "READY and REST overlap"
@@ -165,6 +202,28 @@ def test_weak_period_fused_passes_against_reference_fixture(golden_dir, fuse, ov
         assert rel(d.read_interior(0), z["out_c111_" + name]) < TOL, name
         if fuse == 2 and st == 1 and not overlap:
             assert launches[0] == 1 + oracle.ST_ITER[st] // 2, "exchange + one launch per two steps"
+
+
+@pytest.mark.parametrize("transport,ce_min", [("kernel", None), ("ce", "4096"), ("ce", "0")])
+def test_weak_period_exchange_transports_agree_with_reference_fixture(golden_dir, monkeypatch, transport, ce_min):
+    """the overlapped period with the ghost ranges moved by the pull kernel, by the copy engines (faces) plus the narrow
+    kernel (edges, corners), or by the copy engines alone"""
+    if ce_min is not None:
+        monkeypatch.setenv("BK_CE_MIN_BYTES", ce_min)
+    z = np.load(os.path.join(golden_dir, "weak_steps.npz"))
+    dom = (24, 16, 32)
+    for name, st in bk.STENCILS.items():
+        if st == 0:
+            continue
+        d = bk.WeakDomain(dom, st)
+        d.transport = transport
+        d.connect()
+        d.load_interior(z["in_c111"])
+        d.enable_overlap()
+        for _ in range(2):
+            d.period()
+        bk.device_sync()
+        assert rel(d.read_interior(0), z["out_c111_" + name]) < TOL, (name, transport)
 
 
 class CudaBackend:
