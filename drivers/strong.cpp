@@ -10,8 +10,18 @@
 // plan (ghost <- owner's skin, read through NVLink peer pointers when the owner is another GPU): no pack, no unpack,
 // one kernel.  All subdomains of a rank are swept by one launch (bk_stencil_apply_multi, strong/main.cu:85-99).
 //
+// Stitched mode (default whenever a rank's Z-Morton section is a box of subdomains -- always for power-of-two rank
+// counts): the GPU analogue of the reference's mmap ghost aliasing (strong/main.cpp:205-262).  The rank's subdomains are
+// presented to the marching kernel as ONE dense brick grid ("super grid") whose entries are global brick ids
+// (subdomain * nbricks + local id) into the rank's two subdomain-major allocations: interior positions name the owning
+// subdomain's interior brick, the one-brick shell names the ghost brick of the nearest boundary subdomain, and on an
+// axis where the box spans the whole periodic domain the shell simply aliases the interior bricks of the far side.
+// Same-GPU ghost regions are then never copied and never recomputed; only the regions on the box surface are pulled
+// (from the owners' skins, over NVLink).  -M selects the per-subdomain launch instead.
+//
 // usage: strong [-d global_edge=512] [-s subdomain_edge=128] [-I periods=100] [-g gpus=1] [-S stencil] [-v]
 #include <unistd.h>
+#include <array>
 #include <thread>
 #include "common.h"
 
@@ -21,11 +31,12 @@ struct Shared {
   int size = 1, iters = 100;
   unsigned dom_size = 512, sdom_size = 128;
   const StencilDef *st = nullptr;
-  bool validate = false;
+  bool validate = false, no_stitch = false;
   unsigned long subdim = 4, allsubs = 64;
   std::vector<bElem *> base;  // rank -> device address of field 0 of its first subdomain
   std::vector<double> calc, call, wait, total, mbytes;
   std::vector<size_t> parts;
+  std::vector<int> stitched;  // rank -> swept as one super grid?
   bElem *global_in = nullptr;
   std::vector<std::vector<bElem>> result;  // rank -> interiors of its subdomains, concatenated
 };
@@ -139,11 +150,62 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
   S.base[rank] = st0.dat.get();
   bar.wait();
 
-  // link every ghost region to its owner's skin region (strong/main.cu:188-247), one pull plan for all of them
+  // ---- stitched super grid: is my section a box of subdomains? -----------------------------------------------------
+  const long B = STRIDEB - 2;  // bricks per subdomain edge
+  unsigned long blo[3] = {~0ul, ~0ul, ~0ul}, bhi[3] = {0, 0, 0};
+  std::vector<std::array<unsigned long, 3>> subc(nsub);
+  for (unsigned q = 0; q < nsub; ++q) {
+    unsigned long c[3];
+    bk_zmort_decode(mysec_l + q, c);
+    for (int d = 0; d < 3; ++d) subc[q][d] = c[d], blo[d] = std::min(blo[d], c[d]), bhi[d] = std::max(bhi[d], c[d]);
+  }
+  long bn[3];
+  bool wrap[3];
+  for (int d = 0; d < 3; ++d) bn[d] = (long) (bhi[d] - blo[d] + 1), wrap[d] = (unsigned long) bn[d] == S.subdim;
+  const bool stitched = !S.no_stitch && (unsigned long) (bn[0] * bn[1] * bn[2]) == nsub &&
+                        (unsigned long long) nsub * nb < (1ull << 32);
+  S.stitched[rank] = stitched;
+  unsigned *sgrid_dev = nullptr;
+  std::vector<long> sgd = {bn[0] * B + 2, bn[1] * B + 2, bn[2] * B + 2};
+  if (stitched) {
+    std::vector<unsigned> sg((size_t) sgd[0] * sgd[1] * sgd[2]);
+    for (long K = 0; K < sgd[2]; ++K)
+      for (long J = 0; J < sgd[1]; ++J)
+        for (long I = 0; I < sgd[0]; ++I) {
+          const long p[3] = {I - 1, J - 1, K - 1};  // brick position relative to the box, -1 .. n
+          unsigned long cs[3];
+          long lb[3];
+          for (int d = 0; d < 3; ++d) {
+            const long n = bn[d] * B;
+            long pw = p[d];
+            if (wrap[d]) pw = (pw + n) % n;          // periodic onto myself: alias the far side's interior brick
+            const long cl = std::min(std::max(pw, 0l), n - 1) / B;  // nearest subdomain of the box along this axis
+            cs[d] = blo[d] + (unsigned long) cl;
+            lb[d] = pw - cl * B + 1;                 // position in that subdomain's ghost-inclusive brick grid
+          }
+          const unsigned long q = bk_zmort_encode(cs) - mysec_l;
+          sg[((size_t) K * sgd[1] + J) * sgd[0] + I] = (unsigned) (q * nb + bDecomp[lb[2]][lb[1]][lb[0]]);
+        }
+    copyToDevice(sgd, sgrid_dev, sg.data());
+  }
+
+  // link every ghost region to its owner's skin region (strong/main.cu:188-247), one pull plan for all of them.
+  // Stitched: only regions on the surface of my box are ever read -- a region is needed iff every axis its direction
+  // moves along leaves the box there (and the box does not wrap onto itself along it).
   std::vector<bk_seg_t> segs;
   size_t remote_bytes = 0, peers_mask = 0;
   for (unsigned q = 0; q < nsub; ++q)
     for (size_t i = 0; i < bDecomp.ghost.size(); ++i) {
+      if (stitched) {
+        bool needed = true;
+        for (int d = 0; d < 3; ++d) {
+          const BitSet &n = bDecomp.ghost[i].neighbor;
+          const int off = n.get(d + 1) ? 1 : n.get(-1 - d) ? -1 : 0;
+          if (off == 0) continue;
+          if (wrap[d] || (off > 0 ? subc[q][d] != bhi[d] : subc[q][d] != blo[d])) needed = false;
+        }
+        if (!needed) continue;
+      }
       int dst;
       unsigned long sub;
       sec.owner(neighbour_id(mysec_l + q, bDecomp.ghost[i].neighbor, S.subdim), dst, sub);
@@ -165,6 +227,17 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
   const unsigned full_lo[3] = {0, 0, 0}, full_hi[3] = {gd[0], gd[1], gd[2]};
   const unsigned skip_lo[3] = {1, 1, 1}, skip_hi[3] = {gd[0] - 1, gd[1] - 1, gd[2] - 1};
   double calctime = 0, calltime = 0, waittime = 0;
+  // stitched sweeps: whole-allocation views, sweep box per axis, passes of `fuse` time steps
+  BrickStorage vA = st0, vB = st1;
+  Brick3D sA(&bInfo_dev, vA, (unsigned) 0), sB(&bInfo_dev, vB, (unsigned) 0);
+  std::vector<long> sw_lo(3), sw_hi(3), own_lo(3), own_hi(3);
+  for (int d = 0; d < 3; ++d) {
+    own_lo[d] = 1, own_hi[d] = sgd[d] - 1;
+    sw_lo[d] = wrap[d] ? 1 : 0, sw_hi[d] = wrap[d] ? sgd[d] - 1 : sgd[d];
+  }
+  int fuse = bk_stencil_fused_steps(st->id);
+  if (fuse < 1 || st->st_iter % fuse || (st->st_iter / fuse) % 2) fuse = 1;
+  const int npass = st->st_iter / fuse;
 
   auto brick_func = [&]() {
     bkCheck(bk_event_record(evDone, nullptr));
@@ -183,10 +256,22 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     bar.wait();  // every pull has finished before a skin is overwritten
     waittime += omp_get_wtime() - t0;
     bkCheck(bk_event_record(c0, nullptr));
-    for (int sw = 0; sw < st->st_iter; ++sw) {
-      const bool last = sw == st->st_iter - 1;
-      bkCheck(bk_stencil_apply_multi(st->id, (sw % 2) ? f10_dev : f01_dev, nsub, grid_dev, gd, last ? skip_lo : full_lo,
-                                     last ? skip_hi : full_hi, nullptr, nullptr));
+    if (stitched) {
+      // one sweep (or fused pass of two time steps) over the whole super grid; the shell is swept only along axes whose
+      // shell is real ghost storage (communication avoiding, weak/main.cu:275-285), never where it aliases my interior
+      for (int p = 0; p < npass; ++p) {
+        const bool last = p == npass - 1;
+        Brick3D &src = (p % 2) ? sB : sA, &dst = (p % 2) ? sA : sB;
+        if (!brickAdvance(st->id, fuse, sgrid_dev, sgd, src, dst, last ? own_lo : sw_lo, last ? own_hi : sw_hi, own_lo,
+                          own_hi, BK_PART_ALL, nullptr, nullptr))
+          throw std::runtime_error("marching kernel unavailable for the stitched grid: rerun with -M");
+      }
+    } else {
+      for (int sw = 0; sw < st->st_iter; ++sw) {
+        const bool last = sw == st->st_iter - 1;
+        bkCheck(bk_stencil_apply_multi(st->id, (sw % 2) ? f10_dev : f01_dev, nsub, grid_dev, gd, last ? skip_lo : full_lo,
+                                       last ? skip_hi : full_hi, nullptr, nullptr));
+      }
     }
     bkCheck(bk_event_record(c1, nullptr));
     bkCheck(bk_event_sync(c1));
@@ -216,7 +301,7 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     for (unsigned q = 0; q < nsub; ++q) {
       BrickStorage view = st0;
       Brick3D b(&bInfo_dev, view, (unsigned) 0);
-      b.dat = ((st->st_iter % 2) ? st1 : st0).dat.get() + q * sub_elems;
+      b.dat = (((stitched ? npass : st->st_iter) % 2) ? st1 : st0).dat.get() + q * sub_elems;
       copyFromBrickDevice({s, s, s}, {PADDING, PADDING, PADDING}, {GZ, GZ, GZ}, arr_dev, grid_dev, b);
       copyFromDevice(astride, host, arr_dev);
       for (long k = 0; k < s; ++k)
@@ -249,9 +334,13 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     size_t parts = 0;
     for (size_t p : S.parts) parts = std::max(parts, p);
     std::cout << "part " << parts << std::endl;
+    int ns = 0;
+    for (int v : S.stitched) ns += v;
+    std::cout << "stitched ranks " << ns << " of " << S.size << std::endl;
   }
   freeBrickInfoDevice(bInfo_dev);
   bk_dev_free(grid_dev);
+  if (sgrid_dev) bk_dev_free(sgrid_dev);
   bk_dev_free(f01_dev);
   bk_dev_free(f10_dev);
 }
@@ -263,15 +352,16 @@ int main(int argc, char **argv) {
   std::string sname = "mpi7pt";
   int c;
   if (const char *e = getenv("BRICK_RANKS")) S.size = atoi(e);
-  while ((c = getopt(argc, argv, "d:s:I:g:S:vh")) != -1) switch (c) {
+  while ((c = getopt(argc, argv, "d:s:I:g:S:vhM")) != -1) switch (c) {
       case 'd': S.dom_size = std::stoi(optarg); break;
       case 's': S.sdom_size = std::stoi(optarg); break;
       case 'I': S.iters = std::stoi(optarg); break;
       case 'g': S.size = std::stoi(optarg); break;
       case 'S': sname = optarg; break;
       case 'v': S.validate = true; break;
+      case 'M': S.no_stitch = true; break;
       default:
-        printf("Program options\n  -h: help\n  -d n: global domain edge (default 512)\n  -s n: subdomain edge (default 128)\n"
+        printf("Program options\n  -h: help\n  -M: per-subdomain launches and ghost copies instead of the stitched super grid\n  -d n: global domain edge (default 512)\n  -s n: subdomain edge (default 128)\n"
                "  -I n: exchange periods (default 100)\n  -g n: GPUs = ranks (default 1)\n  -S name: mpi7pt mpi13pt mpi25pt mpi125pt\n"
                "  -v: validate against a CPU sweep of the global periodic array\n");
         return 0;
@@ -291,6 +381,7 @@ int main(int argc, char **argv) {
   S.base.assign(S.size, nullptr);
   S.calc.assign(S.size, 0), S.call = S.wait = S.total = S.mbytes = S.calc;
   S.parts.assign(S.size, 0);
+  S.stitched.assign(S.size, 0);
   S.result.resize(S.size);
   const long G[3] = {(long) S.dom_size, (long) S.dom_size, (long) S.dom_size};
   std::vector<bElem> initial;

@@ -375,5 +375,17 @@ def test_cpp_weak_driver_validates_against_global_periodic_sweep(name, ranks, do
 
 @pytest.mark.parametrize("name,ranks,d,s", [("mpi7pt", 3, 128, 32), ("mpi13pt", 1, 64, 32), ("mpi125pt", 2, 128, 64)])
 def test_cpp_strong_driver_validates_against_global_periodic_sweep(name, ranks, d, s):
+    out = _run_driver("strong", "-d", str(d), "-s", str(s), "-I", "2", "-g", str(ranks), "-S", name, "-v", "-M")
+    assert "result match" in out and "perf" in out and "stitched ranks 0 of" in out
+
+
+@pytest.mark.parametrize("name,ranks,d,s", [("mpi7pt", 1, 64, 32), ("mpi7pt", 8, 128, 32), ("mpi13pt", 4, 128, 32),
+                                            ("mpi25pt", 2, 128, 32), ("mpi125pt", 2, 128, 64), ("mpi7pt", 3, 128, 32),
+                                            ("mpi25pt", 8, 64, 32), ("mpi13pt", 1, 32, 16)])
+def test_cpp_strong_driver_stitched_super_grid(name, ranks, d, s):
+    """default mode: each rank's box of subdomains swept as ONE brick grid (same-GPU ghosts aliased through the grid, only
+    the box surface exchanged); 3 ranks own non-box sections and fall back to per-subdomain launches"""
     out = _run_driver("strong", "-d", str(d), "-s", str(s), "-I", "2", "-g", str(ranks), "-S", name, "-v")
     assert "result match" in out and "perf" in out
+    want = 0 if ranks == 3 else ranks
+    assert f"stitched ranks {want} of {ranks}" in out
