@@ -16,3 +16,6 @@ def have_gpu():
     import ctypes
     n = ctypes.c_int()
     return load().bk_device_count(ctypes.byref(n)) == 0 and n.value > 0
+
+
+from .dsl import CompiledStencil, LoweringError, compile_stencil, lower  # noqa: E402,F401

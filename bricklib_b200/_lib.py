@@ -34,6 +34,10 @@ class Seg(C.Structure):
     _fields_ = [("src", vp), ("dst", vp), ("bytes", sz)]
 
 
+class Tap(C.Structure):
+    _fields_ = [("di", C.c_int), ("dj", C.c_int), ("dk", C.c_int), ("c", C.c_double)]
+
+
 # name -> (restype, argtypes); the list doubles as the export check in tests/test_abi.py
 SIGNATURES = {
     "bk_version": (C.c_char_p, []),
@@ -86,6 +90,11 @@ SIGNATURES = {
     "bk_stencil_advance": (C.c_int, [C.c_int, C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp]),
     "bk_stencil_apply_list": (C.c_int, [C.c_int, C.POINTER(Field), vp, sz, dp, vp]),
     "bk_stencil_apply_multi": (C.c_int, [C.c_int, vp, C.c_uint, vp, up, up, up, dp, vp]),
+    "bk_stencil_compile": (C.c_int, [C.POINTER(vp), C.POINTER(Tap), C.c_int]),
+    "bk_stencil_def_destroy": (C.c_int, [vp]),
+    "bk_stencil_def_info": (C.c_int, [vp, ip, ip, ip, ip, ip]),
+    "bk_stencil_def_apply": (C.c_int, [vp, C.POINTER(Field), vp, up, up, up, C.c_uint, vp]),
+    "bk_stencil_def_advance": (C.c_int, [vp, C.c_int, C.POINTER(Field), vp, up, up, up, up, up, C.c_int, C.c_uint, vp]),
     "bk_launch_count": (C.c_ulonglong, []),
     "bk_xplan_create": (C.c_int, [C.POINTER(vp), C.POINTER(Seg), C.c_int]),
     "bk_xplan_destroy": (C.c_int, [vp]),

@@ -55,4 +55,16 @@ struct CubeCoef {
 int star_coef_for(int stencil, const double *coeff_host, StarCoef *out);   // BK_ST_7PT..BK_ST_MPI25PT
 int cube_coef_for(int stencil, CubeCoef *out);                            // BK_ST_MPI125PT
 
+// What a kernel launch needs to know about a stencil: built from a BK_ST_* id (coef_spec_for) or lowered from a tap list
+// (bk_stencil_compile).  radius is the KERNEL radius (1, 2 or 4 for stars -- a radius-3 star runs on the radius-4
+// kernel with zero outer coefficients; 2 for the cube).
+struct CoefSpec {
+  int kind = 0;    // 0 star, 1 sign- and permutation-symmetric cube
+  int radius = 0;
+  int fused_ok = 0;  // a two-steps-per-pass kernel exists (radius 1 and 2 stars)
+  StarCoef sc;
+  CubeCoef cc;
+};
+int coef_spec_for(int stencil, const double *coeff_host, CoefSpec *out);
+
 }  // namespace bk

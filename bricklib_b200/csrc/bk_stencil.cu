@@ -11,6 +11,11 @@
 // Summation order (fixed, documented in DESIGN.md): centre first, then by distance d = 1..R: +i,-i,+j,-j,+k,-k (star);
 // dz,dy,dx ascending (cube).  The reference's order is codegen-dependent, parity is to 1e-12 relative, not bitwise.
 #include "bk_common.h"
+#include <algorithm>
+#include <array>
+#include <cstdlib>
+#include <map>
+#include <vector>
 
 namespace bk {
 
@@ -77,11 +82,23 @@ int cube_coef_for(int stencil, CubeCoef *o) {
   return 2;
 }
 
+int coef_spec_for(int stencil, const double *coeff, CoefSpec *o) {
+  *o = CoefSpec();
+  if (stencil == BK_ST_MPI125PT) {
+    o->kind = 1;
+    o->radius = cube_coef_for(stencil, &o->cc);
+    return o->radius < 0 ? BK_EINVAL : BK_OK;
+  }
+  o->radius = star_coef_for(stencil, coeff, &o->sc);
+  if (o->radius < 0) return BK_EINVAL;
+  o->fused_ok = o->radius <= 2;
+  return BK_OK;
+}
+
 // implemented in bk_stencil_tiled.cu
-int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, unsigned nsub, const unsigned *grid,
-                 const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff, cudaStream_t s,
-                 int part = BK_PART_ALL, const unsigned *ready_lo = nullptr, const unsigned *ready_hi = nullptr,
-                 int steps = 1);
+int launch_tiled(const CoefSpec &spec, const bk_field_t &f, const bk_field_t *multi_dev, unsigned nsub, const unsigned *grid,
+                 const unsigned *gdims, const unsigned *lo, const unsigned *hi, cudaStream_t s, int part = BK_PART_ALL,
+                 const unsigned *ready_lo = nullptr, const unsigned *ready_hi = nullptr, int steps = 1);
 
 }  // namespace bk
 
@@ -169,22 +186,55 @@ __global__ void __launch_bounds__(256) k_brick(Select sel, bk_field_t f, typenam
   }
 }
 
-int launch_brick(int stencil, const Select &sel, const bk_field_t &f, dim3 grid, const double *coeff, cudaStream_t s) {
+int launch_brick(const bk::CoefSpec &spec, const Select &sel, const bk_field_t &f, dim3 grid, cudaStream_t s) {
   if (grid.x == 0 || grid.y == 0 || grid.z == 0) return BK_OK;
-  if (stencil == BK_ST_MPI125PT) {
-    CubeCoef cc;
-    if (bk::cube_coef_for(stencil, &cc) < 0) return BK_EINVAL;
-    k_brick<2, true><<<grid, 256, 0, s>>>(sel, f, cc);
+  if (spec.kind == 1) {
+    k_brick<2, true><<<grid, 256, 0, s>>>(sel, f, spec.cc);
   } else {
-    StarCoef sc;
-    const int r = bk::star_coef_for(stencil, coeff, &sc);
-    if (r < 0) return BK_EINVAL;
-    if (r == 1) k_brick<1, false><<<grid, 256, 0, s>>>(sel, f, sc);
-    if (r == 2) k_brick<2, false><<<grid, 256, 0, s>>>(sel, f, sc);
-    if (r == 4) k_brick<4, false><<<grid, 256, 0, s>>>(sel, f, sc);
+    if (spec.radius == 1) k_brick<1, false><<<grid, 256, 0, s>>>(sel, f, spec.sc);
+    if (spec.radius == 2) k_brick<2, false><<<grid, 256, 0, s>>>(sel, f, spec.sc);
+    if (spec.radius == 4) k_brick<4, false><<<grid, 256, 0, s>>>(sel, f, spec.sc);
   }
   BK_LAUNCHED();
   return BK_OK;
+}
+
+// ---- arbitrary linear stencils: one CTA per brick, taps from a device table -------------------------------------------
+// The general lowering target of bk_stencil_compile (what codegen/vecscatter does for any stencils/*.py expression that
+// is neither a star nor the symmetric cube): the (8+2R)^3 neighbourhood is gathered through the adjacency list like
+// k_brick does, then every thread walks the tap table (offset into the box, coefficient) for its two cells.
+struct TapDev {
+  int off;  // ((dk * W) + dj) * W + di in the shared box
+  double c;
+};
+
+template <int R>
+__global__ void __launch_bounds__(256) k_taps(Select sel, bk_field_t f, const TapDev *__restrict__ taps, int ntaps) {
+  constexpr int W = 8 + 2 * R;
+  __shared__ double box[W * W * W];
+  __shared__ unsigned nb[27];
+  const unsigned b = sel.ids ? sel.ids[blockIdx.x]
+                             : sel.grid[(sel.lo[0] + blockIdx.x) +
+                                        ((sel.lo[1] + blockIdx.y) + (size_t) (sel.lo[2] + blockIdx.z) * sel.gsy) * sel.gsx];
+  if (threadIdx.x < 27) nb[threadIdx.x] = f.adj[(size_t) b * 27 + threadIdx.x];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < W * W * W; idx += 256) {
+    const int x = idx % W, y = (idx / W) % W, z = idx / (W * W);
+    const int gx = x + 8 - R, gy = y + 8 - R, gz = z + 8 - R;
+    box[idx] = f.in[(size_t) nb[(gz >> 3) * 9 + (gy >> 3) * 3 + (gx >> 3)] * f.in_step + ((gz & 7) << 6) + ((gy & 7) << 3) + (gx & 7)];
+  }
+  __syncthreads();
+  const int e0 = threadIdx.x, e1 = threadIdx.x + 256;
+  const double *c0 = &box[(((e0 >> 6) + R) * W + (((e0 >> 3) & 7) + R)) * W + ((e0 & 7) + R)];
+  const double *c1 = &box[(((e1 >> 6) + R) * W + (((e1 >> 3) & 7) + R)) * W + ((e1 & 7) + R)];
+  double a0 = 0.0, a1 = 0.0;
+  for (int t = 0; t < ntaps; ++t) {
+    const TapDev tp = taps[t];
+    a0 = fma(tp.c, c0[tp.off], a0);
+    a1 = fma(tp.c, c1[tp.off], a1);
+  }
+  f.out[(size_t) b * f.out_step + e0] = a0;
+  f.out[(size_t) b * f.out_step + e1] = a1;
 }
 
 int check_box(const unsigned *gdims, const unsigned *lo, const unsigned *hi) {
@@ -215,6 +265,16 @@ int bk_stencil_points(int s) {
   return (s < 0 || s >= BK_ST_COUNT) ? BK_EINVAL : p[s];
 }
 
+static int apply_spec(const bk::CoefSpec &spec, const bk_field_t *f, const unsigned *grid, const unsigned *gdims,
+                      const unsigned *lo, const unsigned *hi, unsigned flags, cudaStream_t s) {
+  if (flags != BK_KERNEL_BRICK) {
+    int rc = bk::launch_tiled(spec, *f, nullptr, 1, grid, gdims, lo, hi, s);
+    if (rc != BK_EUNSUPPORTED || flags == BK_KERNEL_TILED) return rc;
+  }
+  Select sel = {grid, nullptr, nullptr, gdims[0], gdims[1], {lo[0], lo[1], lo[2]}, 0};
+  return launch_brick(spec, sel, *f, dim3(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]), s);
+}
+
 int bk_stencil_apply(int stencil, const bk_field_t *f, const unsigned *grid, const unsigned *gdims, const unsigned *lo,
                      const unsigned *hi, const double *coeff, unsigned flags, void *stream) {
   BK_REQUIRE(stencil >= 0 && stencil < BK_ST_COUNT, "unknown stencil id");
@@ -223,12 +283,9 @@ int bk_stencil_apply(int stencil, const bk_field_t *f, const unsigned *grid, con
   BK_REQUIRE(f->in != f->out, "in-place sweep is not defined");
   BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
   cudaStream_t s = (cudaStream_t) stream;
-  if (flags != BK_KERNEL_BRICK) {
-    int rc = bk::launch_tiled(stencil, *f, nullptr, 1, grid, gdims, lo, hi, coeff, s);
-    if (rc != BK_EUNSUPPORTED || flags == BK_KERNEL_TILED) return rc;
-  }
-  Select sel = {grid, nullptr, nullptr, gdims[0], gdims[1], {lo[0], lo[1], lo[2]}, 0};
-  return launch_brick(stencil, sel, *f, dim3(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]), coeff, s);
+  bk::CoefSpec spec;
+  if (bk::coef_spec_for(stencil, coeff, &spec) != BK_OK) return BK_EINVAL;
+  return apply_spec(spec, f, grid, gdims, lo, hi, flags, s);
 }
 
 int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid, const unsigned *gdims,
@@ -242,8 +299,9 @@ int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid
   BK_REQUIRE(f->in != f->out, "in-place sweep is not defined");
   BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
   // only the marching kernel has the split enumeration; the caller falls back to whole-box launches on EUNSUPPORTED
-  return bk::launch_tiled(stencil, *f, nullptr, 1, grid, gdims, lo, hi, coeff, (cudaStream_t) stream, part, ready_lo,
-                          ready_hi);
+  bk::CoefSpec spec;
+  if (bk::coef_spec_for(stencil, coeff, &spec) != BK_OK) return BK_EINVAL;
+  return bk::launch_tiled(spec, *f, nullptr, 1, grid, gdims, lo, hi, (cudaStream_t) stream, part, ready_lo, ready_hi);
 }
 
 int bk_stencil_advance(int stencil, int steps, const bk_field_t *f, const unsigned *grid, const unsigned *gdims,
@@ -258,8 +316,10 @@ int bk_stencil_advance(int stencil, int steps, const bk_field_t *f, const unsign
   BK_REQUIRE(f->in_step >= 512 && f->out_step >= 512, "brick step smaller than a brick");
   BK_REQUIRE(f->in != f->out, "in-place sweep is not defined");
   BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
-  return bk::launch_tiled(stencil, *f, nullptr, 1, grid, gdims, lo, hi, coeff, (cudaStream_t) stream, part, ready_lo,
-                          ready_hi, steps);
+  bk::CoefSpec spec;
+  if (bk::coef_spec_for(stencil, coeff, &spec) != BK_OK) return BK_EINVAL;
+  return bk::launch_tiled(spec, *f, nullptr, 1, grid, gdims, lo, hi, (cudaStream_t) stream, part, ready_lo, ready_hi,
+                          steps);
 }
 
 int bk_stencil_apply_list(int stencil, const bk_field_t *f, const unsigned *ids, size_t n, const double *coeff,
@@ -269,7 +329,9 @@ int bk_stencil_apply_list(int stencil, const bk_field_t *f, const unsigned *ids,
   BK_REQUIRE(f->in != f->out, "in-place sweep is not defined");
   BK_REQUIRE(n < (1ull << 31), "list too long");
   Select sel = {nullptr, ids, nullptr, 0, 0, {0, 0, 0}, 0};
-  return launch_brick(stencil, sel, *f, dim3((unsigned) n, 1, 1), coeff, (cudaStream_t) stream);
+  bk::CoefSpec spec;
+  if (bk::coef_spec_for(stencil, coeff, &spec) != BK_OK) return BK_EINVAL;
+  return launch_brick(spec, sel, *f, dim3((unsigned) n, 1, 1), (cudaStream_t) stream);
 }
 
 int bk_stencil_apply_multi(int stencil, const bk_field_t *fields_dev, unsigned nsub, const unsigned *grid,
@@ -280,14 +342,154 @@ int bk_stencil_apply_multi(int stencil, const bk_field_t *fields_dev, unsigned n
   BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
   const unsigned nx = hi[0] - lo[0];
   BK_REQUIRE((unsigned long long) nx * nsub < (1ull << 31) && nsub <= 65535, "launch too wide");
+  bk::CoefSpec spec;
+  if (bk::coef_spec_for(stencil, coeff, &spec) != BK_OK) return BK_EINVAL;
   if (!getenv("BK_MULTI_BRICK")) {  // developer knob: force the per-brick family
     bk_field_t none = {nullptr, nullptr, 512, nullptr, 512};
-    int rc = bk::launch_tiled(stencil, none, fields_dev, nsub, grid, gdims, lo, hi, coeff, (cudaStream_t) stream);
+    int rc = bk::launch_tiled(spec, none, fields_dev, nsub, grid, gdims, lo, hi, (cudaStream_t) stream);
     if (rc != BK_EUNSUPPORTED) return rc;
   }
   Select sel = {grid, nullptr, fields_dev, gdims[0], gdims[1], {lo[0], lo[1], lo[2]}, nx};
   bk_field_t dummy = {nullptr, nullptr, 512, nullptr, 512};
-  return launch_brick(stencil, sel, dummy, dim3(nx * nsub, hi[1] - lo[1], hi[2] - lo[2]), coeff, (cudaStream_t) stream);
+  return launch_brick(spec, sel, dummy, dim3(nx * nsub, hi[1] - lo[1], hi[2] - lo[2]), (cudaStream_t) stream);
+}
+
+// ---- stencils lowered from tap lists (the stencils/*.py expressions) -------------------------
+}  // extern "C"
+
+struct bk_stencil_def {
+  int kind = BK_KIND_TAPS;  // BK_KIND_*
+  int radius = 0;           // of the expression
+  int ntaps = 0;
+  bk::CoefSpec spec;        // kind STAR / CUBE
+  int krad = 0;             // kernel radius (1, 2 or 4)
+  TapDev *taps_dev = nullptr;
+};
+
+extern "C" {
+
+int bk_stencil_compile(bk_stencil_def_t **out, const bk_tap_t *taps, int ntaps) {
+  BK_REQUIRE(out && taps && ntaps > 0 && ntaps <= 4096, "bad arguments");
+  // merge repeated offsets, drop zero coefficients
+  std::map<std::array<int, 3>, double> m;
+  for (int t = 0; t < ntaps; ++t) m[{taps[t].dk, taps[t].dj, taps[t].di}] += taps[t].c;
+  int radius = 0;
+  bool star = true;
+  for (auto it = m.begin(); it != m.end();) {
+    if (it->second == 0.0) {
+      it = m.erase(it);
+      continue;
+    }
+    int nz = 0;
+    for (int a = 0; a < 3; ++a) radius = std::max(radius, std::abs(it->first[a])), nz += it->first[a] != 0;
+    star = star && nz <= 1;
+    ++it;
+  }
+  BK_REQUIRE(!m.empty(), "every coefficient is zero");
+  if (radius > 4) {
+    bk::set_error("bk_stencil_compile: radius %d (kernels cover radius <= 4 = half a brick)", radius);
+    return BK_EUNSUPPORTED;
+  }
+  bk_stencil_def *d = new bk_stencil_def();
+  d->radius = radius, d->ntaps = (int) m.size();
+  d->krad = radius <= 1 ? 1 : radius <= 2 ? 2 : 4;
+  auto coef = [&](int dk, int dj, int di) {
+    auto it = m.find({dk, dj, di});
+    return it == m.end() ? 0.0 : it->second;
+  };
+  if (star) {  // any coefficients: the marching kernels take one per tap
+    d->kind = BK_KIND_STAR;
+    d->spec.kind = 0, d->spec.radius = d->krad, d->spec.fused_ok = d->krad <= 2;
+    d->spec.sc = bk::StarCoef();
+    d->spec.sc.c0 = coef(0, 0, 0);
+    for (int r = 1; r <= radius; ++r) {
+      d->spec.sc.cp[0][r - 1] = coef(0, 0, r), d->spec.sc.cm[0][r - 1] = coef(0, 0, -r);
+      d->spec.sc.cp[1][r - 1] = coef(0, r, 0), d->spec.sc.cm[1][r - 1] = coef(0, -r, 0);
+      d->spec.sc.cp[2][r - 1] = coef(r, 0, 0), d->spec.sc.cm[2][r - 1] = coef(-r, 0, 0);
+    }
+    *out = d;
+    return BK_OK;
+  }
+  bool sym = radius <= 2;  // c(dx,dy,dz) a function of the sorted (|dx|,|dy|,|dz|) only?
+  if (sym) {
+    for (int z = -2; z <= 2 && sym; ++z)
+      for (int y = -2; y <= 2 && sym; ++y)
+        for (int x = -2; x <= 2 && sym; ++x) {
+          int v[3] = {std::abs(x), std::abs(y), std::abs(z)};
+          std::sort(v, v + 3);
+          sym = coef(z, y, x) == coef(v[2], v[1], v[0]);
+        }
+  }
+  if (sym) {
+    d->kind = BK_KIND_CUBE;
+    d->spec.kind = 1, d->spec.radius = 2, d->spec.fused_ok = 0;
+    for (int z = 0; z < 3; ++z)
+      for (int y = 0; y < 3; ++y)
+        for (int x = 0; x < 3; ++x) d->spec.cc.cc[z][y][x] = coef(z, y, x);
+    *out = d;
+    return BK_OK;
+  }
+  d->kind = BK_KIND_TAPS;
+  const int W = 8 + 2 * d->krad;
+  std::vector<TapDev> host;
+  for (auto &kv : m) host.push_back({(kv.first[0] * W + kv.first[1]) * W + kv.first[2], kv.second});
+  if (cudaMalloc(&d->taps_dev, sizeof(TapDev) * host.size()) != cudaSuccess ||
+      cudaMemcpy(d->taps_dev, host.data(), sizeof(TapDev) * host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaError_t e = cudaGetLastError();
+    delete d;
+    return bk::cuda_fail(e, "tap table upload", __FILE__, __LINE__);
+  }
+  *out = d;
+  return BK_OK;
+}
+
+int bk_stencil_def_destroy(bk_stencil_def_t *d) {
+  if (!d) return BK_OK;
+  if (d->taps_dev) cudaFree(d->taps_dev);
+  delete d;
+  return BK_OK;
+}
+
+int bk_stencil_def_info(const bk_stencil_def_t *d, int *kind, int *radius, int *ntaps, int *st_iter, int *fused_steps) {
+  BK_REQUIRE(d, "null stencil");
+  if (kind) *kind = d->kind;
+  if (radius) *radius = d->radius;
+  if (ntaps) *ntaps = d->ntaps;
+  if (st_iter) *st_iter = d->radius ? 8 / d->radius : 8;  // sweeps a ghost depth of 8 cells allows between two exchanges
+  if (fused_steps) *fused_steps = (d->kind == BK_KIND_STAR && d->krad == 1) ? 2 : 1;
+  return BK_OK;
+}
+
+int bk_stencil_def_advance(const bk_stencil_def_t *d, int steps, const bk_field_t *f, const unsigned *grid,
+                           const unsigned *gdims, const unsigned *lo, const unsigned *hi, const unsigned *ready_lo,
+                           const unsigned *ready_hi, int part, unsigned flags, void *stream) {
+  BK_REQUIRE(d && f && f->adj && f->in && f->out && grid && gdims && lo && hi, "null argument");
+  BK_REQUIRE(steps == 1 || steps == 2, "steps must be 1 or 2");
+  BK_REQUIRE(part == BK_PART_ALL ||
+                 (ready_lo && ready_hi && ((part & ~BK_PART_THIN) == BK_PART_READY || (part & ~BK_PART_THIN) == BK_PART_REST)),
+             "bad part");
+  BK_REQUIRE(f->in_step >= 512 && f->out_step >= 512, "brick step smaller than a brick");
+  BK_REQUIRE(f->in != f->out, "in-place sweep is not defined");
+  BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
+  cudaStream_t s = (cudaStream_t) stream;
+  if (d->kind != BK_KIND_TAPS) {
+    if (steps == 1 && part == BK_PART_ALL) return apply_spec(d->spec, f, grid, gdims, lo, hi, flags, s);
+    return bk::launch_tiled(d->spec, *f, nullptr, 1, grid, gdims, lo, hi, s, part, ready_lo, ready_hi, steps);
+  }
+  if (steps != 1 || part != BK_PART_ALL) return BK_EUNSUPPORTED;  // general taps: whole-box single sweeps only
+  const dim3 g(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
+  if (g.x == 0 || g.y == 0 || g.z == 0) return BK_OK;
+  Select sel = {grid, nullptr, nullptr, gdims[0], gdims[1], {lo[0], lo[1], lo[2]}, 0};
+  if (d->krad == 1) k_taps<1><<<g, 256, 0, s>>>(sel, *f, d->taps_dev, d->ntaps);
+  if (d->krad == 2) k_taps<2><<<g, 256, 0, s>>>(sel, *f, d->taps_dev, d->ntaps);
+  if (d->krad == 4) k_taps<4><<<g, 256, 0, s>>>(sel, *f, d->taps_dev, d->ntaps);
+  BK_LAUNCHED();
+  return BK_OK;
+}
+
+int bk_stencil_def_apply(const bk_stencil_def_t *d, const bk_field_t *f, const unsigned *grid, const unsigned *gdims,
+                         const unsigned *lo, const unsigned *hi, unsigned flags, void *stream) {
+  return bk_stencil_def_advance(d, 1, f, grid, gdims, lo, hi, nullptr, nullptr, BK_PART_ALL, flags, stream);
 }
 
 }  // extern "C"

@@ -1089,11 +1089,11 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, 
 
 namespace bk {
 
-int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, unsigned nsub, const unsigned *grid,
-                 const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff, cudaStream_t s,
-                 int part, const unsigned *ready_lo, const unsigned *ready_hi, int steps) {
+int launch_tiled(const CoefSpec &spec, const bk_field_t &f, const bk_field_t *multi_dev, unsigned nsub, const unsigned *grid,
+                 const unsigned *gdims, const unsigned *lo, const unsigned *hi, cudaStream_t s, int part,
+                 const unsigned *ready_lo, const unsigned *ready_hi, int steps) {
   if (!multi_dev && (((size_t) f.in | (size_t) f.out) & 15 || (f.in_step & 1) || (f.out_step & 1))) return BK_EUNSUPPORTED;
-  if (steps == 2 && (bk_stencil_radius(stencil) > 2 || stencil == BK_ST_MPI125PT)) return BK_EUNSUPPORTED;
+  if (steps == 2 && (spec.kind != 0 || spec.radius > 2)) return BK_EUNSUPPORTED;
   TiledArgs a;
   a.in = f.in, a.out = f.out, a.in_step = f.in_step, a.out_step = f.out_step, a.grid = grid;
   a.gx = (int) gdims[0], a.gy = (int) gdims[1], a.gz = (int) gdims[2];
@@ -1111,15 +1111,13 @@ int launch_tiled(int stencil, const bk_field_t &f, const bk_field_t *multi_dev, 
   //   radius 4  : 6x4-brick tiles, 2 rows per thread (12 consumer warps at 152 registers) + 4 producer warps (40
   //               registers, setmaxnreg), 3-stage ring (130 KB: leaves L1 for the id/adjacency reads), 1 CTA per SM
   //   cube      : same shape: 6x4-brick tiles, 12 consumer warps (152 registers) + 4 producer warps, 1 CTA per SM
-  if (stencil == BK_ST_MPI125PT) {
-    CubeCoef cc;
-    if (cube_coef_for(stencil, &cc) < 0) return BK_EINVAL;
+  if (spec.kind == 1) {
+    const CubeCoef &cc = spec.cc;
     if (v == 1) return launch_cfg<Cfg<2, 2, 6, 4, 2, 3, 128, 4, true>>(a, cc, s, nsub, part, rdy_lo, rdy_hi);
     return launch_cfg<Cfg<2, 2, 6, 4, 2, 3, 255, 4, true, 152, 40>>(a, cc, s, nsub, part, rdy_lo, rdy_hi);
   }
-  StarCoef sc;
-  const int r = star_coef_for(stencil, coeff, &sc);
-  if (r < 0) return BK_EINVAL;
+  const StarCoef &sc = spec.sc;
+  const int r = spec.radius;
   if (steps == 2) {  // two time steps per pass: (R, YT, TI, TJ, D, producer warps)
     if (r == 1) {
       if (v == 1) return launch_cfg<FCfg<1, 4, 8, 4, 4, 4>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);

@@ -170,6 +170,33 @@ int bk_stencil_apply_list(int stencil, const bk_field_t *f, const unsigned *ids_
 int bk_stencil_apply_multi(int stencil, const bk_field_t *fields_dev, unsigned nsub, const unsigned *grid_dev,
                            const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff_host,
                            void *stream);
+/* ---- stencils lowered from tap lists ------------------------------------------------------------------------------
+ * The reference turns a stencil expression (stencils/*.py: Grid / Index / ConstRef arithmetic) into code at build time
+ * with codegen/vecscatter (backend table vecscatter:82-109, CUDA backend codegen/st/codegen/backend/cuda.py).  Here the
+ * expression is lowered to its tap list -- out(i,j,k) = sum_t c_t * in(i+di_t, j+dj_t, k+dk_t) -- by the host side
+ * (bricklib_b200/dsl.py evaluates the same scripts) and bk_stencil_compile picks the kernel family:
+ *   BK_KIND_STAR  taps on the axes only, radius <= 4, ANY coefficients  -> marching kernels (k_star / k_star2)
+ *   BK_KIND_CUBE  radius <= 2, coefficient a function of the sorted (|di|,|dj|,|dk|) -> marching cube kernel
+ *   BK_KIND_TAPS  anything else with radius <= 4 -> per-brick kernel walking a tap table (k_taps)
+ * Repeated offsets are merged, zero coefficients dropped.  BK_EUNSUPPORTED for radius > 4. */
+typedef struct {
+  int di, dj, dk;
+  double c;
+} bk_tap_t;
+typedef struct bk_stencil_def bk_stencil_def_t;
+#define BK_KIND_STAR 0
+#define BK_KIND_CUBE 1
+#define BK_KIND_TAPS 2
+int bk_stencil_compile(bk_stencil_def_t **def, const bk_tap_t *taps_host, int ntaps);
+int bk_stencil_def_destroy(bk_stencil_def_t *def);
+/* any out pointer may be NULL; st_iter = 8 / radius (sweeps per exchange at ghost depth 8); fused_steps as bk_stencil_fused_steps */
+int bk_stencil_def_info(const bk_stencil_def_t *def, int *kind, int *radius, int *ntaps, int *st_iter, int *fused_steps);
+/* = bk_stencil_apply / bk_stencil_advance for a compiled stencil (flags: BK_KERNEL_*) */
+int bk_stencil_def_apply(const bk_stencil_def_t *def, const bk_field_t *f, const unsigned *grid_dev, const unsigned *gdims,
+                         const unsigned *lo, const unsigned *hi, unsigned flags, void *stream);
+int bk_stencil_def_advance(const bk_stencil_def_t *def, int steps, const bk_field_t *f, const unsigned *grid_dev,
+                           const unsigned *gdims, const unsigned *lo, const unsigned *hi, const unsigned *ready_lo,
+                           const unsigned *ready_hi, int part, unsigned flags, void *stream);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 unsigned long long bk_launch_count(void);
 

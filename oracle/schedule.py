@@ -160,3 +160,16 @@ def weak_run(backend, stencil, dom, cart, periods, fields, skip_last=False):
             last = s == it - 1
             backend.sweep(stencil, s % 2, 1 - s % 2, skip=1 if (last and skip_last) else 0)
     return backend.unload(0)
+
+
+def taps_sweep(arr, taps, lo, hi):
+    """The meaning of a lowered stencil script, in numpy: out[k,j,i] = sum_t c_t * arr[k+dk_t, j+dj_t, i+di_t] for
+    lo <= (i,j,k) < hi, zero elsewhere (what codegen/vecscatter's generated loop nest computes for a linear
+    stencils/*.py expression).  taps = [((di, dj, dk), c)], summed in the given order."""
+    out = np.zeros_like(arr)
+    (i0, j0, k0), (i1, j1, k1) = lo, hi
+    acc = np.zeros((k1 - k0, j1 - j0, i1 - i0))
+    for (di, dj, dk), c in taps:
+        acc += c * arr[k0 + dk:k1 + dk, j0 + dj:j1 + dj, i0 + di:i1 + di]
+    out[k0:k1, j0:j1, i0:i1] = acc
+    return out

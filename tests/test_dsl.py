@@ -1,0 +1,175 @@
+"""The stencil-script front end (bricklib_b200/st, dsl.py): the reference's stencils/*.py expressions lowered to tap lists,
+pinned against the tap lists the REFERENCE's own DSL builds (tests/golden/stencil_taps.json, oracle/gen_golden_taps.py),
+and -- on the GPU -- the compiled stencils against the oracle."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import bricklib_b200 as bk
+from bricklib_b200 import dsl
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HERE = os.path.join(ROOT, "tests", "stencil_scripts")
+REF_STENCILS = "/root/reference/stencils"
+COEFF7 = [0.31, 0.11, 0.12, 0.13, 0.14, 0.15, 0.04]
+
+
+def golden():
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "stencil_taps.json")))
+
+
+def value_of(text, consts):
+    look = dsl._resolver(consts)
+    neg = text.startswith("-")
+    body = text[1:] if neg else text
+    try:
+        v = float(body)
+    except ValueError:
+        v = look(body)
+    return -v if neg else v
+
+
+def golden_taps(entry, consts):
+    acc = {}
+    for *offs, c in entry["taps"]:
+        acc[tuple(offs)] = acc.get(tuple(offs), 0.0) + value_of(c, consts)
+    return acc
+
+
+@pytest.mark.parametrize("name", ["7pt", "mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt"])
+def test_shipped_scripts_lower_to_the_reference_tap_lists(name):
+    consts = {"coeff": COEFF7}
+    taps, sc = dsl.lower(name, consts)
+    g = golden()[name + ".py"]
+    assert sc.dims == g["dims"] and sc.in_grids == [g["in"]] and sc.out_grid == g["out"]
+    assert dict(taps) == golden_taps(g, consts)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_STENCILS), reason="reference tree not present")
+def test_reference_scripts_run_unmodified_on_this_dsl():
+    consts = {"coeff": COEFF7}
+    for name, g in golden().items():
+        path = os.path.join(REF_STENCILS, name)
+        if not g["linear"]:
+            with pytest.raises(dsl.LoweringError):
+                dsl.lower(path, consts)
+            continue
+        taps, sc = dsl.lower(path, consts)
+        assert sc.dims == g["dims"]
+        assert dict(taps) == golden_taps(g, consts), name
+
+
+def test_linear_form_algebra():
+    taps, sc = dsl.lower(os.path.join(HERE, "upwind.py"), {"W": 0.3})
+    assert dict(taps) == {(0, 0, 0): 0.5, (-1, 0, 0): -0.3, (-2, 1, 0): 0.6, (1, -1, 3): 0.25, (0, 0, -3): -0.125,
+                          (0, 2, 0): 0.25, (0, -2, 0): -0.25}
+    assert sc.symbols == ["W"] and sc.in_grids == ["u"] and sc.out_grid == "v"
+    with pytest.raises(dsl.LoweringError):
+        dsl.lower(os.path.join(HERE, "upwind.py"))          # W unbound
+
+
+def test_c_table_emission_for_cxx_callers():
+    src = dsl.emit_c("mpi13pt", "mpi13")
+    assert "static const bk_tap_t mpi13[] = {" in src and "mpi13_count = 13" in src
+    assert "{0, 0, 0, 0.4}" in src and "{-2, 0, 0, 0.03}" in src
+
+
+def test_nonlinear_and_malformed_scripts_are_refused(tmp_path):
+    head = "from st.expr import Index, ConstRef, If\nfrom st.grid import Grid\nfrom st.func import Func\n" \
+           "i, j, k = Index(0), Index(1), Index(2)\na, b = Grid('a', 3), Grid('b', 3)\n"
+    cases = {
+        "square": "b(i, j, k).assign(a(i, j, k) * a(i + 1, j, k))\nSTENCIL = [b]\n",
+        "call": "b(i, j, k).assign(Func('max', 2)(a(i, j, k), 0.0))\nSTENCIL = [b]\n",
+        "cond": "b(i, j, k).assign(If(a(i, j, k) > 0, a(i, j, k), -a(i, j, k)))\nSTENCIL = [b]\n",
+        "constant": "b(i, j, k).assign(a(i, j, k) + 1.0)\nSTENCIL = [b]\n",
+        "two_inputs": "c = Grid('c', 3)\nb(i, j, k).assign(a(i, j, k) + c(i, j, k))\nSTENCIL = [b]\n",
+        "unassigned": "STENCIL = [b]\n",
+    }
+    for name, body in cases.items():
+        p = tmp_path / (name + ".py")
+        p.write_text(head + body)
+        with pytest.raises(dsl.LoweringError):
+            dsl.lower(str(p))
+    p = tmp_path / "arity.py"
+    p.write_text(head + "b(i, j, k).assign(a(i, j))\nSTENCIL = [b]\n")
+    with pytest.raises(ValueError):
+        dsl.lower(str(p))
+
+
+# ---- GPU: compiled stencils against the oracle ---------------------------------------------------------------------
+PAD = GZ = 8
+
+
+def run_compiled(cs, arr, n):
+    nb = tuple((x + 2 * GZ) // 8 for x in n)
+    grid_h, adj = bk.init_grid(nb)
+    info = bk.BrickInfo(adj)
+    grid = bk.DeviceGrid(grid_h)
+    b_in, b_out = bk.Brick(info, info.allocate(512), 0), bk.Brick(info, info.allocate(512), 0)
+    dev = bk.DeviceBuffer.from_numpy(arr)
+    bk.copyToBrick(tuple(x + 2 * GZ for x in n), (PAD,) * 3, (0,) * 3, dev, grid, b_in)
+    out = {}
+    for label, kernel in (("auto", bk.KERNEL_AUTO), ("brick", bk.KERNEL_BRICK)):
+        b_out.storage.dat.zero()
+        cs.apply(grid, b_in, b_out, (1, 1, 1), tuple(x - 1 for x in nb), kernel)
+        res = bk.DeviceBuffer(arr.nbytes)
+        res.zero()
+        bk.copyFromBrick(n, (PAD,) * 3, (GZ,) * 3, res, grid, b_out)
+        out[label] = res.download(np.float64).reshape(arr.shape)
+    return out
+
+
+def rel(a, b):
+    return float((np.abs(a - b) / (np.abs(a) + np.abs(b) + 1e-300)).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("script,consts,kind,radius", [
+    ("7pt", {"coeff": COEFF7}, "star", 1), ("mpi7pt", None, "star", 1), ("mpi13pt", None, "star", 2),
+    ("mpi25pt", None, "star", 4), ("mpi125pt", None, "cube", 2),
+    (os.path.join(HERE, "star3.py"), {"c": [0.05 * (n + 1) for n in range(19)]}, "star", 3),
+    (os.path.join(HERE, "box27.py"), {"w0": 0.2, "w1": 0.05, "w2": 0.02, "w3": 0.0325}, "cube", 1),
+    (os.path.join(HERE, "box27_skewed.py"), None, "taps", 1),
+    (os.path.join(HERE, "upwind.py"), {"W": 0.3}, "taps", 3),
+])
+def test_compiled_stencils_against_the_oracle(script, consts, kind, radius):
+    from oracle import schedule as S
+    cs = bk.compile_stencil(script, consts)
+    assert (cs.kind, cs.radius) == (kind, radius)
+    n = (40, 24, 32)
+    rng = np.random.default_rng(17)
+    arr = rng.random(tuple(x + 2 * (PAD + GZ) for x in n[::-1]))
+    o = PAD + GZ
+    lo, hi = (o, o, o), tuple(o + x for x in n)
+    want = S.taps_sweep(arr, cs.taps, lo, hi)
+    got = run_compiled(cs, arr, n)
+    for label, res in got.items():
+        assert rel(res[o:-o, o:-o, o:-o], want[o:-o, o:-o, o:-o]) < 1e-12, label
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt"])
+def test_compiled_reference_stencils_equal_the_builtin_ids(name):
+    """a script-compiled stencil and the BK_ST_* id of the same spec run the same kernel with the same coefficients"""
+    cs = bk.compile_stencil(name)
+    st = bk.STENCILS[name]
+    d = bk.BrickDecomp((32, 40, 24), 8)
+    info = d.getBrickInfo()
+    grid = bk.DeviceGrid(d.grid)
+    s_in, s_a, s_b = (info.allocate(512) for _ in range(3))
+    h = np.random.default_rng(3).random(d.nbricks * 512)
+    h[:512] = 0
+    s_in.from_host(h)
+    b_in, b_a, b_b = (bk.Brick(info, s) for s in (s_in, s_a, s_b))
+    bk.stencil(st, grid, b_in, b_a)
+    cs.apply(grid, b_in, b_b)
+    bk.device_sync()
+    assert np.array_equal(s_a.to_host(), s_b.to_host())
+    if cs.fused_steps == 2:
+        s_a.dat.zero(), s_b.dat.zero()
+        bk.stencil_advance(st, 2, grid, b_in, b_a)
+        cs.advance(2, grid, b_in, b_b)
+        bk.device_sync()
+        assert np.array_equal(s_a.to_host(), s_b.to_host())
