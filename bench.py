@@ -309,7 +309,10 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "brick", "tiled"])
     ap.add_argument("--transport", default="kernel", choices=["kernel", "ce"],
                     help="ghost exchange as one pull kernel over NVLink peer mappings (default, faster) or on the copy engines")
-    ap.add_argument("--thin", action="store_true", help="split sweeps with thin ghost-dependent k segments (BK_PART_THIN)")
+    ap.add_argument("--pull-shape", default="", metavar="CTAS,THREADS",
+                    help="launch shape of the pull kernel, e.g. 32,1024 (narrow: leaves the other SMs to the overlapped sweep)")
+    ap.add_argument("--thin", default="auto", choices=["auto", "on", "off"],
+                    help="split sweeps with thin ghost-dependent k segments (BK_PART_THIN); auto = N>1 and radius <= 2")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -339,7 +342,9 @@ def main():
             dm.enable_overlap()
         if args.no_fuse:
             dm.fuse = 1
-        dm.transport, dm.thin = args.transport, args.thin
+        dm.transport, dm.thin = args.transport, {"auto": None, "on": True, "off": False}[args.thin]
+        if args.pull_shape:
+            dm.set_pull_shape(*[int(x) for x in args.pull_shape.split(",")])
         rng = np.random.default_rng(0x5EED + rank)
         host = rng.random(dm.decomp.nbricks * 512)
         host[:512] = 0.0
@@ -371,7 +376,7 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"weak {args.stencil} {size}^3 per GPU, 8^3 bricks, 1 exchange + {it} sweeps per step",
                    "process_grid": "x".join(map(str, cart)), "exchange_MB_per_gpu_per_step": d.view.bytes / 1e6,
-                   "overlap": not args.no_overlap, "kernel": args.kernel,
+                   "overlap": not args.no_overlap, "kernel": args.kernel, "thin_split": d._thin(),
                    "exchange_transport": "copy engines (faces) + narrow pull kernel (edges, corners) over NVLink peer mappings"
                    if d._remote() else "one pull kernel over NVLink peer mappings (CUDA IPC)", "steps_per_pass": d.steps_per_pass(),
                    "l2": f"inputs larger than L2: {2 * d.storage[0].dat.nbytes / 1e9:.2f} GB streamed per sweep"},
@@ -406,7 +411,7 @@ def main():
         except Exception as exc:  # the checker is optional for the product arm
             line["cpu_baseline"] = {"value": None, "unit": "GStencil/s", "cores": 0, "kind": "port",
                                     "sample": f"unavailable: {exc}"}
-    elif n > 1:
+    elif n > 1 and not args.no_extras:
         e2e_s, bi, bo = e2e_periods(bk, [d, make_domain()], 6)
         e2e_s = max_over_ranks(dist, e2e_s)
         line["e2e"] = {"value": pts * it * n / e2e_s / 1e9, "unit": "GStencil/s", "h2d_bytes_per_step": bi * n,

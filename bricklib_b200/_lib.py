@@ -99,6 +99,7 @@ SIGNATURES = {
     "bk_xplan_create": (C.c_int, [C.POINTER(vp), C.POINTER(Seg), C.c_int]),
     "bk_xplan_destroy": (C.c_int, [vp]),
     "bk_xplan_bytes": (sz, [vp]),
+    "bk_xplan_set_shape": (C.c_int, [vp, C.c_int, C.c_int]),
     "bk_xplan_run": (C.c_int, [vp, vp]),
     "bk_xplan_run_sync": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, u64, vp]),
     "bk_xplan_run_gate": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.POINTER(vp), C.c_int, vp, u64, vp]),

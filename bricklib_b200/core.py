@@ -292,6 +292,10 @@ class ExchangeView:
         self._h = h
         self.bytes = load().bk_xplan_bytes(h)
 
+    def set_shape(self, ctas=0, threads=0):
+        """launch shape of the pull kernel: (0, 0) = wide default, e.g. (32, 1024) = narrow (see bk_xplan_set_shape)"""
+        check(load().bk_xplan_set_shape(self._h, ctas, threads))
+
     def exchange(self, stream=None):
         check(load().bk_xplan_run(self._h, stream))
 

@@ -20,6 +20,7 @@ struct bk_xplan {
   size_t bytes = 0;
   uint64_t **flagbuf_dev = nullptr;  // scratch for flag pointer lists (64 wait + 64 signal)
   unsigned long long *done_dev = nullptr;  // CTAs that finished, summed over all launches of this plan
+  int shape_ctas = 0, shape_threads = 0;   // bk_xplan_set_shape: 0 = default (many 256-thread CTAs)
   // copy-engine transport (bk_xplan_run_ce): the segments as host data, dealt largest-first to a few lanes
   std::vector<bk_seg_t> segs_host;
   std::vector<int> lane_of;                // segment -> lane, in issue order `order`
@@ -44,15 +45,20 @@ __device__ __forceinline__ void spin_until(const uint64_t *flag, uint64_t value)
   while (*f < value) __nanosleep(64);
 }
 
-__global__ void __launch_bounds__(kThreads) k_xplan(const bk_seg_t *__restrict__ segs,
-                                                   const unsigned long long *__restrict__ first, int nseg,
-                                                   unsigned long long nchunks, uint64_t *const *wait_flags, int nwait,
-                                                   int nsignal, uint64_t *gate, unsigned long long *done) {
+// A CTA is `blockDim.x / 256` groups of 256 threads; each group moves one 16 KiB chunk per iteration.  The default
+// shape is many 1-group CTAs (fastest when the GPU is otherwise idle); a NARROW shape -- few 1024-thread CTAs -- keeps
+// the pull on a handful of SMs so that sweep CTAs (which need an SM's whole register file) run beside it on the others.
+__global__ void __launch_bounds__(1024) k_xplan(const bk_seg_t *__restrict__ segs,
+                                                const unsigned long long *__restrict__ first, int nseg,
+                                                unsigned long long nchunks, uint64_t *const *wait_flags, int nwait,
+                                                int nsignal, uint64_t *gate, unsigned long long *done) {
   if (nwait > 0) {
-    if (threadIdx.x < nwait) spin_until(wait_flags[threadIdx.x], (uint64_t) (size_t) wait_flags[64]);
+    if ((int) threadIdx.x < nwait) spin_until(wait_flags[threadIdx.x], (uint64_t) (size_t) wait_flags[64]);
     __syncthreads();
   }
-  for (unsigned long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+  const unsigned groups = blockDim.x / kThreads, grp = threadIdx.x / kThreads, tid = threadIdx.x % kThreads;
+  for (unsigned long long c = (unsigned long long) blockIdx.x * groups + grp; c < nchunks;
+       c += (unsigned long long) gridDim.x * groups) {
     int lo = 0, hi = nseg;  // segment s with first[s] <= c < first[s+1]
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
@@ -66,11 +72,11 @@ __global__ void __launch_bounds__(kThreads) k_xplan(const bk_seg_t *__restrict__
     if (n16 == kChunkBytes / 16) {
       int4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = src[threadIdx.x + u * kThreads];
+      for (int u = 0; u < 4; ++u) v[u] = src[tid + u * kThreads];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) dst[threadIdx.x + u * kThreads] = v[u];
+      for (int u = 0; u < 4; ++u) dst[tid + u * kThreads] = v[u];
     } else {
-      for (size_t x = threadIdx.x; x < n16; x += kThreads) dst[x] = src[x];
+      for (size_t x = tid; x < n16; x += kThreads) dst[x] = src[x];
     }
   }
   if (done) {
@@ -119,10 +125,16 @@ int launch_copy(bk_xplan *p, uint64_t *const *wait_dev, int nwait, cudaStream_t 
                 uint64_t *gate = nullptr, bool publish = false) {
   if (p->nchunks == 0 && nwait == 0 && !publish) return BK_OK;
   unsigned long long want = p->nchunks ? p->nchunks : 1;
-  const unsigned long long cap = (unsigned long long) sm_count() * 8;
+  unsigned threads = kThreads;
+  unsigned long long cap = (unsigned long long) sm_count() * 8;
+  if (p->shape_ctas > 0) {
+    threads = (unsigned) p->shape_threads;
+    cap = (unsigned long long) p->shape_ctas;
+    want = (want + threads / kThreads - 1) / (threads / kThreads);
+  }
   const unsigned grid = (unsigned) (want < cap ? want : cap);
-  k_xplan<<<grid, kThreads, 0, s>>>(p->segs_dev, p->chunk_first_dev, p->nseg, p->nchunks, wait_dev, nwait, nsignal, gate,
-                                    publish ? p->done_dev : nullptr);
+  k_xplan<<<grid, threads, 0, s>>>(p->segs_dev, p->chunk_first_dev, p->nseg, p->nchunks, wait_dev, nwait, nsignal, gate,
+                                   publish ? p->done_dev : nullptr);
   BK_LAUNCHED();
   return BK_OK;
 }
@@ -177,6 +189,15 @@ int bk_xplan_destroy(bk_xplan_t *p) {
 }
 
 size_t bk_xplan_bytes(const bk_xplan_t *p) { return p ? p->bytes : 0; }
+
+int bk_xplan_set_shape(bk_xplan_t *p, int ctas, int threads_per_cta) {
+  BK_REQUIRE(p, "null plan");
+  BK_REQUIRE((ctas == 0 && threads_per_cta == 0) ||
+                 (ctas > 0 && threads_per_cta >= 256 && threads_per_cta <= 1024 && threads_per_cta % 256 == 0),
+             "shape: ctas > 0 and threads a multiple of 256 up to 1024 (or 0, 0 for the default)");
+  p->shape_ctas = ctas, p->shape_threads = threads_per_cta;
+  return BK_OK;
+}
 
 int bk_xplan_run(bk_xplan_t *p, void *stream) {
   BK_REQUIRE(p, "null plan");

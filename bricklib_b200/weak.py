@@ -70,7 +70,10 @@ class WeakDomain:
         # every N), "ce" = faces on the copy engines + narrow kernel for edges/corners (bk_xplan_run_ce; takes no SM, but
         # 104 MB from 7 peers took 0.55 ms at N=8 against ~0.15 ms for the kernel: profiles/r01c_multi_gpu.md)
         self.transport = "kernel"
-        self.thin = False    # split sweeps: thin k segments for the ghost-dependent layers (BK_PART_THIN)
+        # split sweeps with thin k segments for the ghost-dependent layers (BK_PART_THIN): None = when ghost ranges cross
+        # NVLink and the stencil radius is <= 2 (measured at N=8, profiles/r01c_multi_gpu.md: 13-pt +8 %, 125-pt +3 %,
+        # 7-pt +1 %, 25-pt -2 %); True / False force it
+        self.thin = None
         self.trace = None    # developer aid: a list collects (label, Event) marks of one period (tools/period_trace.py)
         self.fuse = 2        # time steps per pass where a fused kernel exists (7/13-point); 1 = one sweep per pass
 
@@ -81,6 +84,9 @@ class WeakDomain:
         ptrs[self.rank] = self.storage[0].dat.ptr
         self.view = core.ExchangeView(self.decomp, self.storage[0], ptrs, self.rank)
         self.hs = handshake
+
+    def set_pull_shape(self, ctas=0, threads=0):
+        self.view.set_shape(ctas, threads)
 
     def enable_overlap(self):
         s = C.c_void_p()
@@ -140,6 +146,11 @@ class WeakDomain:
         """does the exchange run on the copy engines (and the split sweep with thin ghost-dependent segments)?"""
         return self.transport == "ce"
 
+    def _thin(self):
+        if self.thin is None:
+            return bool(self.peers) and load().bk_stencil_radius(self.stencil) <= 2
+        return bool(self.thin)
+
     def _wait_peers_done(self, stream):
         if self.hs is None or not self.peers:
             return
@@ -181,7 +192,7 @@ class WeakDomain:
                 self._wait_peers_done(stream)  # pass 1 rewrites storage[0], whose skin the peers were reading
             if p == 0 and overlap and not last:
                 try:
-                    thin = _lib.PART_THIN if (self.thin or self._remote()) else 0
+                    thin = _lib.PART_THIN if self._thin() else 0
                     self._advance(fuse, src, dst, lo, hi, own, _lib.PART_READY | thin, stream)
                     self._mark("pass 0 READY done", stream)
                     self._advance(fuse, src, dst, lo, hi, own, _lib.PART_REST | thin, cs)

@@ -213,6 +213,11 @@ typedef struct bk_xplan bk_xplan_t;
 int bk_xplan_create(bk_xplan_t **plan, const bk_seg_t *segs_host, int nseg);
 int bk_xplan_destroy(bk_xplan_t *plan);
 size_t bk_xplan_bytes(const bk_xplan_t *plan);
+/* Launch shape of the pull kernel.  Default (0, 0): up to 8 CTAs of 256 threads per SM -- the fastest copy on an idle
+ * GPU.  A narrow shape (e.g. 32 CTAs of 1024 threads) confines the pull to a few SMs: the marching sweep kernels
+ * allocate an SM's whole register file, so pull CTAs never co-reside with them; a narrow pull leaves the other SMs to
+ * the overlapped sweep instead of time-sharing all of them. */
+int bk_xplan_set_shape(bk_xplan_t *plan, int ctas, int threads_per_cta);
 /* run the plan on `stream`.  wait/signal (optional, may be NULL/0) implement the cross-process handshake:
  * before copying, spin until every wait_flags[i] >= epoch; after copying (and a system fence) store epoch to every
  * signal_flags[i] (peer-visible device memory). */

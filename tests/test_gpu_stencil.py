@@ -204,7 +204,7 @@ def test_weak_period_fused_passes_against_reference_fixture(golden_dir, fuse, ov
             assert launches[0] == 1 + oracle.ST_ITER[st] // 2, "exchange + one launch per two steps"
 
 
-@pytest.mark.parametrize("transport,ce_min", [("kernel", None), ("ce", "4096"), ("ce", "0")])
+@pytest.mark.parametrize("transport,ce_min", [("kernel", None), ("narrow", None), ("ce", "4096"), ("ce", "0")])
 def test_weak_period_exchange_transports_agree_with_reference_fixture(golden_dir, monkeypatch, transport, ce_min):
     """the overlapped period with the ghost ranges moved by the pull kernel, by the copy engines (faces) plus the narrow
     kernel (edges, corners), or by the copy engines alone"""
@@ -216,8 +216,11 @@ def test_weak_period_exchange_transports_agree_with_reference_fixture(golden_dir
         if st == 0:
             continue
         d = bk.WeakDomain(dom, st)
-        d.transport = transport
+        d.transport = "kernel" if transport == "narrow" else transport
         d.connect()
+        if transport == "narrow":
+            d.set_pull_shape(2, 1024)      # few wide CTAs: the pull confined to a couple of SMs
+            d.thin = True
         d.load_interior(z["in_c111"])
         d.enable_overlap()
         for _ in range(2):

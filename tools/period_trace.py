@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--transport", default="kernel")
     ap.add_argument("--thin", action="store_true")
+    ap.add_argument("--pull-shape", default="")
     ap.add_argument("--no-overlap", action="store_true")
     args = ap.parse_args()
     import bench
@@ -35,7 +36,9 @@ def main():
     bench.wire_peers(bk, d, dist, rank, world)
     if not args.no_overlap:
         d.enable_overlap()
-    d.transport, d.thin = args.transport, args.thin
+    d.transport, d.thin = args.transport, (True if args.thin else None)
+    if args.pull_shape:
+        d.set_pull_shape(*[int(x) for x in args.pull_shape.split(",")])
     host = np.random.default_rng(rank).random(d.decomp.nbricks * 512)
     host[:512] = 0
     d.storage[0].from_host(host)
