@@ -7,8 +7,8 @@ template surface lives in include/*.h and the drivers in drivers/.
 from ._lib import (BK_OK, KERNEL_AUTO, KERNEL_BRICK, KERNEL_TILED, PART_ALL, PART_READY, PART_REST, PART_THIN, STENCILS,  # noqa: F401
                    BrickError, load)
 from .core import (BRICK, Brick, BrickDecomp, BrickInfo, BrickStorage, DeviceBuffer, DeviceGrid, Event,  # noqa: F401
-                   ExchangeView, compareBrick, copyFromBrick, copyToBrick, device_sync, init_grid, stencil,
-                   stencil_advance, stencil_list, stencil_part, Unsupported)
+                   ExchangeView, StitchedGrid, compareBrick, copyFromBrick, copyToBrick, device_sync, init_grid, stencil,
+                   stencil_advance, stencil_list, stencil_part, section_range, zmort_decode, zmort_encode, Unsupported)
 from .weak import WeakDomain, shell_boxes  # noqa: F401
 
 

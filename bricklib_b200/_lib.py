@@ -34,6 +34,11 @@ class Seg(C.Structure):
     _fields_ = [("src", vp), ("dst", vp), ("bytes", sz)]
 
 
+class StitchBox(C.Structure):
+    _fields_ = [("first", C.c_ulong), ("count", C.c_ulong), ("lo", C.c_ulong * 3), ("n", C.c_long * 3),
+                ("wrap", C.c_int * 3), ("is_box", C.c_int)]
+
+
 class Tap(C.Structure):
     _fields_ = [("di", C.c_int), ("dj", C.c_int), ("dk", C.c_int), ("c", C.c_double)]
 
@@ -82,6 +87,10 @@ SIGNATURES = {
     "bk_rank_map": (C.c_int, [ip, ip, C.POINTER(u64), ip]),
     "bk_zmort_encode": (C.c_ulong, [C.POINTER(C.c_ulong)]),
     "bk_zmort_decode": (C.c_int, [C.c_ulong, C.POINTER(C.c_ulong)]),
+    "bk_stitch_box": (C.c_int, [C.c_ulong, C.c_ulong, C.c_ulong, C.POINTER(StitchBox)]),
+    "bk_stitch_dims": (C.c_int, [vp, C.POINTER(StitchBox), up]),
+    "bk_stitch_grid": (C.c_int, [vp, C.POINTER(StitchBox), up]),
+    "bk_stitch_region_needed": (C.c_int, [vp, C.POINTER(StitchBox), C.c_ulong, C.c_int]),
     "bk_copy_to_brick": (C.c_int, [lp, lp, lp, vp, vp, vp, sz, vp]),
     "bk_copy_from_brick": (C.c_int, [lp, lp, lp, vp, vp, vp, sz, vp]),
     "bk_compare_brick": (C.c_int, [lp, lp, lp, vp, vp, vp, sz, C.c_double, C.POINTER(C.c_ulonglong), dp, vp]),

@@ -264,6 +264,61 @@ class BrickDecomp:
             pass
 
 
+def section_range(rank, allsubs, size):
+    """Z-Morton id range [l, r) of `rank` when `allsubs` subdomains are dealt to `size` ranks (strong/args.cpp:104-113):
+    the first allsubs % size ranks get one more."""
+    shift, length = allsubs % size, allsubs // size
+    mylen = length + (1 if shift > rank else 0)
+    lo = rank * mylen + (0 if shift > rank else shift)
+    return lo, lo + mylen
+
+
+def zmort_decode(idx):
+    c = (C.c_ulong * 3)()
+    check(load().bk_zmort_decode(idx, c))
+    return tuple(c)
+
+
+def zmort_encode(coord):
+    return int(load().bk_zmort_encode((C.c_ulong * 3)(*coord)))
+
+
+class StitchedGrid:
+    """A rank's Z-Morton section of subdomains presented as ONE dense brick grid (bk_stitch_*): entries are global brick
+    ids q*nbricks + local id; same-GPU ghosts alias their owners' bricks, only surface regions need the exchange.
+    GPU analogue of the mmap ghost aliasing of strong/main.cpp:205-262."""
+
+    def __init__(self, decomp, first, count, subdim):
+        self.decomp, self.first, self.count, self.subdim = decomp, int(first), int(count), int(subdim)
+        self.box = _lib.StitchBox()
+        check(load().bk_stitch_box(self.first, self.count, self.subdim, C.byref(self.box)))
+        self.is_box = bool(self.box.is_box)
+        self.wrap = tuple(bool(w) for w in self.box.wrap)
+        self.n = tuple(int(x) for x in self.box.n)
+        self.lo = tuple(int(x) for x in self.box.lo)
+        d = (C.c_uint * 3)()
+        check(load().bk_stitch_dims(decomp._h, C.byref(self.box), d))
+        self.dims = tuple(d)
+        self.grid = None
+        if self.is_box:
+            g = np.zeros(self.dims[0] * self.dims[1] * self.dims[2], dtype=np.uint32)
+            check(load().bk_stitch_grid(decomp._h, C.byref(self.box), g.ctypes.data_as(_lib.up)))
+            self.grid = g.reshape(self.dims[::-1])
+
+    def region_needed(self, sub_id, region):
+        rc = load().bk_stitch_region_needed(self.decomp._h, C.byref(self.box), int(sub_id), int(region))
+        if rc < 0:
+            raise ValueError("bad subdomain id or region index")
+        return bool(rc)
+
+    def sweep_box(self, last=False):
+        """brick box a sweep covers: the shell is swept only where it is real ghost storage (communication avoiding),
+        never where it aliases my own interior; the last sweep of a period covers the interior only"""
+        lo = tuple(1 if (w or last) else 0 for w in self.wrap)
+        hi = tuple(d - 1 if (w or last) else d for w, d in zip(self.wrap, self.dims))
+        return lo, hi
+
+
 class ExchangeView:
     """One fused pull of every ghost region of a storage: ghost[i] <- peer_base[rank_map[ghost[i].neighbor]] skin[i].
 

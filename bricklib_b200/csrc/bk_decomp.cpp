@@ -245,4 +245,79 @@ int bk_zmort_decode(unsigned long id, unsigned long *c) {
   return BK_OK;
 }
 
+// ---- stitching: a rank's subdomains as one brick grid (strong scaling) ---------------------------------------------
+// GPU analogue of the reference's ghost aliasing through mmap views (strong/main.cpp:205-262): the subdomains with
+// Z-Morton ids [first, first+count) (strong/args.cpp:104-113) form a box of the periodic subdim^3 arrangement; their
+// bricks, addressed as  q * nbricks + local id  in one subdomain-major allocation, are presented as ONE dense grid.
+int bk_stitch_box(unsigned long first, unsigned long count, unsigned long subdim, bk_stitch_box_t *b) {
+  BK_REQUIRE(b && count > 0 && subdim > 0, "bad arguments");
+  unsigned long lo[3] = {~0ul, ~0ul, ~0ul}, hi[3] = {0, 0, 0};
+  for (unsigned long q = 0; q < count; ++q) {
+    unsigned long c[3];
+    bk_zmort_decode(first + q, c);
+    for (int a = 0; a < 3; ++a) lo[a] = c[a] < lo[a] ? c[a] : lo[a], hi[a] = c[a] > hi[a] ? c[a] : hi[a];
+  }
+  unsigned long vol = 1;
+  for (int a = 0; a < 3; ++a) {
+    b->lo[a] = lo[a];
+    b->n[a] = (long) (hi[a] - lo[a] + 1);
+    b->wrap[a] = (unsigned long) b->n[a] == subdim;
+    vol *= (unsigned long) b->n[a];
+  }
+  b->first = first, b->count = count;
+  b->is_box = vol == count;
+  return BK_OK;
+}
+
+int bk_stitch_dims(const bk_decomp_t *d, const bk_stitch_box_t *b, unsigned *dims3) {
+  BK_REQUIRE(d && b && dims3, "null argument");
+  for (int a = 0; a < 3; ++a) dims3[a] = (unsigned) (b->n[a] * (long) (d->T[a] - 2 * d->G[a]) + 2 * d->G[a]);
+  return BK_OK;
+}
+
+int bk_stitch_grid(const bk_decomp_t *d, const bk_stitch_box_t *b, unsigned *grid) {
+  BK_REQUIRE(d && b && grid, "null argument");
+  BK_REQUIRE(b->is_box, "the section is not a box of subdomains");
+  BK_REQUIRE((unsigned long long) b->count * d->nbricks < (1ull << 32), "global brick ids exceed 32 bits");
+  for (int a = 0; a < 3; ++a) BK_REQUIRE(d->G[a] == 1, "stitching assumes a ghost shell of one brick");
+  long B[3], S[3];
+  for (int a = 0; a < 3; ++a) B[a] = (long) d->T[a] - 2, S[a] = b->n[a] * B[a] + 2;
+  for (long K = 0; K < S[2]; ++K)
+    for (long J = 0; J < S[1]; ++J)
+      for (long I = 0; I < S[0]; ++I) {
+        const long p[3] = {I - 1, J - 1, K - 1};  // brick position relative to the box: -1 .. n
+        unsigned long cs[3];
+        long lb[3];
+        for (int a = 0; a < 3; ++a) {
+          const long n = b->n[a] * B[a];
+          long pw = p[a];
+          if (b->wrap[a]) pw = (pw + n) % n;                 // periodic onto myself: the far side's interior brick
+          long cl = pw < 0 ? 0 : pw >= n ? n - 1 : pw;       // nearest brick of the box along this axis ...
+          cl /= B[a];                                        // ... and the subdomain it belongs to
+          cs[a] = b->lo[a] + (unsigned long) cl;
+          lb[a] = pw - cl * B[a] + 1;                        // position in that subdomain's ghost-inclusive grid
+        }
+        const unsigned long q = bk_zmort_encode(cs) - b->first;
+        grid[((size_t) K * S[1] + J) * S[0] + I] = (unsigned) (q * d->nbricks + d->grid[d->slot(lb[0], lb[1], lb[2])]);
+      }
+  return BK_OK;
+}
+
+int bk_stitch_region_needed(const bk_decomp_t *d, const bk_stitch_box_t *b, unsigned long sub_id, int region) {
+  if (!d || !b || region < 0 || region >= (int) d->ghost.size() || sub_id < b->first || sub_id >= b->first + b->count)
+    return BK_EINVAL;
+  unsigned long c[3];
+  bk_zmort_decode(sub_id, c);
+  const uint64_t set = d->ghost[region].neighbor;
+  for (int a = 0; a < 3; ++a) {
+    const int off = (set >> (a + 1)) & 1 ? 1 : (set >> (31 + a + 1)) & 1 ? -1 : 0;
+    if (off == 0) continue;
+    // the region lies beyond the subdomain along this axis: it is on the box surface only if the subdomain is the
+    // outermost one on that side -- and the box must not wrap onto itself there
+    if (b->wrap[a]) return 0;
+    if (off > 0 ? c[a] != b->lo[a] + (unsigned long) b->n[a] - 1 : c[a] != b->lo[a]) return 0;
+  }
+  return 1;
+}
+
 }  // extern "C"

@@ -21,7 +21,6 @@
 //
 // usage: strong [-d global_edge=512] [-s subdomain_edge=128] [-I periods=100] [-g gpus=1] [-S stencil] [-v]
 #include <unistd.h>
-#include <array>
 #include <thread>
 #include "common.h"
 
@@ -150,42 +149,19 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
   S.base[rank] = st0.dat.get();
   bar.wait();
 
-  // ---- stitched super grid: is my section a box of subdomains? -----------------------------------------------------
-  const long B = STRIDEB - 2;  // bricks per subdomain edge
-  unsigned long blo[3] = {~0ul, ~0ul, ~0ul}, bhi[3] = {0, 0, 0};
-  std::vector<std::array<unsigned long, 3>> subc(nsub);
-  for (unsigned q = 0; q < nsub; ++q) {
-    unsigned long c[3];
-    bk_zmort_decode(mysec_l + q, c);
-    for (int d = 0; d < 3; ++d) subc[q][d] = c[d], blo[d] = std::min(blo[d], c[d]), bhi[d] = std::max(bhi[d], c[d]);
-  }
-  long bn[3];
-  bool wrap[3];
-  for (int d = 0; d < 3; ++d) bn[d] = (long) (bhi[d] - blo[d] + 1), wrap[d] = (unsigned long) bn[d] == S.subdim;
-  const bool stitched = !S.no_stitch && (unsigned long) (bn[0] * bn[1] * bn[2]) == nsub &&
-                        (unsigned long long) nsub * nb < (1ull << 32);
+  // ---- stitched super grid (bk_stitch_*): is my section a box of subdomains? ---------------------------------------
+  bk_stitch_box_t box;
+  bkCheck(bk_stitch_box(mysec_l, nsub, S.subdim, &box));
+  const bool stitched = !S.no_stitch && box.is_box && (unsigned long long) nsub * nb < (1ull << 32);
+  const bool wrap[3] = {box.wrap[0] != 0, box.wrap[1] != 0, box.wrap[2] != 0};
   S.stitched[rank] = stitched;
   unsigned *sgrid_dev = nullptr;
-  std::vector<long> sgd = {bn[0] * B + 2, bn[1] * B + 2, bn[2] * B + 2};
+  unsigned sdims[3];
+  bkCheck(bk_stitch_dims(bDecomp.handle(), &box, sdims));
+  std::vector<long> sgd = {(long) sdims[0], (long) sdims[1], (long) sdims[2]};
   if (stitched) {
     std::vector<unsigned> sg((size_t) sgd[0] * sgd[1] * sgd[2]);
-    for (long K = 0; K < sgd[2]; ++K)
-      for (long J = 0; J < sgd[1]; ++J)
-        for (long I = 0; I < sgd[0]; ++I) {
-          const long p[3] = {I - 1, J - 1, K - 1};  // brick position relative to the box, -1 .. n
-          unsigned long cs[3];
-          long lb[3];
-          for (int d = 0; d < 3; ++d) {
-            const long n = bn[d] * B;
-            long pw = p[d];
-            if (wrap[d]) pw = (pw + n) % n;          // periodic onto myself: alias the far side's interior brick
-            const long cl = std::min(std::max(pw, 0l), n - 1) / B;  // nearest subdomain of the box along this axis
-            cs[d] = blo[d] + (unsigned long) cl;
-            lb[d] = pw - cl * B + 1;                 // position in that subdomain's ghost-inclusive brick grid
-          }
-          const unsigned long q = bk_zmort_encode(cs) - mysec_l;
-          sg[((size_t) K * sgd[1] + J) * sgd[0] + I] = (unsigned) (q * nb + bDecomp[lb[2]][lb[1]][lb[0]]);
-        }
+    bkCheck(bk_stitch_grid(bDecomp.handle(), &box, sg.data()));
     copyToDevice(sgd, sgrid_dev, sg.data());
   }
 
@@ -196,16 +172,7 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
   size_t remote_bytes = 0, peers_mask = 0;
   for (unsigned q = 0; q < nsub; ++q)
     for (size_t i = 0; i < bDecomp.ghost.size(); ++i) {
-      if (stitched) {
-        bool needed = true;
-        for (int d = 0; d < 3; ++d) {
-          const BitSet &n = bDecomp.ghost[i].neighbor;
-          const int off = n.get(d + 1) ? 1 : n.get(-1 - d) ? -1 : 0;
-          if (off == 0) continue;
-          if (wrap[d] || (off > 0 ? subc[q][d] != bhi[d] : subc[q][d] != blo[d])) needed = false;
-        }
-        if (!needed) continue;
-      }
+      if (stitched && bk_stitch_region_needed(bDecomp.handle(), &box, mysec_l + q, (int) i) != 1) continue;
       int dst;
       unsigned long sub;
       sec.owner(neighbour_id(mysec_l + q, bDecomp.ghost[i].neighbor, S.subdim), dst, sub);

@@ -183,6 +183,31 @@ void brickStencil(int stencil, const unsigned *grid_dev, const std::vector<long>
   brickStencil(stencil, grid_dev, gdims, bIn, bOut, {0, 0, 0}, gdims, coeff, stream);
 }
 
+/// A stencil lowered from its tap list (bk_stencil_compile) -- what `brick("script.py", "CUDA", ...)` is to the reference:
+/// the expression of a stencils/*.py script, here as data.  `python -m bricklib_b200.dsl script.py --emit-c NAME` writes
+/// the table for a script at build time.  launch() = brickStencil for this stencil.
+class BrickStencilDef {
+  bk_stencil_def_t *def = nullptr;
+
+ public:
+  int kind = 0, radius = 0, ntaps = 0, st_iter = 0, fused_steps = 1;
+  BrickStencilDef(const bk_tap_t *taps, int n) {
+    bkCheck(bk_stencil_compile(&def, taps, n));
+    bkCheck(bk_stencil_def_info(def, &kind, &radius, &ntaps, &st_iter, &fused_steps));
+  }
+  explicit BrickStencilDef(const std::vector<bk_tap_t> &taps) : BrickStencilDef(taps.data(), (int) taps.size()) {}
+  BrickStencilDef(const BrickStencilDef &) = delete;
+  ~BrickStencilDef() { bk_stencil_def_destroy(def); }
+  template <typename T>
+  void launch(const unsigned *grid_dev, const std::vector<long> &gdims, T &bIn, T &bOut, const std::vector<long> &lo,
+              const std::vector<long> &hi, void *stream = nullptr, unsigned kernel = BK_KERNEL_AUTO) const {
+    bk_field_t f = {&bIn.bInfo->adj[0][0], bIn.dat, bIn.step, bOut.dat, bOut.step};
+    unsigned g[3], l[3], h[3];
+    for (int d = 0; d < 3; ++d) g[d] = (unsigned) gdims[d], l[d] = (unsigned) lo[d], h[d] = (unsigned) hi[d];
+    bkCheck(bk_stencil_def_apply(def, &f, grid_dev, g, l, h, kernel, stream));
+  }
+};
+
 /// cutime_func (stencils/stencils_cu.h:13-28): one warm-up launch, then `reps` launches between two events;
 /// returns seconds per launch
 template <typename F>

@@ -107,6 +107,10 @@ class ExchangeView {
   ~ExchangeView() { bk_xplan_destroy(plan); }
   /// asynchronous on `stream`; the caller orders it against the peers' sweeps (events / flags / a barrier)
   void exchange(void *stream = nullptr) { bkCheck(bk_xplan_run(plan, stream)); }
+  /// launch shape of the pull kernel: (0, 0) = wide default, e.g. (32, 1024) = confined to a few SMs (bk_xplan_set_shape)
+  void setShape(int ctas, int threads_per_cta) { bkCheck(bk_xplan_set_shape(plan, ctas, threads_per_cta)); }
+  /// the same plan with the big ranges on the copy engines (bk_xplan_run_ce): takes no SM from the sweeps
+  void exchangeCopyEngines(void *stream = nullptr) { bkCheck(bk_xplan_run_ce(plan, nullptr, 0, nullptr, 0, 0, stream)); }
   /// with the cross-process handshake of bk_xplan_run_sync
   void exchange(const std::vector<const uint64_t *> &wait, const std::vector<uint64_t *> &signal, uint64_t epoch,
                 void *stream = nullptr) {
@@ -179,6 +183,7 @@ class BrickDecomp {
   unsigned nbricks() const { return bk_decomp_nbricks(h); }
   std::vector<long> gridDims() const { return {(long) tdims[0], (long) tdims[1], (long) tdims[2]}; }
   const unsigned *gridData() const { return grid; }
+  const bk_decomp_t *handle() const { return h; }  ///< for the C-ABI calls that take a decomposition (bk_stitch_*)
   size_t exchangeSize() const {  ///< bricks received per exchange
     size_t n = 0;
     for (auto &g : ghost) n += g.len;

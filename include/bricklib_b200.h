@@ -106,6 +106,31 @@ int bk_rank_map(const int *cart, const int *coo, uint64_t *sets27, int *ranks27)
 unsigned long bk_zmort_encode(const unsigned long *coord3);
 int bk_zmort_decode(unsigned long id, unsigned long *coord3);
 
+/* ---- stitching a rank's subdomains into one brick grid (strong scaling) -------------------------------------------
+ * The reference's CPU strong driver aliases same-rank ghost zones onto their owners' skins with mmap views
+ * (strong/main.cpp:205-262); its CUDA driver copies them with cudaCopy links (strong/main.cu:76-83, :188-247).  Here a
+ * rank's subdomains -- Z-Morton ids [first, first+count), strong/args.cpp:104-113 -- are swept as ONE dense brick grid
+ * whose entries are global brick ids  q * nbricks + local id  (q = id - first) into a subdomain-major allocation:
+ * interior positions name the owning subdomain's brick, the one-brick shell names the ghost brick of the nearest
+ * boundary subdomain, and along an axis where the box spans the whole periodic arrangement the shell aliases the
+ * interior bricks of the far side.  Same-GPU ghost regions are then never copied or recomputed; only regions on the
+ * box surface (bk_stitch_region_needed) take part in the exchange. */
+typedef struct {
+  unsigned long first, count; /* the Z-Morton section */
+  unsigned long lo[3];        /* lowest subdomain coordinate of the bounding box, i first */
+  long n[3];                  /* subdomains per axis */
+  int wrap[3];                /* the box spans the whole periodic arrangement along this axis */
+  int is_box;                 /* the section fills its bounding box (always for power-of-two rank counts) */
+} bk_stitch_box_t;
+int bk_stitch_box(unsigned long first, unsigned long count, unsigned long subdim, bk_stitch_box_t *box);
+/* extents of the stitched grid in bricks: n[a] * (bricks per subdomain edge) + 2 */
+int bk_stitch_dims(const bk_decomp_t *d, const bk_stitch_box_t *box, unsigned *dims3);
+/* fill grid_host[k][j][i] (bk_stitch_dims extents) with global brick ids; needs is_box and a one-brick ghost shell */
+int bk_stitch_grid(const bk_decomp_t *d, const bk_stitch_box_t *box, unsigned *grid_host);
+/* 1 if ghost region `region` (index into BrickDecomp::ghost) of subdomain `sub_id` lies on the box surface, 0 if the
+ * stitched grid never reads it, negative on bad arguments */
+int bk_stitch_region_needed(const bk_decomp_t *d, const bk_stitch_box_t *box, unsigned long sub_id, int region);
+
 /* ---- array <-> brick on the device (include/bricksetup.h:139-221, include/brickcompare.h:30-57) ---------------- */
 /* dimlist/padding/ghost in cells, i first, meaning exactly as in copyToBrick<3>(dimlist, padding, ghost, arr, grid, b) */
 int bk_copy_to_brick(const long *dimlist, const long *padding, const long *ghost, const double *arr_dev,
@@ -171,7 +196,7 @@ int bk_stencil_apply_multi(int stencil, const bk_field_t *fields_dev, unsigned n
                            const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff_host,
                            void *stream);
 /* ---- stencils lowered from tap lists ------------------------------------------------------------------------------
- * The reference turns a stencil expression (stencils/*.py: Grid / Index / ConstRef arithmetic) into code at build time
+ * The reference turns a stencil expression (the stencils/ scripts: Grid / Index / ConstRef arithmetic) into code at build time
  * with codegen/vecscatter (backend table vecscatter:82-109, CUDA backend codegen/st/codegen/backend/cuda.py).  Here the
  * expression is lowered to its tap list -- out(i,j,k) = sum_t c_t * in(i+di_t, j+dj_t, k+dk_t) -- by the host side
  * (bricklib_b200/dsl.py evaluates the same scripts) and bk_stencil_compile picks the kernel family:
