@@ -40,14 +40,42 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region"""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a thread (every 5 ms) when pynvml works,
+    else `nvidia-smi -lms 100` as a subprocess"""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    MASKS = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.nvml, self.samples, self.stop_flag, self.thread = None, [], False, None
+
+    def _nvml_loop(self, nv, handle):
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    why = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except AttributeError:
+                    why = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((sm, int(why)))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+            nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+            self.nvml = nv
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -62,6 +90,13 @@ class ClockSampler:
             self.lines.append(line)
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            sm = [s for s, _ in self.samples]
+            reasons = sorted(n for n, m in self.MASKS.items() if any(w & m for _, w in self.samples))
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(self.sm_max),
+                    "samples": len(sm), "reasons": reasons, "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -82,7 +117,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def dist_setup(n_gpus):
@@ -272,6 +307,23 @@ def reference_period_seconds(stencil_id, size, periods, warm=1):
     return (time.perf_counter() - t0) / periods, kind, cores, isa
 
 
+def strong_leg():
+    """BASELINE.json configs[4] at one GPU's share (512 subdomains of 64^3 = the per-GPU work of 1024^3 on 8 GPUs):
+    the C++ strong driver, stitched super grid (default) and per-subdomain launches (-M)"""
+    exe = os.path.join(ROOT, "drivers", "strong")
+    out = {}
+    for label, extra in (("stitched", []), ("per_subdomain", ["-M"])):
+        try:
+            r = subprocess.run([exe, "-d", "512", "-s", "64", "-I", "20", "-g", "1", "-S", "mpi7pt", *extra],
+                               capture_output=True, text=True, timeout=120)
+            perf = [ln for ln in r.stdout.splitlines() if ln.startswith("perf ")]
+            out[label] = {"GStencil/s": float(perf[-1].split()[1])} if perf else {"error": (r.stdout + r.stderr)[-200:]}
+        except Exception as exc:
+            out[label] = {"error": str(exc)[:200]}
+    out["what"] = "drivers/strong -d 512 -s 64 -I 20 -g 1 -S mpi7pt (20 exchange periods of 8 steps after 1 warm-up)"
+    return out
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -398,6 +450,7 @@ def main():
                             "frac_of_hbm_peak": 16.0 * pts / k2 / 1e9 / peak,
                             "GFLOP/s": (2 * bk.load().bk_stencil_points(sid) - 1) * pts * ks / k2 / 1e9}
         d.stencil, d.st_iter = st, it
+        others["strong_512_in_64_subdomains"] = strong_leg()
         line["others"] = others
         e2e_s, bi, bo = e2e_periods(bk, [d, make_domain()], 8)
         line["e2e"] = {"value": pts * it / e2e_s / 1e9, "unit": "GStencil/s", "h2d_bytes_per_step": bi,
