@@ -34,6 +34,13 @@ class Seg(C.Structure):
     _fields_ = [("src", vp), ("dst", vp), ("bytes", sz)]
 
 
+class Pointwise(C.Structure):
+    _fields_ = [("op", C.c_int), ("c", C.c_double)]
+
+
+POINTWISE_OPS = {"max": 1, "min": 2, "abs": 3}
+
+
 class StitchBox(C.Structure):
     _fields_ = [("first", C.c_ulong), ("count", C.c_ulong), ("lo", C.c_ulong * 3), ("n", C.c_long * 3),
                 ("wrap", C.c_int * 3), ("is_box", C.c_int)]
@@ -100,6 +107,8 @@ SIGNATURES = {
     "bk_stencil_apply_list": (C.c_int, [C.c_int, C.POINTER(Field), vp, sz, dp, vp]),
     "bk_stencil_apply_multi": (C.c_int, [C.c_int, vp, C.c_uint, vp, up, up, up, dp, vp]),
     "bk_stencil_compile": (C.c_int, [C.POINTER(vp), C.POINTER(Tap), C.c_int]),
+    "bk_stencil_compile_pointwise": (C.c_int, [C.POINTER(vp), C.POINTER(Tap), C.c_int, C.POINTER(Pointwise),
+                                               C.POINTER(Pointwise)]),
     "bk_stencil_def_destroy": (C.c_int, [vp]),
     "bk_stencil_def_info": (C.c_int, [vp, ip, ip, ip, ip, ip]),
     "bk_stencil_def_apply": (C.c_int, [vp, C.POINTER(Field), vp, up, up, up, C.c_uint, vp]),

@@ -208,8 +208,13 @@ struct TapDev {
   double c;
 };
 
+__device__ __forceinline__ double pointwise(double x, int op, double c) {
+  return op == BK_OP_MAX ? fmax(x, c) : op == BK_OP_MIN ? fmin(x, c) : op == BK_OP_ABS ? fabs(x) : x;
+}
+
 template <int R>
-__global__ void __launch_bounds__(256) k_taps(Select sel, bk_field_t f, const TapDev *__restrict__ taps, int ntaps) {
+__global__ void __launch_bounds__(256) k_taps(Select sel, bk_field_t f, const TapDev *__restrict__ taps, int ntaps,
+                                              bk_pointwise_t pre, bk_pointwise_t post) {
   constexpr int W = 8 + 2 * R;
   __shared__ double box[W * W * W];
   __shared__ unsigned nb[27];
@@ -221,7 +226,9 @@ __global__ void __launch_bounds__(256) k_taps(Select sel, bk_field_t f, const Ta
   for (int idx = threadIdx.x; idx < W * W * W; idx += 256) {
     const int x = idx % W, y = (idx / W) % W, z = idx / (W * W);
     const int gx = x + 8 - R, gy = y + 8 - R, gz = z + 8 - R;
-    box[idx] = f.in[(size_t) nb[(gz >> 3) * 9 + (gy >> 3) * 3 + (gx >> 3)] * f.in_step + ((gz & 7) << 6) + ((gy & 7) << 3) + (gx & 7)];
+    box[idx] = pointwise(
+        f.in[(size_t) nb[(gz >> 3) * 9 + (gy >> 3) * 3 + (gx >> 3)] * f.in_step + ((gz & 7) << 6) + ((gy & 7) << 3) + (gx & 7)],
+        pre.op, pre.c);
   }
   __syncthreads();
   const int e0 = threadIdx.x, e1 = threadIdx.x + 256;
@@ -233,8 +240,8 @@ __global__ void __launch_bounds__(256) k_taps(Select sel, bk_field_t f, const Ta
     a0 = fma(tp.c, c0[tp.off], a0);
     a1 = fma(tp.c, c1[tp.off], a1);
   }
-  f.out[(size_t) b * f.out_step + e0] = a0;
-  f.out[(size_t) b * f.out_step + e1] = a1;
+  f.out[(size_t) b * f.out_step + e0] = pointwise(a0, post.op, post.c);
+  f.out[(size_t) b * f.out_step + e1] = pointwise(a1, post.op, post.c);
 }
 
 int check_box(const unsigned *gdims, const unsigned *lo, const unsigned *hi) {
@@ -364,12 +371,21 @@ struct bk_stencil_def {
   bk::CoefSpec spec;        // kind STAR / CUBE
   int krad = 0;             // kernel radius (1, 2 or 4)
   TapDev *taps_dev = nullptr;
+  bk_pointwise_t pre = {BK_OP_NONE, 0.0}, post = {BK_OP_NONE, 0.0};
 };
 
 extern "C" {
 
 int bk_stencil_compile(bk_stencil_def_t **out, const bk_tap_t *taps, int ntaps) {
+  return bk_stencil_compile_pointwise(out, taps, ntaps, nullptr, nullptr);
+}
+
+int bk_stencil_compile_pointwise(bk_stencil_def_t **out, const bk_tap_t *taps, int ntaps, const bk_pointwise_t *pre,
+                                 const bk_pointwise_t *post) {
   BK_REQUIRE(out && taps && ntaps > 0 && ntaps <= 4096, "bad arguments");
+  BK_REQUIRE((!pre || (pre->op >= BK_OP_NONE && pre->op <= BK_OP_ABS)) && (!post || (post->op >= BK_OP_NONE && post->op <= BK_OP_ABS)),
+             "unknown pointwise op");
+  const bool nonlinear = (pre && pre->op != BK_OP_NONE) || (post && post->op != BK_OP_NONE);
   // merge repeated offsets, drop zero coefficients
   std::map<std::array<int, 3>, double> m;
   for (int t = 0; t < ntaps; ++t) m[{taps[t].dk, taps[t].dj, taps[t].di}] += taps[t].c;
@@ -397,7 +413,9 @@ int bk_stencil_compile(bk_stencil_def_t **out, const bk_tap_t *taps, int ntaps) 
     auto it = m.find({dk, dj, di});
     return it == m.end() ? 0.0 : it->second;
   };
-  if (star) {  // any coefficients: the marching kernels take one per tap
+  if (pre) d->pre = *pre;
+  if (post) d->post = *post;
+  if (star && !nonlinear) {  // any coefficients: the marching kernels take one per tap
     d->kind = BK_KIND_STAR;
     d->spec.kind = 0, d->spec.radius = d->krad, d->spec.fused_ok = d->krad <= 2;
     d->spec.sc = bk::StarCoef();
@@ -410,7 +428,7 @@ int bk_stencil_compile(bk_stencil_def_t **out, const bk_tap_t *taps, int ntaps) 
     *out = d;
     return BK_OK;
   }
-  bool sym = radius <= 2;  // c(dx,dy,dz) a function of the sorted (|dx|,|dy|,|dz|) only?
+  bool sym = radius <= 2 && !nonlinear;  // c(dx,dy,dz) a function of the sorted (|dx|,|dy|,|dz|) only?
   if (sym) {
     for (int z = -2; z <= 2 && sym; ++z)
       for (int y = -2; y <= 2 && sym; ++y)
@@ -480,9 +498,9 @@ int bk_stencil_def_advance(const bk_stencil_def_t *d, int steps, const bk_field_
   const dim3 g(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
   if (g.x == 0 || g.y == 0 || g.z == 0) return BK_OK;
   Select sel = {grid, nullptr, nullptr, gdims[0], gdims[1], {lo[0], lo[1], lo[2]}, 0};
-  if (d->krad == 1) k_taps<1><<<g, 256, 0, s>>>(sel, *f, d->taps_dev, d->ntaps);
-  if (d->krad == 2) k_taps<2><<<g, 256, 0, s>>>(sel, *f, d->taps_dev, d->ntaps);
-  if (d->krad == 4) k_taps<4><<<g, 256, 0, s>>>(sel, *f, d->taps_dev, d->ntaps);
+  if (d->krad == 1) k_taps<1><<<g, 256, 0, s>>>(sel, *f, d->taps_dev, d->ntaps, d->pre, d->post);
+  if (d->krad == 2) k_taps<2><<<g, 256, 0, s>>>(sel, *f, d->taps_dev, d->ntaps, d->pre, d->post);
+  if (d->krad == 4) k_taps<4><<<g, 256, 0, s>>>(sel, *f, d->taps_dev, d->ntaps, d->pre, d->post);
   BK_LAUNCHED();
   return BK_OK;
 }

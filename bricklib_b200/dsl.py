@@ -37,8 +37,12 @@ class StencilScript:
 
     def __init__(self, path, out_grid, form):
         self.path, self.out_grid, self.form = path, out_grid, form
-        self.in_grids = sorted({g for g, _ in form.taps})
+        self.in_grids = sorted({k[0] for k in form.taps})
         self.dims = len(next(iter(form.taps))[1]) if form.taps else 0
+        pres = {k[2] for k in form.taps}
+        # pointwise clamps: of every value read (one for the whole stencil) and of the sum
+        self.pre = next(iter(pres)) if len(pres) == 1 else (None if not pres else "mixed")
+        self.post = form.post
         syms = set(form.free.symbols())
         for p in form.taps.values():
             syms.update(p.symbols())
@@ -99,18 +103,22 @@ def _resolver(consts):
 
 
 def lower(name_or_path, consts=None):
-    """-> (taps, script): taps = [((d0, d1, ...), coefficient)] in offset order, d0 = offset along Index(0) = i.
-    Raises LoweringError for non-linear scripts, several input grids or a non-zero grid-free term."""
+    """-> (taps, script): taps = [((d0, d1, ...), coefficient)] in offset order, d0 = offset along Index(0) = i;
+    script.pre / script.post = pointwise clamps (op, constant) of the values read / of the sum, or None:
+        out = post( sum_t c_t * pre( in(. + d_t) ) ).
+    Raises LoweringError for other non-linear scripts, several input grids or a non-zero grid-free term."""
     sc = name_or_path if isinstance(name_or_path, StencilScript) else load_script(name_or_path)
     f = sc.form
     if f.opaque:
         raise LoweringError(f"{sc.path}: not a linear stencil ({f.opaque}); no tap list exists")
     if len(sc.in_grids) != 1:
         raise LoweringError(f"{sc.path}: reads {len(sc.in_grids)} grids; a sweep has one input field")
+    if sc.pre == "mixed":
+        raise LoweringError(f"{sc.path}: some reads are clamped and some are not; a kernel applies ONE clamp to the input")
     look = _resolver(consts)
     if f.free.evaluate(look) != 0.0:
         raise LoweringError(f"{sc.path}: constant term {f.free.evaluate(look)}; kernels compute a pure tap sum")
-    taps = sorted(((offs, p.evaluate(look)) for (_, offs), p in f.taps.items()), key=lambda t: t[0][::-1])
+    taps = sorted(((offs, p.evaluate(look)) for (_, offs, _pre), p in f.taps.items()), key=lambda t: t[0][::-1])
     return taps, sc
 
 
@@ -127,7 +135,12 @@ class CompiledStencil:
         for t, ((di, dj, dk), c) in zip(arr, taps):
             t.di, t.dj, t.dk, t.c = di, dj, dk, c
         h = C.c_void_p()
-        rc = load().bk_stencil_compile(C.byref(h), arr, len(taps))
+        self.pre, self.post = sc.pre, sc.post
+        if sc.pre is None and sc.post is None:
+            rc = load().bk_stencil_compile(C.byref(h), arr, len(taps))
+        else:
+            pw = [_lib.Pointwise(_lib.POINTWISE_OPS[x[0]], x[1]) if x else _lib.Pointwise(0, 0.0) for x in (sc.pre, sc.post)]
+            rc = load().bk_stencil_compile_pointwise(C.byref(h), arr, len(taps), C.byref(pw[0]), C.byref(pw[1]))
         if rc == _lib.BK_EUNSUPPORTED:
             raise LoweringError(f"{sc.path}: {load().bk_last_error().decode()}")
         check(rc)

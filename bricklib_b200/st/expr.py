@@ -58,13 +58,18 @@ class Poly:
 
 
 class Expr:
-    """A stencil expression as a linear form: self.taps[(grid name, offsets)] = Poly, self.free = Poly (grid-free part).
-    `opaque` marks a non-linear sub-expression (why lowering will refuse)."""
+    """A stencil expression as a linear form: self.taps[(grid name, offsets, pre)] = Poly, self.free = Poly (grid-free
+    part).  Two pointwise non-linearities are representable because a kernel can apply them for free:
+      pre  -- a clamp of the VALUE READ, e.g. max(in(i+1,j,k), 0): part of the tap key, ("max", 0.0) / ("min", c) / ("abs", 0.0)
+      post -- a clamp of the WHOLE sum, e.g. If(e > 0, e, -e) = abs(e): self.post, same encoding; nothing may be added
+              to or multiplied with such an expression afterwards.
+    `opaque` marks any other non-linear sub-expression (why lowering will refuse)."""
 
-    def __init__(self, taps=None, free=None, opaque=None):
+    def __init__(self, taps=None, free=None, opaque=None, post=None):
         self.taps = taps or {}
         self.free = free if free is not None else Poly()
         self.opaque = opaque
+        self.post = post
 
     # -- construction helpers
     @staticmethod
@@ -76,10 +81,21 @@ class Expr:
         raise TypeError(f"cannot use {type(x).__name__} in a stencil expression")
 
     def _grid_free(self):
-        return not self.taps and self.opaque is None
+        return not self.taps and self.opaque is None and self.post is None
+
+    def _sealed(self):
+        """an expression with a post-clamp is final: arithmetic on it is no longer of the form clamp(sum of taps)"""
+        return "arithmetic on a clamped sum" if self.post is not None else None
 
     def _scaled(self, p):
-        return Expr({k: v * p for k, v in self.taps.items()}, self.free * p, self.opaque)
+        why = self.opaque or self._sealed()
+        return Expr({k: v * p for k, v in self.taps.items()}, self.free * p, why)
+
+    def same_form(self, o):
+        """structurally the same linear form (used to recognise If(e > 0, e, -e) as abs(e))"""
+        return (self.opaque is None and o.opaque is None and self.post == o.post and
+                {k: v.terms for k, v in self.taps.items() if v.terms} == {k: v.terms for k, v in o.taps.items() if v.terms}
+                and self.free.terms == o.free.terms)
 
     # -- arithmetic
     def __add__(self, o):
@@ -87,7 +103,7 @@ class Expr:
         taps = dict(self.taps)
         for k, v in o.taps.items():
             taps[k] = taps[k] + v if k in taps else v
-        return Expr(taps, self.free + o.free, self.opaque or o.opaque)
+        return Expr(taps, self.free + o.free, self.opaque or o.opaque or self._sealed() or o._sealed())
 
     __radd__ = __add__
 
@@ -102,8 +118,8 @@ class Expr:
 
     def __mul__(self, o):
         o = Expr.lift(o)
-        if self.opaque or o.opaque:
-            return Expr(opaque=self.opaque or o.opaque)
+        if self.opaque or o.opaque or self._sealed() or o._sealed():
+            return Expr(opaque=self.opaque or o.opaque or self._sealed() or o._sealed())
         if o._grid_free():
             return self._scaled(o.free)
         if self._grid_free():
@@ -121,11 +137,18 @@ class Expr:
     def __rtruediv__(self, o):
         return Expr.lift(o) / self
 
-    # comparisons / logic only exist to be fed to If(): they make the result non-linear
-    def _cmp(self, o):
-        return Expr(opaque="comparison")
+    # comparisons only exist to be fed to If()
+    def __gt__(self, o):
+        return Comparison(self, ">", Expr.lift(o))
 
-    __lt__ = __le__ = __gt__ = __ge__ = _cmp
+    def __ge__(self, o):
+        return Comparison(self, ">=", Expr.lift(o))
+
+    def __lt__(self, o):
+        return Comparison(self, "<", Expr.lift(o))
+
+    def __le__(self, o):
+        return Comparison(self, "<=", Expr.lift(o))
 
     def __hash__(self):
         return id(self)
@@ -162,6 +185,26 @@ class Index:
         return Index(self.n, self.offset - int(o))
 
 
+class Comparison:
+    def __init__(self, lhs, op, rhs):
+        self.lhs, self.op, self.rhs = lhs, op, rhs
+
+
+def clamp_whole(e, op, c):
+    """post-clamp of a whole expression: op in max / min / abs"""
+    e = Expr.lift(e)
+    if e.opaque or e.post is not None:
+        return Expr(opaque=e.opaque or "nested clamps")
+    return Expr(dict(e.taps), e.free, None, (op, float(c)))
+
+
 def If(cond, then, otherwise):
-    """conditional expression (stencils/cond.py) -- representable, never linear"""
+    """conditional expression (stencils/cond.py).  The one shape a kernel can take is the absolute value written as a
+    select -- If(e > 0, e, -e) and its mirror images; anything else is non-linear."""
+    then, otherwise = Expr.lift(then), Expr.lift(otherwise)
+    if isinstance(cond, Comparison) and cond.rhs._grid_free() and cond.rhs.free.is_number() and cond.rhs.free.number() == 0:
+        e = cond.lhs
+        pos, neg = (then, otherwise) if cond.op in (">", ">=") else (otherwise, then)
+        if pos.same_form(e) and neg.same_form(-e):
+            return clamp_whole(e, "abs", 0.0)
     return Expr(opaque="If")

@@ -4,9 +4,13 @@ from .expr import Expr, Index, Poly
 
 
 class GridRef(Expr):
-    def __init__(self, grid, offsets):
-        super().__init__({(grid.name, offsets): Poly.const(1.0)})
-        self.grid, self.offsets = grid, offsets
+    def __init__(self, grid, offsets, pre=None):
+        super().__init__({(grid.name, offsets, pre): Poly.const(1.0)})
+        self.grid, self.offsets, self.pre = grid, offsets, pre
+
+    def clamped(self, op, c):
+        """the value read, clamped: max(ref, c) / min(ref, c) / abs(ref)"""
+        return GridRef(self.grid, self.offsets, (op, float(c))) if self.pre is None else None
 
     def assign(self, rhs):
         if any(self.offsets):

@@ -140,6 +140,9 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     return brickAdvance(st->id, fuse, grid_dev, strideb, src, dst, last ? skip_lo : full_lo, last ? skip_hi : full_hi,
                         skip_lo, skip_hi, part, nullptr, stream);
   };
+  // thin k segments for the ghost-dependent layers of the split pass: pays off when ghost ranges cross NVLink and the
+  // radius is <= 2 (N = 8 sweep, profiles/r01c_multi_gpu.md)
+  const int thin = (S.size > 1 && st->radius <= 2) ? BK_PART_THIN : 0;
   auto brick_func = [&]() {
     // every rank's previous sweeps are complete before anyone pulls
     bkCheck(bk_event_record(evDone, nullptr));
@@ -154,8 +157,8 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     bkCheck(bk_event_record(c0, nullptr));
     // pass 0 in two launches over the same tiles: CTAs that read only my own bricks overlap the pull (compute
     // stream), the CTAs that touch the ghost shell follow the pull on the high-priority exchange stream
-    if (pass(0, BK_PART_READY, nullptr)) {
-      pass(0, BK_PART_REST, comm_stream);
+    if (pass(0, BK_PART_READY | thin, nullptr)) {
+      pass(0, BK_PART_REST | thin, comm_stream);
       bkCheck(bk_event_record(evX, comm_stream));
       bkCheck(bk_stream_wait_event(nullptr, evX));
     } else {

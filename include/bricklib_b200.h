@@ -213,6 +213,20 @@ typedef struct bk_stencil_def bk_stencil_def_t;
 #define BK_KIND_CUBE 1
 #define BK_KIND_TAPS 2
 int bk_stencil_compile(bk_stencil_def_t **def, const bk_tap_t *taps_host, int ntaps);
+/* The two non-linearities a stencil script may carry and a kernel applies for free (stencils/cond.py uses both):
+ *     out = post( sum_t c_t * pre( in(. + d_t) ) )
+ * pre clamps every value read (cond.py: max(in, 0.0)), post clamps the sum (cond.py: If(calc > 0, calc, -calc) = abs).
+ * NULL or op BK_OP_NONE = identity.  Such stencils always run on the per-brick tap-table kernel (BK_KIND_TAPS). */
+#define BK_OP_NONE 0
+#define BK_OP_MAX 1 /* max(x, c) */
+#define BK_OP_MIN 2 /* min(x, c) */
+#define BK_OP_ABS 3 /* |x| */
+typedef struct {
+  int op;
+  double c;
+} bk_pointwise_t;
+int bk_stencil_compile_pointwise(bk_stencil_def_t **def, const bk_tap_t *taps_host, int ntaps, const bk_pointwise_t *pre,
+                                 const bk_pointwise_t *post);
 int bk_stencil_def_destroy(bk_stencil_def_t *def);
 /* any out pointer may be NULL; st_iter = 8 / radius (sweeps per exchange at ghost depth 8); fused_steps as bk_stencil_fused_steps */
 int bk_stencil_def_info(const bk_stencil_def_t *def, int *kind, int *radius, int *ntaps, int *st_iter, int *fused_steps);

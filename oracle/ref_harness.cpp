@@ -18,6 +18,7 @@
 #include <bricksetup.h>
 #include <brickcompare.h>
 #include <omp.h>
+#include <algorithm>
 #include <vector>
 #include <cstdint>
 
@@ -89,6 +90,18 @@ void sweep_mpi125pt(Brick3D &in, Brick3D &out, const unsigned *grid, const long 
       for (long ti = lo[0]; ti < hi[0]; ++ti) {
         unsigned b = grid[(tk * sb[1] + tj) * sb[0] + ti];
         brick("/root/reference/stencils/mpi125pt.py", VSVEC, (8, 8, 8), (VFOLD), b);
+      }
+}
+
+/* stencils/cond.py: coeff[t] * max(in, 0.0) summed, then If(calc > 0, calc, -calc); its generated code calls max() */
+using std::max;
+void sweep_cond(Brick3D &bIn, Brick3D &bOut, const unsigned *grid, const long *sb, const long *lo, const long *hi) {
+#pragma omp parallel for collapse(2)
+  for (long tk = lo[2]; tk < hi[2]; ++tk)
+    for (long tj = lo[1]; tj < hi[1]; ++tj)
+      for (long ti = lo[0]; ti < hi[0]; ++ti) {
+        unsigned b = grid[(tk * sb[1] + tj) * sb[0] + ti];
+        brick("/root/reference/stencils/cond.py", VSVEC, (8, 8, 8), (VFOLD), b);
       }
 }
 
@@ -209,7 +222,7 @@ int ref_compare_brick(const long *dimlist, const long *padding, const long *ghos
 }
 
 /* ---- one sweep of the generated brick code over the brick box [lo,hi) of `grid` ----------------------------- */
-/* stencil: 0 7pt.py (coeff[7]), 1 mpi7pt, 2 mpi13pt, 3 mpi25pt, 4 mpi125pt */
+/* stencil: 0 7pt.py (coeff[7]), 1 mpi7pt, 2 mpi13pt, 3 mpi25pt, 4 mpi125pt, 5 cond.py (coeff[7]) */
 int ref_sweep_brick(int stencil, const unsigned *grid, const long *sb, const long *lo, const long *hi, unsigned *adj,
                     unsigned nbricks, double *dat_in, size_t step_in, unsigned off_in, double *dat_out,
                     size_t step_out, unsigned off_out, const double *cf) {
@@ -224,6 +237,7 @@ int ref_sweep_brick(int stencil, const unsigned *grid, const long *sb, const lon
     case 2: sweep_mpi13pt(in, out, grid, sb, lo, hi); break;
     case 3: sweep_mpi25pt(in, out, grid, sb, lo, hi); break;
     case 4: sweep_mpi125pt(in, out, grid, sb, lo, hi); break;
+    case 5: sweep_cond(in, out, grid, sb, lo, hi); break; /* cond.py (coeff[7]) */
     default: rc = -1;
   }
   iv.info.adj = nullptr;

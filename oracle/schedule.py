@@ -162,14 +162,24 @@ def weak_run(backend, stencil, dom, cart, periods, fields, skip_last=False):
     return backend.unload(0)
 
 
-def taps_sweep(arr, taps, lo, hi):
-    """The meaning of a lowered stencil script, in numpy: out[k,j,i] = sum_t c_t * arr[k+dk_t, j+dj_t, i+di_t] for
-    lo <= (i,j,k) < hi, zero elsewhere (what codegen/vecscatter's generated loop nest computes for a linear
-    stencils/*.py expression).  taps = [((di, dj, dk), c)], summed in the given order."""
+def _pointwise(x, pw):
+    if not pw:
+        return x
+    op, c = pw
+    return {"max": lambda: np.maximum(x, c), "min": lambda: np.minimum(x, c), "abs": lambda: np.abs(x)}[op]()
+
+
+def taps_sweep(arr, taps, lo, hi, pre=None, post=None):
+    """The meaning of a lowered stencil script, in numpy:
+        out[k,j,i] = post( sum_t c_t * pre( arr[k+dk_t, j+dj_t, i+di_t] ) )   for lo <= (i,j,k) < hi, zero elsewhere
+    (what codegen/vecscatter's generated loop nest computes for a stencils/*.py expression; pre / post = the pointwise
+    clamps of stencils/cond.py, ("max", c) / ("min", c) / ("abs", 0), pinned against the reference's generated cond.py
+    code in tests/test_oracle_pin.py).  taps = [((di, dj, dk), c)], summed in the given order."""
     out = np.zeros_like(arr)
     (i0, j0, k0), (i1, j1, k1) = lo, hi
+    src = _pointwise(arr, pre)
     acc = np.zeros((k1 - k0, j1 - j0, i1 - i0))
     for (di, dj, dk), c in taps:
-        acc += c * arr[k0 + dk:k1 + dk, j0 + dj:j1 + dj, i0 + di:i1 + di]
-    out[k0:k1, j0:j1, i0:i1] = acc
+        acc += c * src[k0 + dk:k1 + dk, j0 + dj:j1 + dj, i0 + di:i1 + di]
+    out[k0:k1, j0:j1, i0:i1] = _pointwise(acc, post)
     return out

@@ -52,13 +52,22 @@ def test_reference_scripts_run_unmodified_on_this_dsl():
     consts = {"coeff": COEFF7}
     for name, g in golden().items():
         path = os.path.join(REF_STENCILS, name)
-        if not g["linear"]:
-            with pytest.raises(dsl.LoweringError):
-                dsl.lower(path, consts)
-            continue
         taps, sc = dsl.lower(path, consts)
-        assert sc.dims == g["dims"]
+        if not g["linear"]:      # cond.py: the reference's AST is not a plain sum; here it lowers with its two clamps
+            assert name == "cond.py" and (sc.pre, sc.post) == (("max", 0.0), ("abs", 0.0))
+            assert dict(taps) == dict(dsl.lower("7pt", consts)[0])
+            continue
+        assert sc.dims == g["dims"] and sc.pre is None and sc.post is None
         assert dict(taps) == golden_taps(g, consts), name
+
+
+def test_cond_script_lowers_to_taps_with_two_pointwise_clamps():
+    """stencils/cond.py: coeff[t] * max(in, 0.0) summed, then If(calc > 0, calc, -calc)"""
+    consts = {"coeff": [0.5, -0.1, 0.2, -0.3, 0.4, 0.05, -0.6]}
+    taps, sc = dsl.lower("cond", consts)
+    assert (sc.pre, sc.post) == (("max", 0.0), ("abs", 0.0))
+    assert dict(taps) == {(0, 0, 0): 0.5, (1, 0, 0): -0.1, (-1, 0, 0): 0.2, (0, 1, 0): -0.3, (0, -1, 0): 0.4,
+                          (0, 0, 1): 0.05, (0, 0, -1): -0.6}
 
 
 def test_linear_form_algebra():
@@ -81,8 +90,10 @@ def test_nonlinear_and_malformed_scripts_are_refused(tmp_path):
            "i, j, k = Index(0), Index(1), Index(2)\na, b = Grid('a', 3), Grid('b', 3)\n"
     cases = {
         "square": "b(i, j, k).assign(a(i, j, k) * a(i + 1, j, k))\nSTENCIL = [b]\n",
-        "call": "b(i, j, k).assign(Func('max', 2)(a(i, j, k), 0.0))\nSTENCIL = [b]\n",
-        "cond": "b(i, j, k).assign(If(a(i, j, k) > 0, a(i, j, k), -a(i, j, k)))\nSTENCIL = [b]\n",
+        "call": "b(i, j, k).assign(Func('sqrt', 1)(a(i, j, k)))\nSTENCIL = [b]\n",
+        "select": "b(i, j, k).assign(If(a(i, j, k) > 0, a(i, j, k), 2 * a(i, j, k)))\nSTENCIL = [b]\n",
+        "mixed_clamps": "b(i, j, k).assign(Func('max', 2)(a(i, j, k), 0.0) + a(i + 1, j, k))\nSTENCIL = [b]\n",
+        "clamp_then_add": "b(i, j, k).assign(Func('fabs', 1)(a(i, j, k) + a(i + 1, j, k)) + a(i, j, k))\nSTENCIL = [b]\n",
         "constant": "b(i, j, k).assign(a(i, j, k) + 1.0)\nSTENCIL = [b]\n",
         "two_inputs": "c = Grid('c', 3)\nb(i, j, k).assign(a(i, j, k) + c(i, j, k))\nSTENCIL = [b]\n",
         "unassigned": "STENCIL = [b]\n",
@@ -147,6 +158,25 @@ def test_compiled_stencils_against_the_oracle(script, consts, kind, radius):
     got = run_compiled(cs, arr, n)
     for label, res in got.items():
         assert rel(res[o:-o, o:-o, o:-o], want[o:-o, o:-o, o:-o]) < 1e-12, label
+
+
+@pytest.mark.gpu
+def test_compiled_cond_stencil_against_the_reference_fixture():
+    """stencils/cond.py on the GPU against one sweep of the reference's own generated code (tests/golden/cond_sweep.npz,
+    oracle/gen_golden_cond.py), and against the numpy restatement on a larger field"""
+    from oracle import schedule as S
+    z = np.load(os.path.join(ROOT, "tests", "golden", "cond_sweep.npz"))
+    cs = bk.compile_stencil("cond", {"coeff": z["coeff"]})
+    assert cs.kind == "taps" and cs.pre == ("max", 0.0) and cs.post == ("abs", 0.0)
+    o = PAD + GZ
+    got = run_compiled(cs, z["input"], (16, 16, 16))
+    for label, res in got.items():
+        assert np.abs(res[o:-o, o:-o, o:-o] - z["out"]).max() < 1e-14, label
+    n = (40, 24, 32)
+    arr = np.random.default_rng(23).random(tuple(x + 2 * (PAD + GZ) for x in n[::-1])) * 2 - 1
+    want = S.taps_sweep(arr, cs.taps, (o, o, o), tuple(o + x for x in n), cs.pre, cs.post)
+    for label, res in run_compiled(cs, arr, n).items():
+        assert np.abs(res[o:-o, o:-o, o:-o] - want[o:-o, o:-o, o:-o]).max() < 1e-14, label
 
 
 @pytest.mark.gpu

@@ -150,3 +150,24 @@ def test_port_vs_compiled_reference_weak_loop_mirrored_cart(P):
     b = S.join_global(S.weak_run(S.PortBackend(), 2, dom, cart, 1, fields), cart, dom)
     assert rel(a, b) < TOL
     assert rel(b, S.periodic_steps(2, glob, 4)) < TOL
+
+
+def test_cond_restatement_matches_reference_generated_code(golden_dir):
+    """the numpy meaning of a script with pointwise clamps (oracle/schedule.py: taps_sweep, pre/post) against one sweep
+    of the code the reference's generator emits for stencils/cond.py: committed fixture, and the build itself if present"""
+    z = np.load(os.path.join(golden_dir, "cond_sweep.npz"))
+    taps = [(0, 0, 0), (1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1)]
+    N, o = 16, 16
+    want = S.taps_sweep(z["input"], list(zip(taps, z["coeff"])), (o, o, o), (o + N,) * 3, ("max", 0.0), ("abs", 0.0))
+    assert np.abs(want[o:-o, o:-o, o:-o] - z["out"]).max() < 1e-14
+    R = oracle.ref()
+    if R is None:
+        return
+    NB = (N + 16) // 8
+    grid, adj = R.init_grid((NB, NB, NB))
+    dat = oracle.aligned_zeros(NB ** 3 * 1024)
+    R.copy_to_brick((N + 16,) * 3, (8,) * 3, (0,) * 3, z["input"], grid, adj, dat, 1024, 0)
+    R.sweep_brick(5, grid, (1, 1, 1), (NB - 1,) * 3, adj, dat, 1024, 0, dat, 1024, 512, z["coeff"])
+    out = np.zeros_like(z["input"])
+    R.copy_from_brick((N,) * 3, (8,) * 3, (8,) * 3, out, grid, adj, dat, 1024, 512)
+    assert np.array_equal(out[o:-o, o:-o, o:-o], z["out"])
