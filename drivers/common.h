@@ -102,6 +102,21 @@ inline void cpu_array_sweep(const std::vector<Tap> &taps, const bElem *in, bElem
       }
 }
 
+/// VALIDATION ONLY: stencils/cond.py on a plain array -- every value read clamped at zero, the sum returned as |sum|
+/// (3axis.cu:229-240 d3cond_arr)
+inline void cpu_array_sweep_cond(const std::vector<Tap> &taps, const bElem *in, bElem *out, const std::vector<long> &stride,
+                                 const long *lo, const long *hi) {
+#pragma omp parallel for collapse(2)
+  for (long k = lo[2]; k < hi[2]; ++k)
+    for (long j = lo[1]; j < hi[1]; ++j)
+      for (long i = lo[0]; i < hi[0]; ++i) {
+        const long p = i + j * stride[1] + k * stride[2];
+        double acc = 0;
+        for (const Tap &t : taps) acc += t.c * std::max(in[p + t.di + t.dj * stride[1] + t.dk * stride[2]], 0.0);
+        out[p] = acc > 0 ? acc : -acc;
+      }
+}
+
 /// U[0,1) doubles, reproducible (the reference seeds from std::random_device, src/multiarray.cpp:13-23)
 inline bElem *randomArray(const std::vector<long> &extent, uint64_t seed = 0x5EED) {
   size_t n = 1;

@@ -5,8 +5,14 @@
 //   -> movBrickInfo / movBrickStorage -> CPU array sweep = golden -> GPU sweeps timed with cutime_func
 //   -> copy back -> compareBrick -> "result match" or std::runtime_error("result mismatch!").
 //
-// usage: single [-n cells_per_axis=512] [-s 7pt|mpi7pt|mpi13pt|mpi25pt|mpi125pt] [-r launches=100]
+// `-s cond` is the reference's second single-GPU case, d3condcu() (stencils/3axis.cu:242-330, stencils/cond.py): the 7-point
+// star with every value read clamped at zero and the sum returned as its absolute value, run through the tap-table
+// kernel (BrickStencilDef + pointwise clamps).  Inputs are shifted to [-0.5,0.5) and two coefficients negated so that both
+// clamps matter (with the reference's all-positive data they never trigger).
+//
+// usage: single [-n cells_per_axis=512] [-s 7pt|mpi7pt|mpi13pt|mpi25pt|mpi125pt|cond] [-r launches=100]
 #include <unistd.h>
+#include <memory>
 #include "common.h"
 
 int main(int argc, char **argv) {
@@ -22,7 +28,9 @@ int main(int argc, char **argv) {
       return c == 'h' ? 0 : 1;
     }
   }
-  const StencilDef *st = find_stencil(sname);
+  static const StencilDef kCond = {"cond", "stencils/cond.py", BK_ST_7PT, 1, 8, 7};
+  const bool cond = sname == "cond";
+  const StencilDef *st = cond ? &kCond : find_stencil(sname);
   if (!st || N % TILE) {
     std::cerr << "unknown stencil or N not a multiple of " << TILE << std::endl;
     return 1;
@@ -36,12 +44,15 @@ int main(int argc, char **argv) {
     std::uniform_real_distribution<bElem> d(0, 1);
     for (auto &x : coeff) x = d(rng);
   }
+  if (cond) coeff[2] = -coeff[2], coeff[5] = -coeff[5];
   bkCheck(bk_set_device(0));
 
   unsigned *grid_ptr;
   BrickInfo<3> bInfo = init_grid<3>(grid_ptr, {STRIDEB, STRIDEB, STRIDEB});
   bElem *in_ptr = randomArray({STRIDE, STRIDE, STRIDE});
   bElem *out_ptr = zeroArray({STRIDE, STRIDE, STRIDE});
+  if (cond)
+    for (long p = 0; p < STRIDE * STRIDE * STRIDE; ++p) in_ptr[p] -= 0.5;
 
   const unsigned bSize = cal_size<BDIM>::value;
   BrickStorage bStorage = bInfo.allocate(bSize * 2);
@@ -59,17 +70,28 @@ int main(int argc, char **argv) {
   const std::vector<Tap> taps = stencil_taps(st->id, coeff.data());
   const long lo[3] = {PADDING + GZ, PADDING + GZ, PADDING + GZ}, hi[3] = {lo[0] + N, lo[1] + N, lo[2] + N};
   const std::vector<long> astride = {1, STRIDE, STRIDE * STRIDE};
-  auto arr_func = [&]() { cpu_array_sweep(taps, in_ptr, out_ptr, astride, lo, hi); };
+  auto arr_func = [&]() {
+    if (cond) cpu_array_sweep_cond(taps, in_ptr, out_ptr, astride, lo, hi);
+    else cpu_array_sweep(taps, in_ptr, out_ptr, astride, lo, hi);
+  };
+  std::unique_ptr<BrickStencilDef> cond_def;  // cond.py lowered to its taps + clamps (what `python -m bricklib_b200.dsl` emits)
+  if (cond) {
+    std::vector<bk_tap_t> ctaps;
+    for (const Tap &t : taps) ctaps.push_back({t.di, t.dj, t.dk, t.c});
+    cond_def.reset(new BrickStencilDef(ctaps, bk_pointwise_t{BK_OP_MAX, 0.0}, bk_pointwise_t{BK_OP_ABS, 0.0}));
+  }
 
   const std::vector<long> gd = {STRIDEB, STRIDEB, STRIDEB}, blo = {GB, GB, GB}, bhi = {NB + GB, NB + GB, NB + GB};
   auto brick_func = [&]() {
-    brickStencil(st->id, grid_dev, gd, bIn_dev, bOut_dev, blo, bhi, coeff.data(), nullptr, BK_KERNEL_BRICK);
+    if (cond) cond_def->launch(grid_dev, gd, bIn_dev, bOut_dev, blo, bhi, nullptr, BK_KERNEL_BRICK);
+    else brickStencil(st->id, grid_dev, gd, bIn_dev, bOut_dev, blo, bhi, coeff.data(), nullptr, BK_KERNEL_BRICK);
   };
   auto brick_func_trans = [&]() {
-    brickStencil(st->id, grid_dev, gd, bIn_dev, bOut_dev, blo, bhi, coeff.data(), nullptr, BK_KERNEL_AUTO);
+    if (cond) cond_def->launch(grid_dev, gd, bIn_dev, bOut_dev, blo, bhi, nullptr, BK_KERNEL_AUTO);
+    else brickStencil(st->id, grid_dev, gd, bIn_dev, bOut_dev, blo, bhi, coeff.data(), nullptr, BK_KERNEL_AUTO);
   };
 
-  std::cout << "d3pt" << st->points << " (" << st->script << ", N = " << N << ")" << std::endl;
+  std::cout << (cond ? "d3cond" : "d3pt") << st->points << " (" << st->script << ", N = " << N << ")" << std::endl;
   std::cout << "Arr: " << time_func(arr_func, 1.0) << " (host, " << omp_get_max_threads() << " threads; the golden)" << std::endl;
   std::cout << "Bri: " << cutime_func(brick_func, std::max(1, reps / 10)) << std::endl;
   const double t = cutime_func(brick_func_trans, reps);

@@ -196,6 +196,11 @@ class BrickStencilDef {
     bkCheck(bk_stencil_def_info(def, &kind, &radius, &ntaps, &st_iter, &fused_steps));
   }
   explicit BrickStencilDef(const std::vector<bk_tap_t> &taps) : BrickStencilDef(taps.data(), (int) taps.size()) {}
+  /// with the pointwise clamps of stencils/cond.py: out = post(sum c * pre(in)), e.g. pre = {BK_OP_MAX, 0.0}, post = {BK_OP_ABS, 0}
+  BrickStencilDef(const std::vector<bk_tap_t> &taps, bk_pointwise_t pre, bk_pointwise_t post) {
+    bkCheck(bk_stencil_compile_pointwise(&def, taps.data(), (int) taps.size(), &pre, &post));
+    bkCheck(bk_stencil_def_info(def, &kind, &radius, &ntaps, &st_iter, &fused_steps));
+  }
   BrickStencilDef(const BrickStencilDef &) = delete;
   ~BrickStencilDef() { bk_stencil_def_destroy(def); }
   template <typename T>

@@ -364,7 +364,7 @@ def _run_driver(*args):
     return r.stdout
 
 
-@pytest.mark.parametrize("name", ["7pt", "mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt"])
+@pytest.mark.parametrize("name", ["7pt", "mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt", "cond"])
 def test_cpp_single_driver_prints_result_match(name):
     out = _run_driver("single", "-n", "64", "-s", name, "-r", "3")
     assert "result match" in out and "Trans:" in out
