@@ -319,6 +319,37 @@ class StitchedGrid:
         return lo, hi
 
 
+def section_owner(sub_id, allsubs, size):
+    """(rank, index inside the rank) of a Z-Morton id -- inverse of section_range (strong/args.cpp:47-55)"""
+    shift, length = allsubs % size, allsubs // size
+    split = shift * ((allsubs + size - 1) // size)
+    if sub_id < split:
+        return sub_id // (length + 1), sub_id % (length + 1)
+    return (sub_id - shift) // length, (sub_id - shift) % length
+
+
+def strong_pull_plan(decomp, rank, size, subdim, stitched=None):
+    """The strong-scaling exchange of one rank as pure host data (what drivers/strong.cpp feeds bk_xplan_create):
+    one (owner rank, owner subdomain index, source brick, my subdomain index, destination brick, bricks) per ghost region
+    -- ghost[i] of my subdomain <- skin[i] of the subdomain in direction ghost[i].neighbor, periodic in the Z-Morton
+    arrangement (strong/args.cpp:36-56, strong/main.cu:188-247).  With a StitchedGrid only the regions on the surface of
+    my box are kept (bk_stitch_region_needed)."""
+    allsubs = subdim ** 3
+    lo, hi = section_range(rank, allsubs, size)
+    plan = []
+    for q in range(hi - lo):
+        c = zmort_decode(lo + q)
+        for i, (g, sk) in enumerate(zip(decomp.ghost, decomp.skin)):
+            if stitched is not None and not stitched.region_needed(lo + q, i):
+                continue
+            s = int(g.neighbor)
+            nb = tuple((c[a] + subdim + (1 if (s >> (a + 1)) & 1 else -1 if (s >> (31 + a + 1)) & 1 else 0)) % subdim
+                       for a in range(3))
+            owner, sub = section_owner(zmort_encode(nb), allsubs, size)
+            plan.append((owner, sub, sk.pos, q, g.pos, g.len))
+    return plan
+
+
 class ExchangeView:
     """One fused pull of every ghost region of a storage: ghost[i] <- peer_base[rank_map[ghost[i].neighbor]] skin[i].
 

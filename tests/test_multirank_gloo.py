@@ -104,6 +104,100 @@ def test_plan_and_rank_map_across_processes(cart, stencil):
     assert isinstance(err, float) and err < 1e-12, err
 
 
+def _strong_rank_main(rank, world, port, dom, subdim, stencil, periods, q):
+    """strong scaling, stitched: every process owns a Z-Morton section of subdomains, builds ITS stitched grid and pull
+    plan through the C ABI (bk_stitch_*, bricklib_b200.strong_pull_plan) and runs the period schedule of
+    drivers/strong.cpp -- exchange of the box-surface regions, then ST_ITER sweeps over the stitched grid, the shell swept
+    only where it is real ghost storage -- with the oracle as the sweep and gloo as the transport"""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import itertools
+    import torch
+    import torch.distributed as dist
+    import bricklib_b200 as bk
+    import oracle
+    from oracle import schedule as S
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        dec = bk.BrickDecomp(dom, 8)
+        nb, B = dec.nbricks, tuple(t - 2 for t in dec.tdims)
+        lo, hi = bk.section_range(rank, subdim ** 3, world)
+        nsub = hi - lo
+        sg = bk.StitchedGrid(dec, lo, nsub, subdim)
+        assert sg.is_box
+        plan = bk.strong_pull_plan(dec, rank, world, subdim, sg)
+        # adjacency of the stitched grid, from the positions that are swept (an aliased shell entry repeats an interior id)
+        g = sg.grid
+        adj = np.zeros((nsub * nb, 27), dtype=np.uint32)
+        slo, shi = sg.sweep_box()
+        for K, J, I in itertools.product(range(slo[2], shi[2]), range(slo[1], shi[1]), range(slo[0], shi[0])):
+            for dk, dj, di in itertools.product((-1, 0, 1), repeat=3):
+                k, j, i = K + dk, J + dj, I + di
+                inside = 0 <= k < g.shape[0] and 0 <= j < g.shape[1] and 0 <= i < g.shape[2]
+                adj[g[K, J, I], (dk + 1) * 9 + (dj + 1) * 3 + (di + 1)] = g[k, j, i] if inside else 0
+        # field: the global periodic array, my subdomains' interiors loaded brick by brick
+        P = oracle.port()
+        G = tuple(subdim * n for n in dom)
+        glob = np.random.default_rng(7).random(G[::-1])
+        store = [oracle.aligned_zeros(nsub * nb * 512), oracle.aligned_zeros(nsub * nb * 512)]
+        ext = tuple(n + 16 for n in dom)
+        for qi in range(nsub):
+            c = bk.zmort_decode(lo + qi)
+            arr = np.zeros(tuple(n + 32 for n in dom[::-1]))
+            arr[16:-16, 16:-16, 16:-16] = glob[c[2] * dom[2]:(c[2] + 1) * dom[2], c[1] * dom[1]:(c[1] + 1) * dom[1],
+                                               c[0] * dom[0]:(c[0] + 1) * dom[0]]
+            P.copy_brick(0, ext, (8,) * 3, (0,) * 3, arr, dec.grid, store[0][qi * nb * 512:(qi + 1) * nb * 512], 512)
+        it = oracle.ST_ITER[stencil]
+        sizes = [None] * world
+        dist.all_gather_object(sizes, nsub * nb * 512)
+        for _ in range(periods):
+            pub = [torch.empty(n, dtype=torch.float64) for n in sizes]
+            dist.all_gather(pub, torch.from_numpy(store[0].copy()))
+            for owner, sub, spos, qi, gpos, n in plan:
+                store[0][(qi * nb + gpos) * 512:(qi * nb + gpos + n) * 512] = \
+                    pub[owner].numpy()[(sub * nb + spos) * 512:(sub * nb + spos + n) * 512]
+            for s_ in range(it):
+                blo, bhi = sg.sweep_box(last=s_ == it - 1)
+                P.sweep_brick(stencil, g, blo, bhi, adj, store[s_ % 2], 512, 0, store[1 - s_ % 2], 512, 0)
+        worst = 0.0
+        want = S.periodic_steps(stencil, glob, it * periods)
+        for qi in range(nsub):
+            c = bk.zmort_decode(lo + qi)
+            out = np.zeros(tuple(n + 32 for n in dom[::-1]))
+            P.copy_brick(1, dom, (8,) * 3, (8,) * 3, out, dec.grid, store[0][qi * nb * 512:(qi + 1) * nb * 512], 512)
+            got = out[16:-16, 16:-16, 16:-16]
+            ref = want[c[2] * dom[2]:(c[2] + 1) * dom[2], c[1] * dom[1]:(c[1] + 1) * dom[1], c[0] * dom[0]:(c[0] + 1) * dom[0]]
+            worst = max(worst, float((np.abs(got - ref) / (np.abs(got) + np.abs(ref))).max()))
+        errs = [None] * world
+        dist.all_gather_object(errs, worst)
+        if rank == 0:
+            q.put(max(errs))
+    except Exception as exc:
+        if rank == 0:
+            q.put(repr(exc))
+        raise
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("world,stencil", [(2, 1), (4, 2), (2, 4)])
+def test_stitched_strong_schedule_across_processes(world, stencil):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_strong_rank_main, args=(r, world, port, (16, 16, 16), 2, stencil, 2, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
+    err = q.get(timeout=5)
+    assert isinstance(err, float) and err < 1e-12, err
+
+
 def test_reference_arm_only_rank0_prints(tmp_path):
     """bench.py --impl reference under torchrun: ranks != 0 exit 0 without work or output"""
     import subprocess

@@ -100,3 +100,64 @@ def test_sweep_boxes_and_errors():
         sg.region_needed(40, 0)
     odd = bk.StitchedGrid(d, 0, 22, 4)          # 3 ranks: not a box
     assert not odd.is_box and odd.grid is None
+
+
+def _simulate_exchange(dom, subdim, size, stitched):
+    """every rank's storage holds, per brick, the code of the GLOBAL brick position whose data it carries (-1 = none);
+    apply every rank's pull plan as plain range copies, as k_xplan does"""
+    d = bk.BrickDecomp(dom, 8)
+    nb, B = d.nbricks, tuple(t - 2 for t in d.tdims)
+    G = tuple(subdim * b for b in B)
+    stores, grids = [], []
+    for rank in range(size):
+        lo, hi = bk.section_range(rank, subdim ** 3, size)
+        st = np.full((hi - lo) * nb, -1, dtype=np.int64)
+        for q in range(hi - lo):
+            c = bk.zmort_decode(lo + q)
+            for bk_, bj, bi in itertools.product(range(B[2]), range(B[1]), range(B[0])):
+                code = (c[0] * B[0] + bi) + G[0] * ((c[1] * B[1] + bj) + G[1] * (c[2] * B[2] + bk_))
+                st[q * nb + d.grid[1 + bk_, 1 + bj, 1 + bi]] = code
+        stores.append(st)
+        grids.append(bk.StitchedGrid(d, lo, hi - lo, subdim) if stitched else None)
+    before = [s.copy() for s in stores]
+    moved = 0
+    for rank in range(size):
+        for owner, sub, spos, q, gpos, n in bk.strong_pull_plan(d, rank, size, subdim, grids[rank]):
+            stores[rank][q * nb + gpos:q * nb + gpos + n] = before[owner][sub * nb + spos:sub * nb + spos + n]
+            moved += n
+    return d, B, G, stores, grids, moved
+
+
+@pytest.mark.parametrize("dom,subdim,size", [((16, 16, 16), 2, 1), ((16, 16, 16), 4, 2), ((16, 24, 32), 2, 8),
+                                             ((16, 16, 16), 4, 8), ((24, 16, 16), 4, 4)])
+def test_stitched_exchange_delivers_what_the_grid_names(dom, subdim, size):
+    """after one exchange of the kept regions, EVERY entry of every rank's stitched grid -- interior, real shell, aliased
+    shell -- carries the data of the periodic global position it stands for"""
+    d, B, G, stores, grids, moved = _simulate_exchange(dom, subdim, size, stitched=True)
+    for rank, sg in enumerate(grids):
+        g = sg.grid
+        for K, J, I in itertools.product(*[range(s) for s in g.shape]):
+            pos = [(sg.lo[a] * B[a] + p - 1) % G[a] for a, p in enumerate((I, J, K))]
+            want = pos[0] + G[0] * (pos[1] + G[1] * pos[2])
+            assert stores[rank][g[K, J, I]] == want, (rank, (I, J, K))
+    _, _, _, _, _, moved_all = _simulate_exchange(dom, subdim, size, stitched=False)
+    assert moved < moved_all or size == subdim ** 3     # stitching exchanges the box surface only
+
+
+@pytest.mark.parametrize("dom,subdim,size", [((16, 16, 16), 2, 1), ((16, 16, 16), 2, 3), ((16, 24, 32), 2, 8)])
+def test_per_subdomain_exchange_fills_every_ghost_brick(dom, subdim, size):
+    """the unstitched plan (drivers/strong -M): every ghost brick of every subdomain receives the periodic neighbour's data"""
+    d, B, G, stores, _, _ = _simulate_exchange(dom, subdim, size, stitched=False)
+    nb = d.nbricks
+    for rank in range(size):
+        lo, hi = bk.section_range(rank, subdim ** 3, size)
+        for q in range(hi - lo):
+            c = bk.zmort_decode(lo + q)
+            for lk, lj, li in itertools.product(*[range(t) for t in d.tdims[::-1]]):
+                pos = [(c[a] * B[a] + p - 1) % G[a] for a, p in enumerate((li, lj, lk))]
+                want = pos[0] + G[0] * (pos[1] + G[1] * pos[2])
+                assert stores[rank][q * nb + d.grid[lk, lj, li]] == want
+    for sub_id in range(subdim ** 3):
+        r, idx = bk.section_owner(sub_id, subdim ** 3, size)
+        lo, hi = bk.section_range(r, subdim ** 3, size)
+        assert lo + idx == sub_id and idx < hi - lo
