@@ -203,3 +203,49 @@ def test_compiled_reference_stencils_equal_the_builtin_ids(name):
         cs.advance(2, grid, b_in, b_b)
         bk.device_sync()
         assert np.array_equal(s_a.to_host(), s_b.to_host())
+
+
+# ---- property test: random linear expressions in varied surface syntax lower to the expected taps --------------------
+from hypothesis import given, settings, strategies as hst  # noqa: E402
+
+_off = hst.integers(min_value=-3, max_value=3)
+_term = hst.tuples(_off, _off, _off, hst.integers(min_value=-8, max_value=8).filter(lambda v: v != 0),
+                   hst.sampled_from(["c*u", "u*c", "neg", "div", "sym", "sub"]))
+
+
+def _shift(name, d):
+    return name if d == 0 else f"{name} {'+' if d > 0 else '-'} {abs(d)}"
+
+
+@settings(max_examples=40, deadline=None)
+@given(hst.lists(_term, min_size=1, max_size=10))
+def test_random_linear_expressions_lower_to_their_taps(tmp_path_factory, terms):
+    want = {}
+    pieces = []
+    for di, dj, dk, num, form in terms:
+        ref = f"u({_shift('i', di)}, {_shift('j', dj)}, {_shift('k', dk)})"
+        c = num / 4.0
+        if form == "c*u":
+            pieces.append(f"+ {c!r} * {ref}")
+        elif form == "u*c":
+            pieces.append(f"+ {ref} * {c!r}")
+        elif form == "neg":
+            pieces.append(f"+ (-({(-c)!r} * {ref}))")
+        elif form == "div":
+            pieces.append(f"+ {ref} / {(1.0 / c)!r}")
+            c = 1.0 / (1.0 / c)
+        elif form == "sym":          # a named constant times a literal
+            pieces.append(f"+ S * {ref} * {num}")
+            c = 0.25 * num
+        else:                        # subtraction of a scaled reference
+            pieces.append(f"- {(-c)!r} * {ref}")
+        want[(di, dj, dk)] = want.get((di, dj, dk), 0.0) + c
+    body = ("from st.expr import Index, ConstRef\nfrom st.grid import Grid\ni, j, k = Index(0), Index(1), Index(2)\n"
+            "u, v = Grid('u', 3), Grid('v', 3)\nS = ConstRef('S')\nrhs = 0 " + " ".join(pieces) +
+            "\nv(i, j, k).assign(rhs)\nSTENCIL = [v]\n")
+    path = tmp_path_factory.mktemp("dsl") / "random_stencil.py"
+    path.write_text(body)
+    taps, sc = dsl.lower(str(path), {"S": 0.25})
+    got = dict(taps)
+    for key in set(want) | set(got):
+        assert abs(got.get(key, 0.0) - want.get(key, 0.0)) < 1e-12, (key, body)
