@@ -324,6 +324,30 @@ def strong_leg():
     return out
 
 
+def single_leg():
+    """BASELINE.json configs[0]: the single-GPU 7-point case of single/cuda.cpp (coeff[] stencil, in/out interleaved in one
+    storage, step 1024), through the C++ single driver: kernel-only sweep rate + the host array sweep it validates against"""
+    exe = os.path.join(ROOT, "drivers", "single")
+    try:
+        r = subprocess.run([exe, "-n", "512", "-s", "7pt", "-r", "50"], capture_output=True, text=True, timeout=180)
+        out = {"what": "drivers/single -n 512 -s 7pt -r 50 (one sweep per launch, interleaved storage)"}
+        for ln in r.stdout.splitlines():
+            f = ln.split()
+            if ln.startswith("perf "):
+                out["GStencil/s"], out["GB/s_algorithmic"] = float(f[1]), float(f[3])
+            elif ln.startswith("Trans:"):
+                out["sweep_ms"] = float(f[1]) * 1e3
+            elif ln.startswith("Arr:"):
+                out["host_array_sweep_s"] = float(f[1])
+            elif ln.startswith("result"):
+                out["validation"] = ln.strip()
+        if "GStencil/s" not in out:
+            out["error"] = (r.stdout + r.stderr)[-200:]
+        return out
+    except Exception as exc:
+        return {"error": str(exc)[:200]}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -451,7 +475,18 @@ def main():
                             "GFLOP/s": (2 * bk.load().bk_stencil_points(sid) - 1) * pts * ks / k2 / 1e9}
         d.stencil, d.st_iter = st, it
         others["strong_512_in_64_subdomains"] = strong_leg()
+        others["single_7pt_512"] = single_leg()
         line["others"] = others
+        # the five BASELINE.json configs, as measured in THIS run (one GPU's share of the multi-GPU ones)
+        line["baseline_configs"] = {
+            "configs[0] single 7pt 512^3": others["single_7pt_512"].get("GStencil/s"),
+            "configs[1] single-GPU 125pt 512^3": others.get("mpi125pt", {}).get("GStencil/s"),
+            "configs[2] weak 7pt / 13pt 512^3 per GPU": [value, others.get("mpi13pt", {}).get("GStencil/s")],
+            "configs[3] weak 25pt 512^3 per GPU": others.get("mpi25pt", {}).get("GStencil/s"),
+            "configs[4] strong 64^3 subdomains, one GPU's 512^3 share": others["strong_512_in_64_subdomains"].get(
+                "stitched", {}).get("GStencil/s"),
+            "unit": "GStencil/s at N=1; N=2/4/8: rerun with --gpus N (--stencil ...), drivers/strong -g 8",
+        }
         e2e_s, bi, bo = e2e_periods(bk, [d, make_domain()], 8)
         line["e2e"] = {"value": pts * it / e2e_s / 1e9, "unit": "GStencil/s", "h2d_bytes_per_step": bi,
                        "d2h_bytes_per_step": bo, "ms_per_step": e2e_s * 1e3,
