@@ -9,6 +9,7 @@
 // PULL exchange -- no pack, no unpack, no staging buffer.  The optional flags implement the cross-process handshake.
 #include "bk_common.h"
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <vector>
 
@@ -18,8 +19,11 @@ struct bk_xplan {
   int nseg = 0;
   unsigned long long nchunks = 0;
   size_t bytes = 0;
-  uint64_t **flagbuf_dev = nullptr;  // scratch for flag pointer lists (64 wait + 64 signal)
-  unsigned long long *done_dev = nullptr;  // CTAs that finished, summed over all launches of this plan
+  // scratch for flag pointer lists (64 wait + epoch + 64 signal): kFlagSlots of them, used round-robin, so that runs of
+  // one plan enqueued on different streams (or back to back) never share a list that is still being read
+  uint64_t **flagbuf_dev = nullptr;
+  std::atomic<unsigned> flag_turn{0};
+  unsigned *done_dev = nullptr;  // CTAs of the running gated launch that have finished; wraps to 0 with the last one
   int shape_ctas = 0, shape_threads = 0;   // bk_xplan_set_shape: 0 = default (many 256-thread CTAs)
   // copy-engine transport (bk_xplan_run_ce): the segments as host data, dealt largest-first to a few lanes
   std::vector<bk_seg_t> segs_host;
@@ -39,6 +43,7 @@ namespace {
 constexpr unsigned kChunkBytes = 16384;
 constexpr size_t kCeMinBytes = 1u << 20;  // copy-engine transport: smaller segments are cheaper through the kernel
 constexpr int kThreads = 256;
+constexpr int kFlagSlots = 16, kFlagSlotLen = 192;
 
 __device__ __forceinline__ void spin_until(const uint64_t *flag, uint64_t value) {
   const volatile uint64_t *f = flag;
@@ -51,7 +56,7 @@ __device__ __forceinline__ void spin_until(const uint64_t *flag, uint64_t value)
 __global__ void __launch_bounds__(1024) k_xplan(const bk_seg_t *__restrict__ segs,
                                                 const unsigned long long *__restrict__ first, int nseg,
                                                 unsigned long long nchunks, uint64_t *const *wait_flags, int nwait,
-                                                int nsignal, uint64_t *gate, unsigned long long *done) {
+                                                int nsignal, uint64_t *gate, unsigned *done) {
   if (nwait > 0) {
     if ((int) threadIdx.x < nwait) spin_until(wait_flags[threadIdx.x], (uint64_t) (size_t) wait_flags[64]);
     __syncthreads();
@@ -85,7 +90,8 @@ __global__ void __launch_bounds__(1024) k_xplan(const bk_seg_t *__restrict__ seg
     __shared__ bool last;
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) last = ((atomicAdd(done, 1ull) + 1ull) % gridDim.x) == 0ull;
+    // self-resetting counter (atomicInc wraps to 0 at gridDim.x - 1): correct whatever grid the previous launch used
+    if (threadIdx.x == 0) last = atomicInc(done, gridDim.x - 1) == gridDim.x - 1;
     __syncthreads();
     if (last) {
       const uint64_t epoch = (uint64_t) (size_t) wait_flags[64];
@@ -120,6 +126,8 @@ int sm_count() {
   }
   return n;
 }
+
+uint64_t **flag_slot(bk_xplan *p) { return p->flagbuf_dev + (size_t) (p->flag_turn++ % kFlagSlots) * kFlagSlotLen; }
 
 int launch_copy(bk_xplan *p, uint64_t *const *wait_dev, int nwait, cudaStream_t s, int nsignal = 0,
                 uint64_t *gate = nullptr, bool publish = false) {
@@ -164,9 +172,9 @@ int bk_xplan_create(bk_xplan_t **out, const bk_seg_t *segs, int nseg) {
   }
   BK_CUDA(cudaMalloc(&p->chunk_first_dev, sizeof(unsigned long long) * (nseg + 1)));
   BK_CUDA(cudaMemcpy(p->chunk_first_dev, first.data(), sizeof(unsigned long long) * (nseg + 1), cudaMemcpyHostToDevice));
-  BK_CUDA(cudaMalloc(&p->flagbuf_dev, sizeof(uint64_t *) * 192));
-  BK_CUDA(cudaMalloc(&p->done_dev, sizeof(unsigned long long)));
-  BK_CUDA(cudaMemset(p->done_dev, 0, sizeof(unsigned long long)));
+  BK_CUDA(cudaMalloc(&p->flagbuf_dev, sizeof(uint64_t *) * kFlagSlots * kFlagSlotLen));
+  BK_CUDA(cudaMalloc(&p->done_dev, sizeof(unsigned)));
+  BK_CUDA(cudaMemset(p->done_dev, 0, sizeof(unsigned)));
   *out = p;
   return BK_OK;
 }
@@ -214,11 +222,12 @@ int bk_xplan_run_sync(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwai
   for (int i = 0; i < nwait; ++i) host[i] = const_cast<uint64_t *>(wait_flags[i]);
   host[64] = (uint64_t *) (size_t) epoch;
   for (int i = 0; i < nsignal; ++i) host[65 + i] = signal_flags[i];
-  BK_CUDA(cudaMemcpyAsync(p->flagbuf_dev, host, sizeof(host), cudaMemcpyHostToDevice, s));
-  int rc = launch_copy(p, p->flagbuf_dev, nwait, s);
+  uint64_t **fb = flag_slot(p);
+  BK_CUDA(cudaMemcpyAsync(fb, host, sizeof(host), cudaMemcpyHostToDevice, s));
+  int rc = launch_copy(p, fb, nwait, s);
   if (rc != BK_OK) return rc;
   if (nsignal > 0) {
-    k_signal<<<1, 64, 0, s>>>(p->flagbuf_dev + 65, nsignal, epoch);
+    k_signal<<<1, 64, 0, s>>>(fb + 65, nsignal, epoch);
     BK_LAUNCHED();
   }
   return BK_OK;
@@ -233,8 +242,9 @@ int bk_xplan_run_gate(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwai
   for (int i = 0; i < nwait; ++i) host[i] = const_cast<uint64_t *>(wait_flags[i]);
   host[64] = (uint64_t *) (size_t) epoch;
   for (int i = 0; i < nsignal; ++i) host[65 + i] = signal_flags[i];
-  BK_CUDA(cudaMemcpyAsync(p->flagbuf_dev, host, sizeof(host), cudaMemcpyHostToDevice, s));
-  return launch_copy(p, p->flagbuf_dev, nwait, s, nsignal, gate, true);
+  uint64_t **fb = flag_slot(p);
+  BK_CUDA(cudaMemcpyAsync(fb, host, sizeof(host), cudaMemcpyHostToDevice, s));
+  return launch_copy(p, fb, nwait, s, nsignal, gate, true);
 }
 
 // The same plan with the big segments on the COPY ENGINES: no SM is taken from the sweep kernels, which matters because
@@ -290,12 +300,12 @@ int bk_xplan_run_ce(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwait,
   for (int i = 0; i < nwait; ++i) host[i] = const_cast<uint64_t *>(wait_flags[i]);
   host[64] = (uint64_t *) (size_t) epoch;
   for (int i = 0; i < nsignal; ++i) host[65 + i] = signal_flags[i];
-  if (nwait > 0 || nsignal > 0)
-    BK_CUDA(cudaMemcpyAsync(p->flagbuf_dev, host, sizeof(host), cudaMemcpyHostToDevice, s));
+  uint64_t **fb = flag_slot(p);
+  if (nwait > 0 || nsignal > 0) BK_CUDA(cudaMemcpyAsync(fb, host, sizeof(host), cudaMemcpyHostToDevice, s));
   if (p->small_nchunks > 0 || nwait > 0) {
     const unsigned grid = (unsigned) std::max(1ull, std::min(p->small_nchunks, 32ull));
     k_xplan<<<grid, kThreads, 0, s>>>(p->small_segs_dev, p->small_first_dev, p->small_nseg, p->small_nchunks,
-                                      p->flagbuf_dev, nwait, 0, nullptr, nullptr);
+                                      fb, nwait, 0, nullptr, nullptr);
     BK_LAUNCHED();
   }
   if (!p->order.empty()) {
@@ -315,7 +325,7 @@ int bk_xplan_run_ce(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwait,
       }
   }
   if (nsignal > 0) {
-    k_signal<<<1, 64, 0, s>>>(p->flagbuf_dev + 65, nsignal, epoch);
+    k_signal<<<1, 64, 0, s>>>(fb + 65, nsignal, epoch);
     BK_LAUNCHED();
   }
   return BK_OK;

@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <type_traits>
 #include <algorithm>
+#include <atomic>
 #include <functional>
 #include <map>
 #include <mutex>
@@ -538,8 +539,10 @@ __global__ void __launch_bounds__(C::NT) __maxnreg__(C::MAXREG) k_star_capped(co
 // register scatter along k.  The intermediate field never touches HBM: 16 B of traffic per point per TWO steps.
 // Semantics = bk_stencil_apply over the whole grid followed by bk_stencil_apply over [lo,hi): the intermediate is
 // computed at every in-grid cell the second step reads and is zero outside the grid (the null brick).
-template <int R_, int YT_, int TI_, int TJ_, int D_, int NPW_, int MINB_ = 1, int CREG_ = 0, int PREG_ = 40, bool LAG_ = false>
+template <int R_, int YT_, int TI_, int TJ_, int D_, int NPW_, int MINB_ = 1, int CREG_ = 0, int PREG_ = 40, bool LAG_ = false,
+          bool EW_ = false>
 struct FCfg {
+  static constexpr bool EW = EW_;                      // wait for the next input plane BEFORE stage B (no spin loop between B(n) and A(n+1))
   static constexpr bool LAG = LAG_;                    // stage B runs one plane behind stage A (independent work between barriers)
   static constexpr int MINB = MINB_;                   // CTAs per SM the register allocation must allow
   static constexpr int CREG = CREG_, PREG = PREG_;     // setmaxnreg re-balancing as in Cfg (0 = off)
@@ -559,7 +562,7 @@ struct FCfg {
   static constexpr size_t SMEM = (size_t) (D + M) * STAGE + 2 * D * 8 + 128;
   static constexpr int OVH = 2 * H + 3;                // cost-model overhead planes per segment
   [[maybe_unused]] static constexpr int MAXREG = 255;
-  static_assert(NSTRIP <= NCONS && 8 % YT == 0 && TI % 2 == 0 && 2 * H <= 8, "geometry");
+  static_assert(NSTRIP <= NCONS && 8 % YT == 0 && TI % 2 == 0 && 2 * H <= 8 && !(EW && LAG), "geometry");
   static_assert(CREG == 0 || (NCW % 4 == 0 && NPW % 4 == 0 && NCONS * CREG + 32 * NPW * PREG <= 65536), "setmaxnreg");
   __host__ __device__ static constexpr int slotoff(int bi, int bj) { return (bj * SW + bi) * SLOTP; }
   // byte offset of the cell at tile-relative (X,Y), X in [-8, 8TI+8), Y in [-H, 8TJ+H): rows below/above the tile live in
@@ -879,7 +882,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_star2(const __grid_constant_
         if (C::LAG && n - 1 >= H) stage_b(n - 1, mprev, u % W);  // (n - 1 - H) mod W with H = W - 1
         // ---- stage A: input plane n-H completes intermediate plane n-H-R ------------------------------------------
         if (n < P) {
-          mbar_wait(bar_full + 8 * st, ph);
+          if (!C::EW || n == 0) mbar_wait(bar_full + 8 * st, ph);
           const unsigned char *pbA = ring + st * C::STAGE;
           unsigned char *pm = mid + msl * C::STAGE;
           const int zm = zabs0 + n - H - R;
@@ -927,6 +930,9 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_star2(const __grid_constant_
         if (n < P) {
           if (tid == 0) mbar_arrive(bar_empty + 8 * st);
           if (++st == D) st = 0, ph ^= 1;
+          // early wait: the next plane's data is awaited here, so that stage B of this plane and stage A of the next one
+          // form one straight-line block whose shared-memory latencies overlap
+          if (C::EW && n + 1 < P) mbar_wait(bar_full + 8 * st, ph);
           if (!C::LAG && n >= H) stage_b(n, msl, (u + 1) % W);  // (n - H) mod W
         }
         mprev = msl;
@@ -1013,13 +1019,15 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, 
   // k segments: every CTA streams kl*8 + 2*RUP planes and the launch takes ceil(CTAs / resident slots) rounds, so pick
   // the segment count that minimises rounds * planes (long segments amortise the halo planes, short ones fill the
   // last round)
-  static int slots = 0;
+  static std::atomic<int> slots_cached{0};  // several rank threads (drivers/*) may get here at once: benign double init
+  int slots = slots_cached.load(std::memory_order_relaxed);
   if (!slots) {
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NT, C::SMEM);
     slots = sms * (per_sm > 0 ? per_sm : 1);
+    slots_cached.store(slots, std::memory_order_relaxed);
   }
   // split launches: the layers whose CTAs read not-yet-ready bricks get thin segments of their own, so that the READY
   // part (which overlaps the exchange) is as large as possible
@@ -1124,6 +1132,9 @@ int launch_tiled(const CoefSpec &spec, const bk_field_t &f, const bk_field_t *mu
       if (v == 2) return launch_cfg<FCfg<1, 2, 4, 4, 3, 2, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
       if (v == 3) return launch_cfg<FCfg<1, 4, 8, 4, 4, 4, 1, 0, 40, true>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
       if (v == 4) return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2, 0, 40, true>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+      if (v == 5) return launch_cfg<FCfg<1, 4, 4, 4, 4, 2, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);                    // deeper ring
+      if (v == 6) return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2, 0, 40, false, true>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);  // early wait
+      if (v == 7) return launch_cfg<FCfg<1, 4, 4, 4, 4, 2, 2, 0, 40, false, true>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);  // both
       return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
     }
     if (r == 2) return launch_cfg<FCfg<2, 2, 4, 4, 4, 4>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
@@ -1138,7 +1149,18 @@ int launch_tiled(const CoefSpec &spec, const bk_field_t &f, const bk_field_t *mu
     return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 128, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
   }
   if (v == 1) return launch_cfg<Cfg<4, 2, 4, 4, 2, 5, 255, 4>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+  if (v == 5) return launch_cfg<Cfg<4, 2, 6, 4, 2, 3, 255, 4, false, 152, 40>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
   if (v == 2) return launch_cfg<Cfg<4, 4, 8, 4, 2, 4, 255, 4, false, 232, 40>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+  if (v == 3) return launch_cfg<Cfg<4, 4, 6, 4, 2, 4, 232, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+  if (v == 4) return launch_cfg<Cfg<4, 4, 6, 4, 2, 3, 232, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+  // radius 4 has two tuned shapes with the same cost per (padded) brick column (profiles/r02_kernels.md): 6x4-brick
+  // tiles with 2 rows per thread, and 8x4-brick tiles with 4 rows per thread (56 instead of 72 B of LDS per point).  The
+  // box decides: whichever pads it less wins (64 bricks: 8x4 exact vs 66 for 6x4; 66 bricks: 6x4 exact vs 72).
+  if (v == 0) {
+    const long nx = a.hi[0] - a.lo[0], ny = a.hi[1] - a.lo[1];
+    const long pad64 = ((nx + 5) / 6) * 6 * ((ny + 3) / 4) * 4, pad84 = ((nx + 7) / 8) * 8 * ((ny + 3) / 4) * 4;
+    if (pad84 <= pad64) return launch_cfg<Cfg<4, 4, 8, 4, 2, 4, 255, 4, false, 232, 40>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+  }
   return launch_cfg<Cfg<4, 2, 6, 4, 2, 3, 255, 4, false, 152, 40>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
 }
 

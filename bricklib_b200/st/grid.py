@@ -23,8 +23,6 @@ class Grid:
         self.name, self.dims, self.out = str(src_name), int(dims), None
 
     def __call__(self, *indices):
-        if self.out is not None:      # a grid that has been assigned reads as its defining expression
-            return self.out[1]
         if len(indices) != self.dims:
             raise ValueError("Index list not consistent with dimensions")
         offs = [0] * self.dims
@@ -34,4 +32,17 @@ class Grid:
             if ix.n != pos:
                 raise ValueError("transposed index order is not supported: argument %d uses Index(%d)" % (pos, ix.n))
             offs[pos] = ix.offset
+        if self.out is not None:      # a grid that has been assigned reads as its defining expression ...
+            e = self.out[1]
+            if not any(offs):
+                return e
+            # ... moved to the point it is read at: tmp(i+1,j,k) shifts every tap of tmp's definition by (+1,0,0)
+            if e.post is not None:
+                return Expr(opaque="shifted read of a clamped sum")
+            taps = {}
+            for (name, o, pre), poly in e.taps.items():
+                if len(o) != len(offs):
+                    return Expr(opaque="shifted read across grids of different rank")
+                taps[(name, tuple(a + b for a, b in zip(o, offs)), pre)] = poly
+            return Expr(taps, e.free, e.opaque)
         return GridRef(self, tuple(offs))

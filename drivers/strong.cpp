@@ -183,7 +183,7 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
       segs.push_back(sg);
       if (dst != rank) {
         remote_bytes += sg.bytes, peers_mask |= 1ull << dst;
-        if (dst % ndev != dev) bk_peer_enable(dst % ndev);
+        if (dst % ndev != dev) bkCheck(bk_peer_enable(dst % ndev));  // no P2P between the two GPUs: fail here, not in the pull kernel
       }
     }
   ExchangeView ev(segs);

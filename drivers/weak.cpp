@@ -117,7 +117,7 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
   S.storage_ptr[rank] = bStorage_dev.dat.get();
   bar.wait();
   for (auto &kv : bDecomp.rank_map)
-    if (kv.second % ndev != dev) bk_peer_enable(kv.second % ndev);  // idempotent
+    if (kv.second % ndev != dev) bkCheck(bk_peer_enable(kv.second % ndev));  // idempotent; throws without P2P
   ExchangeView ev = bDecomp.exchangeView(bStorage_dev, S.storage_ptr);
 
   void *comm_stream, *evDone, *evX, *c0, *c1, *x0, *x1;

@@ -79,6 +79,23 @@ def test_linear_form_algebra():
         dsl.lower(os.path.join(HERE, "upwind.py"))          # W unbound
 
 
+def test_read_of_an_assigned_grid_is_shifted_to_the_point_it_is_read_at(tmp_path):
+    """tmp(i+1,j,k) after tmp(...).assign(...) = tmp's definition moved by (+1,0,0) (reference: codegen/st/grid.py inlines
+    the producer at the shifted index)"""
+    head = "from st.expr import Index, ConstRef\nfrom st.grid import Grid\n" \
+           "i, j, k = Index(0), Index(1), Index(2)\na, t, b = Grid('a', 3), Grid('t', 3), Grid('b', 3)\n"
+    p = tmp_path / "two_stage.py"
+    p.write_text(head + "t(i, j, k).assign(a(i + 1, j, k) - a(i - 1, j, k))\n"
+                        "b(i, j, k).assign(0.5 * t(i + 1, j, k) + 0.25 * t(i, j - 2, k) + t(i, j, k))\nSTENCIL = [b]\n")
+    taps, sc = dsl.lower(str(p))
+    assert dict(taps) == {(2, 0, 0): 0.5, (0, 0, 0): -0.5, (1, -2, 0): 0.25, (-1, -2, 0): -0.25, (1, 0, 0): 1.0,
+                          (-1, 0, 0): -1.0}
+    q = tmp_path / "bad_arity.py"
+    q.write_text(head + "t(i, j, k).assign(a(i, j, k))\nb(i, j, k).assign(t(i, j))\nSTENCIL = [b]\n")
+    with pytest.raises(ValueError):
+        dsl.lower(str(q))
+
+
 def test_c_table_emission_for_cxx_callers():
     src = dsl.emit_c("mpi13pt", "mpi13")
     assert "static const bk_tap_t mpi13[] = {" in src and "mpi13_count = 13" in src
