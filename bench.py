@@ -19,8 +19,19 @@ import sys
 import threading
 import time
 
-# bind OpenMP threads of the CPU reference leg -- only where a single process runs it
-if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+# OpenMP set-up of the CPU legs, BEFORE libgomp loads.  The reference arm runs on rank 0 alone with every host core:
+# torchrun exports OMP_NUM_THREADS=1 to its workers, which would time the reference on ONE thread (round-1 ADVICE).
+def _host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+if "reference" in sys.argv[1:]:
+    os.environ["OMP_NUM_THREADS"] = str(_host_cores())
+    os.environ["OMP_PROC_BIND"] = "close"
+elif int(os.environ.get("WORLD_SIZE", "1")) == 1:
     os.environ.setdefault("OMP_PROC_BIND", "close")
 
 import numpy as np  # noqa: E402
@@ -121,17 +132,19 @@ class ClockSampler:
 
 
 def dist_setup(n_gpus):
-    """one process per GPU under torchrun; returns (rank, world, torch.distributed or None)"""
+    """one process per GPU under torchrun; returns (rank, world, torch.distributed or None, host-side gloo group)"""
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world == 1:
-        return 0, 1, None
+        return 0, 1, None, None
     import torch
     import torch.distributed as dist
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    return rank, world, dist
+    # a host-side barrier (no kernel on any GPU) for the legs that rank 0 runs through a driver binary on ALL GPUs
+    host_group = dist.new_group(backend="gloo")
+    return rank, world, dist, host_group
 
 
 def max_over_ranks(dist, value):
@@ -140,6 +153,15 @@ def max_over_ranks(dist, value):
     import torch
     t = torch.tensor([value], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(dist, value):
+    if dist is None:
+        return value
+    import torch
+    t = torch.tensor([value], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
     return float(t.item())
 
 
@@ -176,8 +198,7 @@ def wire_peers(bk, dom_obj, dist, rank, world):
 
 
 def time_periods(bk, d, steps, warmup, dist):
-    """W warm-up periods, then K timed periods between barriers; returns (seconds max over ranks, sweep seconds, launches)"""
-    L = bk.load()
+    """W warm-up periods, then K timed periods between barriers; returns (seconds max over ranks, launches)"""
     for _ in range(warmup):
         d.period()
     bk.device_sync()
@@ -221,77 +242,171 @@ def time_sweeps(bk, d, reps):
 
 
 def roofline_of(pts, launch_s, steps, peak, peak_src, traffic):
-    """HBM roofline of one launch of the sweep kernel.  A launch reads and writes every interior point once whatever
-    the number of time steps it fuses, so its compulsory traffic is 16 B x points; the single-sweep algorithmic figure
-    of SURVEY 8(d) (16 B per point PER STEP) is reported next to it as `frac_of_single_sweep_roofline`."""
-    achieved = 16.0 * pts / launch_s / 1e9
+    """HBM roofline of one launch of the dominant sweep kernel, in SURVEY 8(d)'s unit: 16 algorithmic bytes per point per
+    TIME STEP x the point-steps one launch processes (points x steps fused in the launch) / its CUDA-event duration.
+    For the two-steps-per-pass kernel `frac` can exceed 1: the kernel moves each byte through HBM once per TWO steps
+    (temporal blocking), which no one-sweep-per-pass kernel can do; `hbm_frac` is the physical view of the same launch
+    (16 B x points actually read+written / duration / peak), and `traffic` the DRAM bytes ncu counted for it."""
+    achieved = 16.0 * pts * steps / launch_s / 1e9
+    physical = 16.0 * pts / launch_s / 1e9
     kern = "k_star2 (two time steps per pass)" if steps == 2 else "k_star (one sweep)"
     return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "kernel": f"{kern}: one launch = 512^3 interior points x 16 B compulsory, {steps} step(s)",
+            "traffic": traffic, "kernel": f"{kern}: one launch = {pts} interior points x {steps} step(s) x 16 B",
             "kernel_ms": launch_s * 1e3, "steps_per_launch": steps, "peak_source": peak_src,
             "GStencil/s_kernel": pts * steps / launch_s / 1e9,
-            "frac_of_single_sweep_roofline": 16.0 * pts * steps / launch_s / 1e9 / peak}
+            "hbm_GB/s": physical, "hbm_frac": physical / peak,
+            "note": "frac = algorithmic bytes (16 B per point per step, SURVEY 8d) / time / measured copy peak; "
+                    "hbm_frac = compulsory bytes that cross HBM (16 B per point per LAUNCH) / time / peak"}
+
+
+# ---- parity inside the bench: what was timed is also checked ---------------------------------------------------------
+PARITY_TOL = 1e-12
+PARITY_SEED = 0xB200
+
+
+def sampled_parity(bk, d, box_bricks=4):
+    """One exchange period of the CURRENT stencil on the position-addressable synthetic field, then four sampled boxes of
+    this rank's interior (low corner, high corner, centre, one edge: every kind of ghost dependency) against the oracle
+    (the C port's array sweeps on the same global field, evaluated independently from the hash).  The oracle is the
+    checker here, never the thing measured.  Returns (max relative difference, points checked)."""
+    import oracle
+    P = oracle.port()
+    st, it = d.stencil, d.st_iter
+    r = oracle.RADIUS[st]
+    d.fill_synthetic(PARITY_SEED)
+    d.storage[1].dat.zero()
+    bk.device_sync()
+    d.period()
+    bk.device_sync()
+    nb = tuple(x // 8 for x in d.dom)
+    B = tuple(min(box_bricks, n) for n in nb)
+    where = [(0, 0, 0), tuple(n - b for n, b in zip(nb, B)), tuple((n - b) // 2 for n, b in zip(nb, B)),
+             (0, (nb[1] - B[1]) // 2, nb[2] - B[2])]
+    org, glob = d.global_origin(), d.global_cells()
+    worst, pts = 0.0, 0
+    for p in sorted(set(where)):
+        got = d.read_bricks(p, tuple(a + b for a, b in zip(p, B)))
+        lo = tuple(org[a] + 8 * p[a] - 8 for a in range(3))
+        hi = tuple(org[a] + 8 * (p[a] + B[a]) + 8 for a in range(3))
+        cur = bk.synthetic_field(PARITY_SEED, glob, lo, hi)
+        for _ in range(it):    # the halo of 8 cells is exactly what ST_ITER steps of radius 8/ST_ITER consume
+            n = cur.shape
+            cur = P.sweep_array(st, np.ascontiguousarray(cur), (r, r, r), (n[2] - r, n[1] - r, n[0] - r))
+        want = cur[8:-8, 8:-8, 8:-8]
+        worst = max(worst, float((np.abs(got - want) / (np.abs(got) + np.abs(want) + 1e-300)).max()))
+        pts += got.size
+    return worst, pts
+
+
+def fused_vs_two_sweeps(bk, d):
+    """device-side, over the FULL interior: one two-steps-per-pass launch against two plain sweeps of the same input.
+    Returns None when the stencil has no fused kernel in use, else (mismatching cells at 1e-12, max rel diff, points)."""
+    if d.steps_per_pass() != 2:
+        return None
+    t = d.grid.dims
+    lo, hi = (1, 1, 1), tuple(x - 1 for x in t)
+    extra = [d.info.allocate(bk.BRICK), d.info.allocate(bk.BRICK)]
+    fused, plain = bk.Brick(d.info, extra[0], 0), bk.Brick(d.info, extra[1], 0)
+    d.fill_synthetic(PARITY_SEED + 1)
+    bk.stencil_advance(d.stencil, 2, d.grid, d.bricks[0], fused, lo, hi)
+    d._sweep(0, 1, (0, 0, 0), t, None)
+    bk.stencil(d.stencil, d.grid, d.bricks[1], plain, lo, hi, None, d.kernel)
+    ok, bad, rel = bk.compare_storage(d.grid, lo, hi, fused, plain, PARITY_TOL)
+    for e in extra:
+        e.dat.free()
+    return bad, rel, int(np.prod([h - l for l, h in zip(lo, hi)])) * 512
+
+
+def parity_of(bk, d, dist):
+    worst, pts = sampled_parity(bk, d)
+    out = {"max_rel": max_over_ranks(dist, worst), "checked_points": int(sum_over_ranks(dist, pts)), "tolerance": PARITY_TOL,
+           "what": "one exchange period on the synthetic field; 4 sampled 32^3 boxes per rank (corners, centre, edge) vs the "
+                   "oracle's array sweeps of the same global periodic field"}
+    f = fused_vs_two_sweeps(bk, d)
+    if f is not None:
+        out["fused_vs_two_sweeps"] = {"mismatches": int(sum_over_ranks(dist, f[0])), "max_rel": max_over_ranks(dist, f[1]),
+                                      "points": int(sum_over_ranks(dist, f[2])),
+                                      "what": "k_star2 (one launch) vs two k_star sweeps, whole interior, compared on the device"}
+    out["ok"] = bool(out["max_rel"] < PARITY_TOL and out.get("fused_vs_two_sweeps", {}).get("mismatches", 0) == 0)
+    return out
 
 
 def e2e_periods(bk, doms, steps):
     """End to end through the public API with HOST buffers: every step uploads the field's interior bricks from pinned
     host memory (H2D), runs one period (exchange + ST_ITER sweeps) and downloads the result bricks (D2H) -- all inside
-    the timed region.  Steps are independent fields, so two are kept in flight (double buffering on two streams): the
-    upload of step i+1 and the download of step i-1 overlap the sweeps of step i, as a user streaming fields through
-    the GPU would do.  Returns (seconds per step, h2d bytes, d2h bytes)."""
+    the timed region.  Steps are independent fields, so three are kept in flight (one uploading, one computing, one
+    downloading), as a user streaming fields through the GPU would do.  Each slot has its own upload, compute and
+    download stream, so both PCIe directions are busy all the time: the step time is bounded by one direction's copy.  Returns (seconds per step, h2d bytes, d2h bytes)."""
     import ctypes as C
     L = bk.load()
+    ck = bk._lib.check
     d0 = doms[0]
     lo, hi = 1, d0.decomp.sep_pos[1]            # inner + skin bricks = the interior; ghosts come from the exchange
     off, nbytes = lo * 512 * 8, (hi - lo) * 512 * 8
     slots = []
     for d in doms:
-        hin, hout, st = C.c_void_p(), C.c_void_p(), C.c_void_p()
-        bk._lib.check(L.bk_host_alloc(C.byref(hin), nbytes))
-        bk._lib.check(L.bk_host_alloc(C.byref(hout), nbytes))
-        bk._lib.check(L.bk_stream_create(C.byref(st)))
-        bk._lib.check(L.bk_memcpy_d2h(hin, d.storage[0].dat.ptr + off, nbytes, None))
-        slots.append((d, hin, hout, st))
+        hin, hout = C.c_void_p(), C.c_void_p()
+        ck(L.bk_host_alloc(C.byref(hin), nbytes))
+        ck(L.bk_host_alloc(C.byref(hout), nbytes))
+        st = [C.c_void_p() for _ in range(3)]   # upload, compute, download
+        for x in st:
+            ck(L.bk_stream_create(C.byref(x)))
+        ev = [bk.Event() for _ in range(3)]     # uploaded, computed, downloaded
+        ck(L.bk_memcpy_d2h(hin, d.storage[0].dat.ptr + off, nbytes, None))
+        slots.append((d, hin, hout, st, ev))
     bk.device_sync()
 
     def step(i):
-        d, hin, hout, st = slots[i % len(slots)]
-        bk._lib.check(L.bk_memcpy_h2d(d.storage[0].dat.ptr + off, hin, nbytes, st))
-        d.period(st)
-        bk._lib.check(L.bk_memcpy_d2h(hout, d.storage[0].dat.ptr + off, nbytes, st))
+        d, hin, hout, (s_up, s_run, s_down), (e_up, e_run, e_down) = slots[i % len(slots)]
+        ck(L.bk_stream_wait_event(s_up, e_down.h))         # this slot's previous result has left the device
+        ck(L.bk_memcpy_h2d(d.storage[0].dat.ptr + off, hin, nbytes, s_up))
+        e_up.record(s_up)
+        ck(L.bk_stream_wait_event(s_run, e_up.h))
+        d.period(s_run)
+        e_run.record(s_run)
+        ck(L.bk_stream_wait_event(s_down, e_run.h))
+        ck(L.bk_memcpy_d2h(hout, d.storage[0].dat.ptr + off, nbytes, s_down))
+        e_down.record(s_down)
 
+    for _, _, _, _, ev in slots:
+        for e in ev:
+            e.record(None)
+    bk.device_sync()
     for i in range(len(slots)):                 # warm-up: one step per slot
         step(i)
-    for _, _, _, st in slots:
-        bk._lib.check(L.bk_stream_sync(st))
+    bk.device_sync()
     t0 = time.perf_counter()
     for i in range(steps):
         step(i)
-    for _, _, _, st in slots:
-        bk._lib.check(L.bk_stream_sync(st))
+    for _, _, _, st, _ in slots:
+        for x in st:
+            ck(L.bk_stream_sync(x))
     sec = time.perf_counter() - t0
-    for _, hin, hout, st in slots:
+    for _, hin, hout, st, _ in slots:
         L.bk_host_free(hin)
         L.bk_host_free(hout)
-        L.bk_stream_destroy(st)
+        for x in st:
+            L.bk_stream_destroy(x)
     return sec / steps, nbytes, nbytes
 
 
-def reference_period_seconds(stencil_id, size, periods, warm=1):
+def reference_period_seconds(stencil_id, size, periods, warm=1, cart=(1, 1, 1)):
     """the reference's own CPU implementation of the path (oracle/_ref: its BrickDecomp, its exchange() over the
-    in-process MPI stand-in, its generated AVX brick code) on all host threads; else the C port.  Returns
-    (seconds per period, kind, cores, isa)."""
+    in-process MPI stand-in, its generated AVX brick code) on all host threads; else the C port.  `cart` ranks are run
+    in this one process, each with its own subdomain, exchanging through the stand-in -- the whole weak-scaling job on
+    the host's cores.  Returns (seconds per period, kind, cores, isa)."""
     import oracle
     from oracle import schedule as S
     R = oracle.ref()
     if R is not None:
         be, kind, isa, cores = S.RefBackend(), "reference", R.isa, R.threads
     else:
-        be, kind, isa, cores = S.PortBackend(), "port", "scalar-c", os.cpu_count()
+        be, kind, isa, cores = S.PortBackend(), "port", "scalar-c", _host_cores()
     dom = (size,) * 3
-    be.setup(dom, (1, 1, 1))
+    be.setup(dom, tuple(cart))
     rng = np.random.default_rng(0x5EED)
-    be.store[0][0][512:] = rng.random(be.store[0][0].size - 512)
+    for r in range(len(be.store)):
+        be.store[r][0][512:] = rng.random(be.store[r][0].size - 512)
     it = oracle.ST_ITER[stencil_id]
 
     def period():
@@ -307,20 +422,38 @@ def reference_period_seconds(stencil_id, size, periods, warm=1):
     return (time.perf_counter() - t0) / periods, kind, cores, isa
 
 
-def strong_leg():
-    """BASELINE.json configs[4] at one GPU's share (512 subdomains of 64^3 = the per-GPU work of 1024^3 on 8 GPUs):
-    the C++ strong driver, stitched super grid (default) and per-subdomain launches (-M)"""
+def workload_name(stencil, size, it):
+    return f"weak {stencil} {size}^3 per GPU, 8^3 bricks, 1 exchange + {it} sweeps per step"
+
+
+def strong_leg(n):
+    """BASELINE.json configs[4]: 1024^3 global, 64^3 subdomains, Z-Morton sections over n GPUs -- the C++ strong driver
+    on ALL n GPUs (one host thread per GPU), stitched super grid; at n = 1 also one GPU's 1/8 share (512^3) both
+    stitched and with per-subdomain launches (-M, the reference CUDA driver's structure)"""
     exe = os.path.join(ROOT, "drivers", "strong")
     out = {}
-    for label, extra in (("stitched", []), ("per_subdomain", ["-M"])):
+
+    def run(label, args, timeout):
         try:
-            r = subprocess.run([exe, "-d", "512", "-s", "64", "-I", "20", "-g", "1", "-S", "mpi7pt", *extra],
-                               capture_output=True, text=True, timeout=120)
+            env = dict(os.environ, OMP_NUM_THREADS="4")
+            r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=timeout, env=env)
             perf = [ln for ln in r.stdout.splitlines() if ln.startswith("perf ")]
-            out[label] = {"GStencil/s": float(perf[-1].split()[1])} if perf else {"error": (r.stdout + r.stderr)[-200:]}
+            calc = [ln for ln in r.stdout.splitlines() if ln.startswith("calc ")]
+            if perf:
+                out[label] = {"GStencil/s": float(perf[-1].split()[1]), "cmd": "drivers/strong " + " ".join(args)}
+                if calc:
+                    out[label]["calc"] = calc[-1].strip()
+            else:
+                out[label] = {"error": (r.stdout + r.stderr)[-300:]}
         except Exception as exc:
-            out[label] = {"error": str(exc)[:200]}
-    out["what"] = "drivers/strong -d 512 -s 64 -I 20 -g 1 -S mpi7pt (20 exchange periods of 8 steps after 1 warm-up)"
+            out[label] = {"error": str(exc)[:300]}
+
+    run("global_1024_sub_64", ["-d", "1024", "-s", "64", "-I", "10", "-g", str(n), "-S", "mpi7pt"], 600)
+    run("global_1024_sub_64_mpi25pt", ["-d", "1024", "-s", "64", "-I", "10", "-g", str(n), "-S", "mpi25pt"], 600)
+    if n == 1:
+        run("share_512_stitched", ["-d", "512", "-s", "64", "-I", "20", "-g", "1", "-S", "mpi7pt"], 300)
+        run("share_512_per_subdomain", ["-d", "512", "-s", "64", "-I", "20", "-g", "1", "-S", "mpi7pt", "-M"], 300)
+    out["what"] = f"strong scaling: fixed 1024^3 global domain in 64^3 subdomains on {n} GPU(s); 10 exchange periods after 1 warm-up"
     return out
 
 
@@ -349,23 +482,29 @@ def single_leg():
 
 
 def run_reference_arm(args):
+    """the reference's CPU implementation of the SAME workload (N subdomains, periodic process grid) on rank 0 with
+    every host core; the other ranks of a torchrun launch exit without work"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import oracle
     st = oracle.STENCILS[args.stencil]
-    size = args.size
-    sec, kind, cores, isa = reference_period_seconds(st, size, args.steps, max(1, min(args.warmup, 1)))
+    size, n = args.size, args.gpus
+    cart = CART.get(n)
+    if cart is None:
+        raise SystemExit("supported GPU counts: 1, 2, 4, 8")
+    sec, kind, cores, isa = reference_period_seconds(st, size, args.steps, max(1, min(args.warmup, 1)), cart)
     it = oracle.ST_ITER[st]
-    gst = size ** 3 * it / sec / 1e9
+    gst = size ** 3 * it * n / sec / 1e9
     line = {
-        "impl": "reference", "metric": "GStencil/s", "value": gst, "unit": "GStencil/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": "GStencil/s", "value": gst, "unit": "GStencil/s", "n_gpus": n,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"weak {args.stencil} {size}^3 per rank, 8^3 bricks, 1 exchange + {it} sweeps per step",
-                   "ranks": 1, "note": "reference CPU path (OpenMP + generated %s code), single process" % isa},
+        "config": {"workload": workload_name(args.stencil, size, it), "process_grid": "x".join(map(str, cart)),
+                   "note": f"reference CPU path (OpenMP + generated {isa} code): the {n} subdomain(s) of the job run in one "
+                           f"process on {cores} host threads, exchange through its own BrickDecomp::exchange"},
         "cpu_baseline": {"value": gst, "unit": "GStencil/s", "cores": cores, "kind": kind,
-                         "sample": f"{args.steps} periods of {size}^3 after 1 warm-up"},
+                         "sample": f"{args.steps} periods of {n} x {size}^3 after 1 warm-up"},
         "e2e": {"value": gst, "unit": "GStencil/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -381,7 +520,7 @@ def main():
     ap.add_argument("--size", type=int, default=512, help="cells per axis per GPU")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="one sweep per pass (no temporal blocking)")
-    ap.add_argument("--no-extras", action="store_true", help="skip other stencils / e2e / cpu baseline")
+    ap.add_argument("--no-extras", action="store_true", help="skip other stencils / strong / e2e / cpu baseline / parity")
     ap.add_argument("--kernel", default="auto", choices=["auto", "brick", "tiled"])
     ap.add_argument("--transport", default="kernel", choices=["kernel", "ce"],
                     help="ghost exchange as one pull kernel over NVLink peer mappings (default, faster) or on the copy engines")
@@ -397,9 +536,11 @@ def main():
         return
 
     import bricklib_b200 as bk
-    rank, world, dist = dist_setup(args.gpus)
+    rank, world, dist, host_group = dist_setup(args.gpus)
     if world == 1:
         bk._lib.check(bk.load().bk_set_device(0))
+    L = bk.load()
+    L.bk_bind_host_to_device()      # NUMA: pin this process next to its GPU before any pinned allocation (best effort)
     n = world
     cart = CART.get(n)
     if cart is None:
@@ -421,10 +562,8 @@ def main():
         dm.transport, dm.thin = args.transport, {"auto": None, "on": True, "off": False}[args.thin]
         if args.pull_shape:
             dm.set_pull_shape(*[int(x) for x in args.pull_shape.split(",")])
-        rng = np.random.default_rng(0x5EED + rank)
-        host = rng.random(dm.decomp.nbricks * 512)
-        host[:512] = 0.0
-        dm.storage[0].from_host(host)
+        dm.fill_synthetic(0x5EED)          # synthetic U[0,1) field, written on the device
+        bk.device_sync()
         return dm
 
     d = make_domain()
@@ -450,7 +589,7 @@ def main():
         "metric": "GStencil/s", "value": value, "unit": "GStencil/s", "n_gpus": n, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"weak {args.stencil} {size}^3 per GPU, 8^3 bricks, 1 exchange + {it} sweeps per step",
+        "config": {"workload": workload_name(args.stencil, size, it),
                    "process_grid": "x".join(map(str, cart)), "exchange_MB_per_gpu_per_step": d.view.bytes / 1e6,
                    "overlap": not args.no_overlap, "kernel": args.kernel, "thin_split": d._thin(),
                    "exchange_transport": "copy engines (faces) + narrow pull kernel (edges, corners) over NVLink peer mappings"
@@ -460,52 +599,68 @@ def main():
         "roofline": roofline_of(pts, sweep_s, sweep_steps, peak, peak_src, traffic),
         "clocks": clocks,
     }
+    line["roofline"]["traffic_source"] = "ncu --set full capture of this kernel at this size (profiles/traffic.json), per launch"
 
-    if n == 1 and not args.no_extras:
+    if not args.no_extras:
+        # what was timed is also checked: sampled boxes vs the oracle, fused pass vs two sweeps on the device
+        line["parity"] = parity_of(bk, d, dist)
         others = {}
+        k_other = max(3, args.steps // 4)
         for name, sid in bk.STENCILS.items():
             if name in ("7pt", args.stencil):
                 continue
-            d.stencil, d.st_iter = sid, bk.load().bk_stencil_st_iter(sid)
-            s2, _ = time_periods(bk, d, max(3, args.steps // 4), 3, None)
+            d.stencil, d.st_iter = sid, L.bk_stencil_st_iter(sid)
+            d.fill_synthetic(0x5EED)
+            s2, _ = time_periods(bk, d, k_other, 3, dist)
             k2, ks = time_sweeps(bk, d, 10)
-            others[name] = {"GStencil/s": pts * d.st_iter * max(3, args.steps // 4) / s2 / 1e9,
-                            "sweep_ms": k2 * 1e3, "steps_per_launch": ks, "hbm_GB/s": 16.0 * pts / k2 / 1e9,
-                            "frac_of_hbm_peak": 16.0 * pts / k2 / 1e9 / peak,
-                            "GFLOP/s": (2 * bk.load().bk_stencil_points(sid) - 1) * pts * ks / k2 / 1e9}
+            k2 = max_over_ranks(dist, k2)
+            flops = 2 * L.bk_stencil_points(sid) - 1
+            others[name] = {"GStencil/s": pts * d.st_iter * n * k_other / s2 / 1e9, "ms_per_step": s2 / k_other * 1e3,
+                            "sweep_ms": k2 * 1e3, "steps_per_launch": ks, "hbm_GB/s": 16.0 * pts * ks / k2 / 1e9,
+                            "frac_of_hbm_peak": 16.0 * pts * ks / k2 / 1e9 / peak,
+                            "GFLOP/s_nominal": flops * pts * ks / k2 / 1e9,
+                            "flops_note": f"nominal {flops} flop per point (FMA form, SURVEY 8d)" +
+                            ("; the kernel EXECUTES ~50 flop per point (sign/permutation folds: 16 adds + 18 FMA), i.e. "
+                             f"{50 * pts * ks / k2 / 1e12:.1f} TFLOP/s executed" if name == "mpi125pt" else ""),
+                            "parity": parity_of(bk, d, dist)}
         d.stencil, d.st_iter = st, it
-        others["strong_512_in_64_subdomains"] = strong_leg()
-        others["single_7pt_512"] = single_leg()
         line["others"] = others
-        # the five BASELINE.json configs, as measured in THIS run (one GPU's share of the multi-GPU ones)
-        line["baseline_configs"] = {
-            "configs[0] single 7pt 512^3": others["single_7pt_512"].get("GStencil/s"),
-            "configs[1] single-GPU 125pt 512^3": others.get("mpi125pt", {}).get("GStencil/s"),
-            "configs[2] weak 7pt / 13pt 512^3 per GPU": [value, others.get("mpi13pt", {}).get("GStencil/s")],
-            "configs[3] weak 25pt 512^3 per GPU": others.get("mpi25pt", {}).get("GStencil/s"),
-            "configs[4] strong 64^3 subdomains, one GPU's 512^3 share": others["strong_512_in_64_subdomains"].get(
-                "stitched", {}).get("GStencil/s"),
-            "unit": "GStencil/s at N=1; N=2/4/8: rerun with --gpus N (--stencil ...), drivers/strong -g 8",
-        }
-        e2e_s, bi, bo = e2e_periods(bk, [d, make_domain()], 8)
-        line["e2e"] = {"value": pts * it / e2e_s / 1e9, "unit": "GStencil/s", "h2d_bytes_per_step": bi,
-                       "d2h_bytes_per_step": bo, "ms_per_step": e2e_s * 1e3,
-                       "what": "per step: H2D of the interior bricks from pinned host memory, exchange + sweeps, D2H of "
-                               "the result bricks; two independent fields in flight (double buffered on two streams)"}
-        try:
-            cs, kind, cores, isa = reference_period_seconds(st, size, 2, 1)
-            line["cpu_baseline"] = {"value": pts * it / cs / 1e9, "unit": "GStencil/s", "cores": cores, "kind": kind,
-                                    "sample": f"2 periods (exchange + {it} sweeps) of {size}^3 after 1 warm-up, {isa}"}
-        except Exception as exc:  # the checker is optional for the product arm
-            line["cpu_baseline"] = {"value": None, "unit": "GStencil/s", "cores": 0, "kind": "port",
-                                    "sample": f"unavailable: {exc}"}
-    elif n > 1 and not args.no_extras:
-        e2e_s, bi, bo = e2e_periods(bk, [d, make_domain()], 6)
+        # strong scaling (configs[4]) and the single driver (configs[0]): C++ drivers spawned by rank 0 on all N GPUs while
+        # the other ranks wait on a HOST-side barrier (no kernel of theirs is running)
+        bk.device_sync()
+        if dist is not None:
+            dist.barrier(group=host_group)
+        if rank == 0:
+            others["strong"] = strong_leg(n)
+            if n == 1:
+                others["single_7pt_512"] = single_leg()
+        if dist is not None:
+            dist.barrier(group=host_group)
+        if rank == 0:
+            line["baseline_configs"] = {
+                "configs[0] single 7pt 512^3 (N=1 only)": others.get("single_7pt_512", {}).get("GStencil/s"),
+                "configs[1] 125pt 512^3 per GPU": others.get("mpi125pt", {}).get("GStencil/s"),
+                "configs[2] weak 7pt / 13pt 512^3 per GPU": [value, others.get("mpi13pt", {}).get("GStencil/s")],
+                "configs[3] weak 25pt 512^3 per GPU": others.get("mpi25pt", {}).get("GStencil/s"),
+                "configs[4] strong 1024^3 in 64^3 subdomains": others["strong"].get("global_1024_sub_64", {}).get("GStencil/s"),
+                "unit": f"GStencil/s, whole job on {n} GPU(s)",
+            }
+        e2e_s, bi, bo = e2e_periods(bk, [d, make_domain(), make_domain()], 9)
         e2e_s = max_over_ranks(dist, e2e_s)
         line["e2e"] = {"value": pts * it * n / e2e_s / 1e9, "unit": "GStencil/s", "h2d_bytes_per_step": bi * n,
                        "d2h_bytes_per_step": bo * n, "ms_per_step": e2e_s * 1e3,
-                       "what": "per rank and step: H2D of the interior bricks from pinned host memory, exchange + sweeps, "
-                               "D2H of the result bricks; two fields in flight; max over ranks"}
+                       "h2d_GB/s_per_gpu": bi / e2e_s / 1e9, "d2h_GB/s_per_gpu": bo / e2e_s / 1e9,
+                       "what": "per rank and step: H2D of the interior bricks from pinned host memory, exchange + sweeps, D2H "
+                               "of the result bricks; three independent fields in flight, upload / compute / download on "
+                               "separate streams; max over ranks"}
+        if n == 1:
+            try:
+                cs, kind, cores, isa = reference_period_seconds(st, size, 2, 1)
+                line["cpu_baseline"] = {"value": pts * it / cs / 1e9, "unit": "GStencil/s", "cores": cores, "kind": kind,
+                                        "sample": f"2 periods (exchange + {it} sweeps) of {size}^3 after 1 warm-up, {isa}"}
+            except Exception as exc:  # the checker is optional for the product arm
+                line["cpu_baseline"] = {"value": None, "unit": "GStencil/s", "cores": 0, "kind": "port",
+                                        "sample": f"unavailable: {exc}"}
 
     if rank == 0:
         print(json.dumps(line))

@@ -8,7 +8,7 @@ from ._lib import (BK_OK, KERNEL_AUTO, KERNEL_BRICK, KERNEL_TILED, PART_ALL, PAR
                    BrickError, load)
 from .core import (BRICK, Brick, BrickDecomp, BrickInfo, BrickStorage, DeviceBuffer, DeviceGrid, Event,  # noqa: F401
                    ExchangeView, StitchedGrid, compareBrick, copyFromBrick, copyToBrick, device_sync, init_grid, stencil,
-                   stencil_advance, stencil_list, stencil_part, section_owner, section_range, strong_pull_plan, zmort_decode, zmort_encode, Unsupported)
+                   stencil_advance, stencil_list, stencil_part, fill_synthetic, synthetic_field, compare_storage, section_owner, section_range, strong_pull_plan, zmort_decode, zmort_encode, Unsupported)
 from .weak import WeakDomain, shell_boxes  # noqa: F401
 
 

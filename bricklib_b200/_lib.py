@@ -60,6 +60,7 @@ SIGNATURES = {
     "bk_stencil_fused_steps": (C.c_int, [C.c_int]),
     "bk_device_count": (C.c_int, [ip]),
     "bk_set_device": (C.c_int, [C.c_int]),
+    "bk_bind_host_to_device": (C.c_int, []),
     "bk_dev_alloc": (C.c_int, [C.POINTER(vp), sz]),
     "bk_dev_free": (C.c_int, [vp]),
     "bk_dev_memset": (C.c_int, [vp, C.c_int, sz, vp]),
@@ -101,6 +102,9 @@ SIGNATURES = {
     "bk_copy_to_brick": (C.c_int, [lp, lp, lp, vp, vp, vp, sz, vp]),
     "bk_copy_from_brick": (C.c_int, [lp, lp, lp, vp, vp, vp, sz, vp]),
     "bk_compare_brick": (C.c_int, [lp, lp, lp, vp, vp, vp, sz, C.c_double, C.POINTER(C.c_ulonglong), dp, vp]),
+    "bk_fill_synthetic": (C.c_int, [vp, up, lp, lp, u64, vp, sz, vp]),
+    "bk_synthetic_value": (C.c_double, [u64, u64]),
+    "bk_compare_storage": (C.c_int, [vp, up, up, up, vp, sz, vp, sz, C.c_double, C.POINTER(C.c_ulonglong), dp, vp]),
     "bk_stencil_apply": (C.c_int, [C.c_int, C.POINTER(Field), vp, up, up, up, dp, C.c_uint, vp]),
     "bk_stencil_apply_part": (C.c_int, [C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp]),
     "bk_stencil_advance": (C.c_int, [C.c_int, C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp]),

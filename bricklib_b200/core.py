@@ -154,6 +154,36 @@ def compareBrick(dimlist, padding, ghost, arr_dev, grid, brick, tol=1e-12, strea
     return bad.value == 0, bad.value, rel.value
 
 
+def fill_synthetic(grid, brick, origin_cells, global_cells, seed, stream=None):
+    """bk_fill_synthetic: every non-null brick of `grid` gets the counter-based synthetic field (a hash of the global
+    periodic cell coordinate); origin_cells = global coordinate of cell 0 of grid position (0,0,0)"""
+    check(load().bk_fill_synthetic(grid.dev.ptr, _u3(grid.dims), _l3(origin_cells), _l3(global_cells), int(seed),
+                                   brick.dat, brick.step, stream))
+
+
+def synthetic_field(seed, global_cells, lo, hi):
+    """the same field on the host (numpy): cells lo <= (i,j,k) < hi of the global periodic array, returned as [k][j][i].
+    Bit-identical to bk_fill_synthetic / bk_synthetic_value (splitmix64 of the linear global cell index)."""
+    ax = [np.mod(np.arange(lo[d], hi[d], dtype=np.int64), int(global_cells[d])).astype(np.uint64) for d in range(3)]
+    g0, g1 = np.uint64(global_cells[0]), np.uint64(global_cells[1])
+    lin = (ax[2][:, None, None] * g1 + ax[1][None, :, None]) * g0 + ax[0][None, None, :]
+    with np.errstate(over="ignore"):
+        z = np.uint64(int(seed) & (2 ** 64 - 1)) + (lin + np.uint64(1)) * np.uint64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+        z = z ^ (z >> np.uint64(31))
+    return (z >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+
+
+def compare_storage(grid, lo, hi, brick_a, brick_b, tol=1e-12, stream=None):
+    """compareBrick between two brick storages over the brick box [lo,hi): (ok, mismatching cells, max relative diff)"""
+    bad = C.c_ulonglong()
+    rel = C.c_double()
+    check(load().bk_compare_storage(grid.dev.ptr, _u3(grid.dims), _u3(lo), _u3(hi), brick_a.dat, brick_a.step,
+                                    brick_b.dat, brick_b.step, tol, C.byref(bad), C.byref(rel), stream))
+    return bad.value == 0, bad.value, rel.value
+
+
 def _field(b_in, b_out):
     assert b_in.info is b_out.info or b_in.info.adj.ptr == b_out.info.adj.ptr
     return Field(b_in.info.adj.ptr, b_in.dat, b_in.step, b_out.dat, b_out.step)

@@ -2,6 +2,8 @@
 // movBrickInfo / movBrickStorage / copyToDevice helpers (include/brick-gpu.h:43-103, stencils/cudaarray.h:11-31),
 // which cudaMalloc + blocking cudaMemcpy with 32-bit sizes; here sizes are size_t and copies are stream-ordered.
 #include "bk_common.h"
+#include <sched.h>
+#include <cctype>
 #include <cstring>
 #include <mutex>
 
@@ -29,6 +31,44 @@ int bk_device_count(int *n) {
 }
 int bk_set_device(int dev) {
   BK_CUDA(cudaSetDevice(dev));
+  return BK_OK;
+}
+// NUMA placement: pinned buffers are first-touch pages, and an 8-GPU box hangs its GPUs off two sockets.  Bind the
+// calling thread (and so the pages it touches next) to the CPUs local to the current device's PCIe root, as listed by
+// /sys/bus/pci/devices/<bus id>/local_cpulist.  Best effort: BK_EUNSUPPORTED when sysfs has no answer; nothing changes.
+int bk_bind_host_to_device(void) {
+  int dev = 0;
+  BK_CUDA(cudaGetDevice(&dev));
+  char bus[32] = "";
+  BK_CUDA(cudaDeviceGetPCIBusId(bus, sizeof(bus), dev));
+  for (char *c = bus; *c; ++c) *c = (char) tolower(*c);
+  char path[128];
+  snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+  FILE *f = fopen(path, "r");
+  if (!f) {
+    bk::set_error("bk_bind_host_to_device: %s is not readable", path);
+    return BK_EUNSUPPORTED;
+  }
+  char list[1024] = "";
+  const bool got = fgets(list, sizeof(list), f) != nullptr;
+  fclose(f);
+  cpu_set_t want, have;
+  CPU_ZERO(&want);
+  int n = 0;
+  for (char *tok = got ? strtok(list, ",\n") : nullptr; tok; tok = strtok(nullptr, ",\n")) {
+    int a = 0, b = 0;
+    if (sscanf(tok, "%d-%d", &a, &b) == 2) {
+    } else if (sscanf(tok, "%d", &a) == 1) {
+      b = a;
+    } else {
+      continue;
+    }
+    for (int c = a; c <= b && c < CPU_SETSIZE; ++c) CPU_SET(c, &want), ++n;
+  }
+  // stay inside the mask we were given (containers, taskset)
+  if (n == 0 || sched_getaffinity(0, sizeof(have), &have) != 0) return BK_EUNSUPPORTED;
+  CPU_AND(&want, &want, &have);
+  if (CPU_COUNT(&want) == 0 || sched_setaffinity(0, sizeof(want), &want) != 0) return BK_EUNSUPPORTED;
   return BK_OK;
 }
 int bk_dev_alloc(void **dev, size_t bytes) {

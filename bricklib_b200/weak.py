@@ -49,6 +49,7 @@ class WeakDomain:
         self.kernel = kernel
         self.rank = rank
         self.cart = tuple(cart)
+        self.coo = tuple(coo)
         self.world = cart[0] * cart[1] * cart[2]
         L = load()
         self.st_iter = L.bk_stencil_st_iter(stencil_id)
@@ -106,6 +107,36 @@ class WeakDomain:
         core.copyToBrick(strideg, (PADDING,) * 3, (0,) * 3, dev, self.grid, self.bricks[0])
         core.device_sync()
         dev.free()
+
+    def global_origin(self):
+        """cell origin (i,j,k) of this subdomain inside the periodic global array.  populate() pairs set element +d with
+        Cartesian coordinate c-1 (brick-mpi.h:740-751), i.e. coordinates run AGAINST the axes; axis d (1=i) <-> coo[3-d]"""
+        return tuple((self.cart[2 - a] - 1 - self.coo[2 - a]) * self.dom[a] for a in range(3))
+
+    def global_cells(self):
+        return tuple(self.cart[2 - a] * self.dom[a] for a in range(3))
+
+    def fill_synthetic(self, seed, which=0, stream=None):
+        """storage[which] <- the position-addressable synthetic field (bk_fill_synthetic), ghost shell included (it holds
+        the periodic neighbours' values, exactly what the first exchange delivers)"""
+        o = self.global_origin()
+        core.fill_synthetic(self.grid, self.bricks[which], tuple(x - GZ for x in o), self.global_cells(), seed, stream)
+
+    def read_bricks(self, lo, hi, which=0):
+        """cells of the INTERIOR brick box [lo,hi) (brick coordinates without the ghost shell) as a [k][j][i] array"""
+        g = GZ // 8
+        n = tuple(h - l for l, h in zip(lo, hi))
+        out = np.empty((n[2] * 8, n[1] * 8, n[0] * 8))
+        one = np.empty(512)
+        L = load()
+        for k in range(n[2]):
+            for j in range(n[1]):
+                for i in range(n[0]):
+                    b = int(self.decomp.grid[lo[2] + g + k, lo[1] + g + j, lo[0] + g + i])
+                    check(L.bk_memcpy_d2h(one.ctypes.data, self.storage[which].brick_ptr(b), 4096, None))
+                    check(L.bk_stream_sync(None))
+                    out[k * 8:k * 8 + 8, j * 8:j * 8 + 8, i * 8:i * 8 + 8] = one.reshape(8, 8, 8)
+        return out
 
     def read_interior(self, which=0):
         ext = tuple(n + 2 * (PADDING + GZ) for n in self.dom[::-1])

@@ -104,7 +104,7 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
   const std::vector<long> strideb = {STRIDEB, STRIDEB, STRIDEB};
   copyToDevice(strideb, grid_dev, bDecomp.gridData());
 
-  {  // inputs: interior cells of every subdomain
+  if (S.validate) {  // inputs: interior cells of every subdomain, cut from the host's global array
     const std::vector<long> astride = {STRIDE, STRIDE, STRIDE};
     bElem *arr_dev = nullptr, *in_ptr = zeroArray(astride);
     copyToDevice(astride, arr_dev, in_ptr);
@@ -112,19 +112,10 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     for (unsigned q = 0; q < nsub; ++q) {
       unsigned long c[3];
       bk_zmort_decode(mysec_l + q, c);
-      if (S.validate) {
-        for (long k = 0; k < s; ++k)
-          for (long j = 0; j < s; ++j)
-            std::memcpy(in_ptr + (PADDING + GZ) + (j + PADDING + GZ) * STRIDE + (k + PADDING + GZ) * STRIDE * STRIDE,
-                        S.global_in + c[0] * s + (c[1] * s + j) * G + (c[2] * s + k) * G * G, s * sizeof(bElem));
-      } else {
-        std::mt19937_64 rng(0x5EED + mysec_l + q);
-        std::uniform_real_distribution<bElem> d(0, 1);
-        for (long k = 0; k < s; ++k)
-          for (long j = 0; j < s; ++j)
-            for (long i = 0; i < s; ++i)
-              in_ptr[(i + PADDING + GZ) + (j + PADDING + GZ) * STRIDE + (k + PADDING + GZ) * STRIDE * STRIDE] = d(rng);
-      }
+      for (long k = 0; k < s; ++k)
+        for (long j = 0; j < s; ++j)
+          std::memcpy(in_ptr + (PADDING + GZ) + (j + PADDING + GZ) * STRIDE + (k + PADDING + GZ) * STRIDE * STRIDE,
+                      S.global_in + c[0] * s + (c[1] * s + j) * G + (c[2] * s + k) * G * G, s * sizeof(bElem));
       bkCheck(bk_memcpy_h2d(arr_dev, in_ptr, (size_t) STRIDE * STRIDE * STRIDE * sizeof(bElem), nullptr));
       BrickStorage view = st0;  // a Brick over subdomain q of field 0
       Brick3D b(&bInfo_dev, view, (unsigned) 0);
@@ -134,6 +125,16 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     }
     bk_dev_free(arr_dev);
     free(in_ptr);
+  } else {  // timing runs: the synthetic field is written straight into the bricks on the device (bk_fill_synthetic)
+    const unsigned gd0[3] = {(unsigned) STRIDEB, (unsigned) STRIDEB, (unsigned) STRIDEB};
+    const long glob[3] = {(long) S.dom_size, (long) S.dom_size, (long) S.dom_size};
+    for (unsigned q = 0; q < nsub; ++q) {
+      unsigned long c[3];
+      bk_zmort_decode(mysec_l + q, c);
+      const long org[3] = {(long) c[0] * s - GZ, (long) c[1] * s - GZ, (long) c[2] * s - GZ};
+      bkCheck(bk_fill_synthetic(grid_dev, gd0, org, glob, 0x5EED, st0.dat.get() + q * sub_elems, bSize, nullptr));
+    }
+    bkCheck(bk_device_sync());
   }
 
   // per-subdomain field descriptors for the two sweep directions

@@ -50,6 +50,9 @@ int bk_stencil_fused_steps(int stencil); /* `steps` of bk_stencil_advance that i
 /* ---- device plumbing (stands in for include/brick-gpu.h:43-103 movBrickInfo/movBrickStorage, cudaarray.h:11-31) - */
 int bk_device_count(int *n);
 int bk_set_device(int dev);
+/* bind the calling host thread to the CPUs local to the current device (NUMA: call before allocating pinned memory);
+ * best effort, BK_EUNSUPPORTED when the platform does not say */
+int bk_bind_host_to_device(void);
 int bk_dev_alloc(void **dev, size_t bytes); /* cudaMalloc: 256-B aligned, exportable with bk_ipc_export */
 int bk_dev_free(void *dev);
 int bk_dev_memset(void *dev, int byte, size_t bytes, void *stream);
@@ -142,6 +145,21 @@ int bk_copy_from_brick(const long *dimlist, const long *padding, const long *gho
 int bk_compare_brick(const long *dimlist, const long *padding, const long *ghost, const double *arr_dev,
                      const unsigned *grid_dev, const double *dat_dev, size_t step, double tol,
                      unsigned long long *mismatches, double *max_rel, void *stream);
+
+/* Synthetic field straight into the bricks (the reference fills host arrays with randomArray, src/multiarray.cpp:33-45,
+ * then copyToBrick): every cell of every non-null brick named by the dense id array `grid_dev` (gdims = bricks per axis,
+ * i first) becomes a counter-based hash of its GLOBAL periodic cell coordinate,
+ *     value = bk_synthetic_value(seed, ((z * global[1] + y) * global[0] + x)),   (x,y,z) = (origin + cell) mod global,
+ * U[0,1) with 53 random bits (splitmix64).  origin_cells = global coordinate of cell 0 of grid position (0,0,0), may be
+ * negative (a ghost shell wraps periodically).  Position-addressable: any rank, and a CPU checker, can evaluate any cell. */
+int bk_fill_synthetic(const unsigned *grid_dev, const unsigned *gdims, const long *origin_cells, const long *global_cells,
+                      uint64_t seed, double *dat_dev, size_t step, void *stream);
+double bk_synthetic_value(uint64_t seed, uint64_t linear_cell); /* the same hash on the host */
+/* compareBrick between two brick storages over the bricks of box [lo,hi) of `grid_dev` (same tolerance rule as
+ * bk_compare_brick).  Synchronises `stream`. */
+int bk_compare_storage(const unsigned *grid_dev, const unsigned *gdims, const unsigned *lo, const unsigned *hi,
+                       const double *a_dev, size_t a_step, const double *b_dev, size_t b_step, double tol,
+                       unsigned long long *mismatches, double *max_rel, void *stream);
 
 /* ---- the stencil sweep ---------------------------------------------------------------------------------------- */
 /* One field pair = the two Brick<Dim<8,8,8>,Dim<4,8>> objects a reference kernel receives by value

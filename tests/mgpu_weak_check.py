@@ -38,7 +38,7 @@ def main():
     from oracle import schedule as S
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank, world, dist = bench.dist_setup(world)
+    rank, world, dist, _ = bench.dist_setup(world)
     if world == 1:
         bk._lib.check(bk.load().bk_set_device(0))
     cart = bench.CART[world]

@@ -32,9 +32,34 @@ def test_roofline_object_and_peak_source():
     pts = 512 ** 3
     r = bench.roofline_of(pts, 0.46e-3, 2, peak, src, 2175366000)
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] == peak
-    assert abs(r["achieved"] - 16.0 * pts / 0.46e-3 / 1e9) < 1e-6 and abs(r["frac"] - r["achieved"] / peak) < 1e-12
-    assert abs(r["frac_of_single_sweep_roofline"] - 2 * r["frac"]) < 1e-12 and r["steps_per_launch"] == 2
+    # 16 algorithmic bytes per point per time step x the point-steps of one launch / its duration
+    assert abs(r["achieved"] - 16.0 * pts * 2 / 0.46e-3 / 1e9) < 1e-6 and abs(r["frac"] - r["achieved"] / peak) < 1e-12
+    # ... and the physical view: a launch moves every point through HBM once whatever it fuses
+    assert abs(r["hbm_frac"] * 2 - r["frac"]) < 1e-12 and r["steps_per_launch"] == 2
     assert r["traffic"] == 2175366000
+    one = bench.roofline_of(pts, 0.35e-3, 1, peak, src, None)
+    assert one["frac"] == one["hbm_frac"]
+
+
+def test_reference_arm_runs_the_whole_job_with_every_host_core():
+    """under torchrun the workers inherit OMP_NUM_THREADS=1: the reference arm must override it, run all N subdomains of
+    the job on rank 0 and say how many cores it used (round-1 ADVICE)"""
+    env = dict(os.environ, OMP_NUM_THREADS="1", RANK="0", WORLD_SIZE="2", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--size", "64",
+                        "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    d = json.loads([x for x in r.stdout.splitlines() if x.startswith("{")][0])
+    cores = len(os.sched_getaffinity(0))
+    assert d["n_gpus"] == 2 and d["config"]["process_grid"] == "2x1x1" and d["cpu_baseline"]["cores"] == cores
+    assert d["config"]["workload"] == bench_workload("mpi7pt", 64, 8)
+    other = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--size", "64",
+                            "--steps", "1"], capture_output=True, text=True, timeout=60, cwd=ROOT, env=dict(env, RANK="1"))
+    assert other.returncode == 0 and other.stdout.strip() == ""
+
+
+def bench_workload(stencil, size, it):
+    import bench
+    return bench.workload_name(stencil, size, it)
 
 
 def test_clock_sampler_degrades_without_a_gpu():

@@ -330,7 +330,7 @@ def test_full_size_matches_oracle_on_a_sampled_slab(big):
     """512^3 single sweep: compare a 16-cell-thick slab through the middle with the C port's array form"""
     P = oracle.port()
     rng = np.random.default_rng(77)
-    for name in ("mpi7pt", "mpi25pt", "mpi125pt"):
+    for name in ("mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt"):
         st = bk.STENCILS[name]
         big.stencil = st
         host = rng.random(big.decomp.nbricks * 512)
@@ -350,6 +350,70 @@ def test_full_size_matches_oracle_on_a_sampled_slab(big):
         a_in, a_out = assemble(inp), assemble(out)
         want = P.sweep_array(st, a_in, (8, 8, 8), (a_in.shape[2] - 8, a_in.shape[1] - 8, a_in.shape[0] - 8))
         assert rel(a_out[8:-8, 8:-8, 8:-8], want[8:-8, 8:-8, 8:-8]) < TOL, name
+
+
+def test_synthetic_field_on_the_device_equals_the_host_hash():
+    """bk_fill_synthetic writes hash(global periodic cell coordinate) into the bricks: identical to core.synthetic_field,
+    ghost shell wrapped periodically, null brick untouched"""
+    d = bk.WeakDomain((24, 16, 32), 1, (2, 1, 2), (1, 0, 0), rank=2)
+    d.fill_synthetic(0xABCDEF)
+    bk.device_sync()
+    host = d.storage[0].to_host().reshape(-1, 8, 8, 8)
+    assert not host[0].any()
+    org, glob = d.global_origin(), d.global_cells()
+    assert glob == (48, 16, 64) and org == (24, 0, 0)
+    want = bk.synthetic_field(0xABCDEF, glob, tuple(o - 8 for o in org), tuple(o + n + 8 for o, n in zip(org, d.dom)))
+    g = d.decomp.grid
+    got = host[g].transpose(0, 3, 1, 4, 2, 5).reshape(want.shape)
+    assert np.array_equal(got, want)
+    assert 0.0 <= want.min() and want.max() < 1.0 and abs(want.mean() - 0.5) < 0.01
+    assert d.read_bricks((1, 0, 2), (3, 2, 4)).tolist() == want[24:40, 8:24, 16:32].tolist()
+
+
+def test_compare_storage_counts_cells_beyond_the_tolerance():
+    d = bk.WeakDomain((32, 32, 32), 1)
+    d.connect()
+    d.fill_synthetic(3, 0)
+    d.fill_synthetic(3, 1)
+    lo, hi = (1, 1, 1), (5, 5, 5)
+    assert bk.compare_storage(d.grid, lo, hi, d.bricks[0], d.bricks[1], TOL) == (True, 0, 0.0)
+    h = d.storage[1].to_host()
+    b = int(d.decomp.grid[2, 3, 4])
+    h[b * 512 + 77] *= 1.0 + 1e-9
+    d.storage[1].from_host(h)
+    ok, bad, worst = bk.compare_storage(d.grid, lo, hi, d.bricks[0], d.bricks[1], TOL)
+    assert not ok and bad == 1 and 1e-10 < worst < 1e-8
+
+
+@pytest.mark.parametrize("name", ["mpi7pt", "mpi13pt"])
+def test_full_size_two_steps_per_pass_equal_two_sweeps_on_a_random_field(big, name):
+    """512^3, the launch bench.py times: k_star2 over the whole interior against two k_star sweeps of the same random
+    (synthetic) field, compared on the device -- segment lengths and tile counts here differ from every small case"""
+    st = bk.STENCILS[name]
+    big.stencil = st
+    t = big.grid.dims
+    lo, hi = (1, 1, 1), tuple(x - 1 for x in t)
+    extra = [big.info.allocate(bk.BRICK), big.info.allocate(bk.BRICK)]
+    fused, plain = bk.Brick(big.info, extra[0], 0), bk.Brick(big.info, extra[1], 0)
+    big.fill_synthetic(0xF00D)
+    bk.stencil_advance(st, 2, big.grid, big.bricks[0], fused, lo, hi)
+    big._sweep(0, 1, (0, 0, 0), t, None)
+    bk.stencil(st, big.grid, big.bricks[1], plain, lo, hi)
+    ok, bad, worst = bk.compare_storage(big.grid, lo, hi, fused, plain, TOL)
+    for e in extra:
+        e.dat.free()
+    assert ok and bad == 0 and worst < 1e-13
+
+
+@pytest.mark.parametrize("name", ["mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt"])
+def test_full_size_period_matches_oracle_on_sampled_boxes(big, name):
+    """the whole exchange period at 512^3 (fused passes where they exist) on the synthetic field: corner, centre and edge
+    boxes against the oracle -- the same check bench.py prints as `parity`"""
+    import bench
+    big.stencil = bk.STENCILS[name]
+    big.st_iter = bk.load().bk_stencil_st_iter(big.stencil)
+    worst, pts = bench.sampled_parity(bk, big)
+    assert pts == 4 * 32 ** 3 and worst < TOL
 
 
 # ---- the C++ drivers (drivers/*.cpp over include/*.h): self-validating like the reference's single/weak/strong ------

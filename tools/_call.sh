@@ -1,2 +1,3 @@
-python tools/sweep_bench.py --steps 1 --stencils mpi25pt --variants 0,2,3,4 --reps 20 2>&1 | tee gpurun_out/c4_25.log
-python tools/sweep_bench.py --steps 1 --stencils mpi25pt --variants 0,2,3,4 --reps 20 --full 2>&1 | tee gpurun_out/c4_25full.log
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/c5_pytest.log
+timeout 600 python bench.py > gpurun_out/c5_bench.json 2> gpurun_out/c5_bench.err
+tail -3 gpurun_out/c5_pytest.log; tail -5 gpurun_out/c5_bench.err; wc -c gpurun_out/c5_bench.json

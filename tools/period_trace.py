@@ -27,7 +27,7 @@ def main():
     args = ap.parse_args()
     import bench
     import bricklib_b200 as bk
-    rank, world, dist = bench.dist_setup(int(os.environ.get("WORLD_SIZE", "1")))
+    rank, world, dist, _ = bench.dist_setup(int(os.environ.get("WORLD_SIZE", "1")))
     if world == 1:
         bk._lib.check(bk.load().bk_set_device(0))
     cart = bench.CART[world]
