@@ -457,6 +457,26 @@ def strong_leg(n):
     return out
 
 
+def array_baseline_leg(n):
+    """the reference's `Arr:` vs `Bri:` comparison through the C++ weak driver on all n GPUs -- the same
+    512^3-per-GPU job on a plain array layout (arr_kernel + exchangeArr as one strided-box pull) and on bricks"""
+    exe = os.path.join(ROOT, "drivers", "weak")
+    out = {"what": f"drivers/weak -s 512,512,512 -I 10 -g {n} -S <stencil>: array-layout loop, then the brick loop, same input"}
+    for name in ("mpi7pt", "mpi25pt"):
+        try:
+            r = subprocess.run([exe, "-s", "512,512,512", "-I", "10", "-g", str(n), "-S", name], capture_output=True, text=True,
+                               timeout=600, env=dict(os.environ, OMP_NUM_THREADS="4"))
+            perf = [float(ln.split()[1]) for ln in r.stdout.splitlines() if ln.startswith("perf ")]
+            if len(perf) == 2:
+                out[name] = {"array_GStencil/s": perf[0], "brick_GStencil/s": perf[1],
+                             "arr_equals_bri": "Arr == Bri: result match" in r.stdout}
+            else:
+                out[name] = {"error": (r.stdout + r.stderr)[-300:]}
+        except Exception as exc:
+            out[name] = {"error": str(exc)[:300]}
+    return out
+
+
 def single_leg():
     """BASELINE.json configs[0]: the single-GPU 7-point case of single/cuda.cpp (coeff[] stencil, in/out interleaved in one
     storage, step 1024), through the C++ single driver: kernel-only sweep rate + the host array sweep it validates against"""
@@ -632,6 +652,7 @@ def main():
             dist.barrier(group=host_group)
         if rank == 0:
             others["strong"] = strong_leg(n)
+            others["array_layout_baseline"] = array_baseline_leg(n)
             if n == 1:
                 others["single_7pt_512"] = single_leg()
         if dist is not None:

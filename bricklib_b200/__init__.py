@@ -7,9 +7,9 @@ template surface lives in include/*.h and the drivers in drivers/.
 from ._lib import (BK_OK, KERNEL_AUTO, KERNEL_BRICK, KERNEL_TILED, PART_ALL, PART_READY, PART_REST, PART_THIN, STENCILS,  # noqa: F401
                    BrickError, load)
 from .core import (BRICK, Brick, BrickDecomp, BrickInfo, BrickStorage, DeviceBuffer, DeviceGrid, Event,  # noqa: F401
-                   ExchangeView, StitchedGrid, compareBrick, copyFromBrick, copyToBrick, device_sync, init_grid, stencil,
+                   ExchangeView, ArrayExchangeView, array_stencil, bitset_of, StitchedGrid, compareBrick, copyFromBrick, copyToBrick, device_sync, init_grid, stencil,
                    stencil_advance, stencil_list, stencil_part, fill_synthetic, synthetic_field, compare_storage, section_owner, section_range, strong_pull_plan, zmort_decode, zmort_encode, Unsupported)
-from .weak import WeakDomain, shell_boxes  # noqa: F401
+from .weak import ArrayDomain, WeakDomain, shell_boxes  # noqa: F401
 
 
 def have_gpu():

@@ -34,6 +34,10 @@ class Seg(C.Structure):
     _fields_ = [("src", vp), ("dst", vp), ("bytes", sz)]
 
 
+class Box(C.Structure):
+    _fields_ = [("src", vp), ("dst", vp), ("n", C.c_long * 3), ("src_stride", C.c_long * 2), ("dst_stride", C.c_long * 2)]
+
+
 class Pointwise(C.Structure):
     _fields_ = [("op", C.c_int), ("c", C.c_double)]
 
@@ -109,6 +113,7 @@ SIGNATURES = {
     "bk_stencil_apply_part": (C.c_int, [C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp]),
     "bk_stencil_advance": (C.c_int, [C.c_int, C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp]),
     "bk_stencil_apply_list": (C.c_int, [C.c_int, C.POINTER(Field), vp, sz, dp, vp]),
+    "bk_array_stencil_apply": (C.c_int, [C.c_int, vp, vp, lp, lp, lp, dp, vp]),
     "bk_stencil_apply_multi": (C.c_int, [C.c_int, vp, C.c_uint, vp, up, up, up, dp, vp]),
     "bk_stencil_compile": (C.c_int, [C.POINTER(vp), C.POINTER(Tap), C.c_int]),
     "bk_stencil_compile_pointwise": (C.c_int, [C.POINTER(vp), C.POINTER(Tap), C.c_int, C.POINTER(Pointwise),
@@ -119,6 +124,7 @@ SIGNATURES = {
     "bk_stencil_def_advance": (C.c_int, [vp, C.c_int, C.POINTER(Field), vp, up, up, up, up, up, C.c_int, C.c_uint, vp]),
     "bk_launch_count": (C.c_ulonglong, []),
     "bk_xplan_create": (C.c_int, [C.POINTER(vp), C.POINTER(Seg), C.c_int]),
+    "bk_xplan_create_boxes": (C.c_int, [C.POINTER(vp), C.POINTER(Box), C.c_int]),
     "bk_xplan_destroy": (C.c_int, [vp]),
     "bk_xplan_bytes": (sz, [vp]),
     "bk_xplan_set_shape": (C.c_int, [vp, C.c_int, C.c_int]),

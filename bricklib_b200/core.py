@@ -439,6 +439,87 @@ class ExchangeView:
             pass
 
 
+def array_stencil(stencil_id, arr_in, arr_out, extent, lo, hi, coeff=None, stream=None):
+    """the array-layout baseline kernel (arr_kernel, weak/main.cu:27-33): out = stencil(in) for cells lo <= (i,j,k) < hi of
+    a plain array with `extent` cells per axis (i first); arr_in / arr_out are DeviceBuffers"""
+    check(load().bk_array_stencil_apply(stencil_id, arr_in.ptr, arr_out.ptr, _l3(extent), _l3(lo), _l3(hi), _coeff(coeff),
+                                        stream))
+
+
+def bitset_of(direction):
+    """BitSet.set of a direction vector (di, dj, dk) in {-1,0,1}^3: +axis a is bit a, -axis a bit 31+a, axis 1 = i"""
+    s = 0
+    for a, v in enumerate(direction, start=1):
+        if v > 0:
+            s |= 1 << a
+        elif v < 0:
+            s |= 1 << (31 + a)
+    return s
+
+
+class ArrayExchangeView:
+    """exchangeArr<3> (include/array-mpi.h:146-213) for DEVICE arrays: the 26 ghost regions of a padded array are pulled
+    straight from the neighbours' interior faces / edges / corners as strided boxes by one kernel (bk_xplan_create_boxes)
+    -- the reference packs them into 26 buffers, sends, receives and unpacks.  `peer_ptrs[r]` = device address of rank
+    r's array as seen from this process; rank_map as filled by populate()."""
+
+    @staticmethod
+    def boxes(dom, pad, ghost):
+        """pure host data: (direction, src offset, dst offset, cells (i,j,k)) per neighbour, offsets in elements"""
+        ext = [dom[a] + 2 * (pad[a] + ghost[a]) for a in range(3)]
+        stride = (1, ext[0], ext[0] * ext[1])
+        out = []
+        for dk in (-1, 0, 1):
+            for dj in (-1, 0, 1):
+                for di in (-1, 0, 1):
+                    v = (di, dj, dk)
+                    if v == (0, 0, 0):
+                        continue
+                    n, so, do = [], 0, 0
+                    for a in range(3):
+                        p, g, d = pad[a], ghost[a], dom[a]
+                        if v[a] > 0:      # my upper ghost <- the neighbour's lowest interior cells
+                            n.append(g); src, dst = p + g, p + g + d
+                        elif v[a] < 0:    # my lower ghost <- the neighbour's highest interior cells
+                            n.append(g); src, dst = p + d, p
+                        else:
+                            n.append(d); src = dst = p + g
+                        so += src * stride[a]
+                        do += dst * stride[a]
+                    out.append((v, so, do, tuple(n)))
+        return out, tuple(ext)
+
+    def __init__(self, dom, pad, ghost, rank_map, arr, peer_ptrs, my_rank=0):
+        plan, ext = self.boxes(dom, pad, ghost)
+        bx = (_lib.Box * len(plan))()
+        self.bytes = 0
+        for i, (v, so, do, n) in enumerate(plan):
+            peer = rank_map[bitset_of(v)]
+            bx[i].src = peer_ptrs[peer] + so * 8
+            bx[i].dst = arr.ptr + do * 8
+            bx[i].n = (C.c_long * 3)(*n)
+            bx[i].src_stride = (C.c_long * 2)(ext[0], ext[0] * ext[1])
+            bx[i].dst_stride = (C.c_long * 2)(ext[0], ext[0] * ext[1])
+            self.bytes += n[0] * n[1] * n[2] * 8
+        h = C.c_void_p()
+        check(load().bk_xplan_create_boxes(C.byref(h), bx, len(plan)))
+        self._h = h
+
+    def exchange(self, stream=None):
+        check(load().bk_xplan_run(self._h, stream))
+
+    def exchange_sync(self, wait_flags, signal_flags, epoch, stream=None):
+        w = (C.c_void_p * max(1, len(wait_flags)))(*wait_flags)
+        s = (C.c_void_p * max(1, len(signal_flags)))(*signal_flags)
+        check(load().bk_xplan_run_sync(self._h, w, len(wait_flags), s, len(signal_flags), epoch, stream))
+
+    def __del__(self):
+        try:
+            load().bk_xplan_destroy(self._h)
+        except Exception:
+            pass
+
+
 def device_sync():
     check(load().bk_device_sync())
 

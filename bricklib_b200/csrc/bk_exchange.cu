@@ -25,6 +25,10 @@ struct bk_xplan {
   std::atomic<unsigned> flag_turn{0};
   unsigned *done_dev = nullptr;  // CTAs of the running gated launch that have finished; wraps to 0 with the last one
   int shape_ctas = 0, shape_threads = 0;   // bk_xplan_set_shape: 0 = default (many 256-thread CTAs)
+  // array-layout plans (bk_xplan_create_boxes): strided 3-D boxes instead of contiguous ranges; `chunk_first_dev` then
+  // counts chunks of kBoxChunk elements per box
+  bk_box_t *boxes_dev = nullptr;
+  int nbox = 0;
   // copy-engine transport (bk_xplan_run_ce): the segments as host data, dealt largest-first to a few lanes
   std::vector<bk_seg_t> segs_host;
   std::vector<int> lane_of;                // segment -> lane, in issue order `order`
@@ -44,6 +48,7 @@ constexpr unsigned kChunkBytes = 16384;
 constexpr size_t kCeMinBytes = 1u << 20;  // copy-engine transport: smaller segments are cheaper through the kernel
 constexpr int kThreads = 256;
 constexpr int kFlagSlots = 16, kFlagSlotLen = 192;
+constexpr unsigned kBoxChunk = 4096;  // elements of a strided box one thread group moves per iteration
 
 __device__ __forceinline__ void spin_until(const uint64_t *flag, uint64_t value) {
   const volatile uint64_t *f = flag;
@@ -56,7 +61,8 @@ __device__ __forceinline__ void spin_until(const uint64_t *flag, uint64_t value)
 __global__ void __launch_bounds__(1024) k_xplan(const bk_seg_t *__restrict__ segs,
                                                 const unsigned long long *__restrict__ first, int nseg,
                                                 unsigned long long nchunks, uint64_t *const *wait_flags, int nwait,
-                                                int nsignal, uint64_t *gate, unsigned *done) {
+                                                int nsignal, uint64_t *gate, unsigned *done,
+                                                const bk_box_t *__restrict__ boxes) {
   if (nwait > 0) {
     if ((int) threadIdx.x < nwait) spin_until(wait_flags[threadIdx.x], (uint64_t) (size_t) wait_flags[64]);
     __syncthreads();
@@ -68,6 +74,19 @@ __global__ void __launch_bounds__(1024) k_xplan(const bk_seg_t *__restrict__ seg
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
       if (first[mid] <= c) lo = mid; else hi = mid;
+    }
+    if (boxes) {
+      // array-layout exchange (exchangeArr, array-mpi.h:146-213, without its pack / unpack buffers): element e of box b
+      // is cell (e % n0, (e / n0) % n1, e / (n0 n1)); consecutive threads move consecutive cells of a row
+      const bk_box_t bx = boxes[lo];
+      const unsigned long long tot = (unsigned long long) bx.n[0] * bx.n[1] * bx.n[2];
+      const unsigned long long e0 = (c - first[lo]) * kBoxChunk;
+      for (unsigned long long e = e0 + tid; e < min(tot, e0 + kBoxChunk); e += kThreads) {
+        const long i = (long) (e % bx.n[0]), r = (long) (e / bx.n[0]);
+        const long j = r % bx.n[1], k = r / bx.n[1];
+        bx.dst[i + j * bx.dst_stride[0] + k * bx.dst_stride[1]] = bx.src[i + j * bx.src_stride[0] + k * bx.src_stride[1]];
+      }
+      continue;
     }
     const bk_seg_t sg = segs[lo];
     const size_t off = (size_t) (c - first[lo]) * kChunkBytes;
@@ -141,8 +160,8 @@ int launch_copy(bk_xplan *p, uint64_t *const *wait_dev, int nwait, cudaStream_t 
     want = (want + threads / kThreads - 1) / (threads / kThreads);
   }
   const unsigned grid = (unsigned) (want < cap ? want : cap);
-  k_xplan<<<grid, threads, 0, s>>>(p->segs_dev, p->chunk_first_dev, p->nseg, p->nchunks, wait_dev, nwait, nsignal, gate,
-                                   publish ? p->done_dev : nullptr);
+  k_xplan<<<grid, threads, 0, s>>>(p->segs_dev, p->chunk_first_dev, p->nbox ? p->nbox : p->nseg, p->nchunks, wait_dev, nwait,
+                                   nsignal, gate, publish ? p->done_dev : nullptr, p->boxes_dev);
   BK_LAUNCHED();
   return BK_OK;
 }
@@ -179,8 +198,34 @@ int bk_xplan_create(bk_xplan_t **out, const bk_seg_t *segs, int nseg) {
   return BK_OK;
 }
 
+int bk_xplan_create_boxes(bk_xplan_t **out, const bk_box_t *boxes, int nbox) {
+  BK_REQUIRE(out && boxes && nbox > 0, "bad arguments");
+  std::vector<unsigned long long> first(nbox + 1, 0);
+  size_t total = 0;
+  for (int i = 0; i < nbox; ++i) {
+    BK_REQUIRE(boxes[i].src && boxes[i].dst && boxes[i].n[0] > 0 && boxes[i].n[1] > 0 && boxes[i].n[2] > 0, "empty box");
+    const unsigned long long cells = (unsigned long long) boxes[i].n[0] * boxes[i].n[1] * boxes[i].n[2];
+    first[i + 1] = first[i] + (cells + kBoxChunk - 1) / kBoxChunk;
+    total += cells * sizeof(double);
+  }
+  bk_xplan *p = new bk_xplan();
+  p->nbox = nbox;
+  p->nchunks = first[nbox];
+  p->bytes = total;
+  BK_CUDA(cudaMalloc(&p->boxes_dev, sizeof(bk_box_t) * nbox));
+  BK_CUDA(cudaMemcpy(p->boxes_dev, boxes, sizeof(bk_box_t) * nbox, cudaMemcpyHostToDevice));
+  BK_CUDA(cudaMalloc(&p->chunk_first_dev, sizeof(unsigned long long) * (nbox + 1)));
+  BK_CUDA(cudaMemcpy(p->chunk_first_dev, first.data(), sizeof(unsigned long long) * (nbox + 1), cudaMemcpyHostToDevice));
+  BK_CUDA(cudaMalloc(&p->flagbuf_dev, sizeof(uint64_t *) * kFlagSlots * kFlagSlotLen));
+  BK_CUDA(cudaMalloc(&p->done_dev, sizeof(unsigned)));
+  BK_CUDA(cudaMemset(p->done_dev, 0, sizeof(unsigned)));
+  *out = p;
+  return BK_OK;
+}
+
 int bk_xplan_destroy(bk_xplan_t *p) {
   if (!p) return BK_OK;
+  cudaFree(p->boxes_dev);
   cudaFree(p->segs_dev);
   cudaFree(p->chunk_first_dev);
   cudaFree(p->flagbuf_dev);
@@ -256,6 +301,7 @@ int bk_xplan_run_gate(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwai
 int bk_xplan_run_ce(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwait, uint64_t *const *signal_flags,
                     int nsignal, uint64_t epoch, void *stream) {
   BK_REQUIRE(p, "null plan");
+  BK_REQUIRE(p->nbox == 0, "the copy-engine transport moves contiguous ranges, not array boxes");
   BK_REQUIRE(nwait >= 0 && nwait <= 64 && nsignal >= 0 && nsignal <= 64, "at most 64 flags each");
   cudaStream_t s = (cudaStream_t) stream;
   if (p->nlanes == 0) {
@@ -305,7 +351,7 @@ int bk_xplan_run_ce(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwait,
   if (p->small_nchunks > 0 || nwait > 0) {
     const unsigned grid = (unsigned) std::max(1ull, std::min(p->small_nchunks, 32ull));
     k_xplan<<<grid, kThreads, 0, s>>>(p->small_segs_dev, p->small_first_dev, p->small_nseg, p->small_nchunks,
-                                      fb, nwait, 0, nullptr, nullptr);
+                                      fb, nwait, 0, nullptr, nullptr, nullptr);
     BK_LAUNCHED();
   }
   if (!p->order.empty()) {

@@ -267,6 +267,54 @@ class WeakDomain:
                                  None, stream)
 
 
+class ArrayDomain:
+    """The reference's array-layout baseline loop ("Arr:" block, weak/main.cu:161-213) on the device: two padded arrays,
+    per period one exchangeArr (ArrayExchangeView: 26 strided boxes pulled by one kernel) and ST_ITER arr_kernel sweeps
+    over the WHOLE ghost-inclusive region, ping-ponging in -> out -> in (the rim the sweeps cannot compute correctly
+    grows by one radius per sweep and is exactly consumed by the ghost depth, as with bricks)."""
+
+    def __init__(self, dom, stencil_id, cart=(1, 1, 1), coo=(0, 0, 0), rank=0):
+        self.dom, self.stencil, self.rank = tuple(dom), stencil_id, rank
+        self.cart, self.coo = tuple(cart), tuple(coo)
+        self.st_iter = load().bk_stencil_st_iter(stencil_id)
+        self.ext = tuple(n + 2 * (PADDING + GZ) for n in self.dom)
+        nbytes = int(np.prod(self.ext)) * 8
+        self.arr = [core.DeviceBuffer(nbytes), core.DeviceBuffer(nbytes)]
+        for a in self.arr:
+            a.zero()
+        sets, ranks = (C.c_uint64 * 27)(), (C.c_int * 27)()
+        check(load().bk_rank_map((C.c_int * 3)(*cart), (C.c_int * 3)(*coo), sets, ranks))
+        self.rank_map = {int(s): int(r) for s, r in zip(sets, ranks)}
+        self.peers = sorted(set(self.rank_map.values()) - {rank})
+        self.view = None
+
+    def connect(self, peer_ptrs=None):
+        ptrs = dict(peer_ptrs or {})
+        ptrs[self.rank] = self.arr[0].ptr
+        self.view = core.ArrayExchangeView(self.dom, (PADDING,) * 3, (GZ,) * 3, self.rank_map, self.arr[0], ptrs, self.rank)
+
+    def load_interior(self, field):
+        host = np.zeros(self.ext[::-1])
+        o = PADDING + GZ
+        host[o:-o, o:-o, o:-o] = field
+        self.arr[0].upload(host)
+
+    def read_interior(self, which=0):
+        o = PADDING + GZ
+        return np.ascontiguousarray(self.arr[which].download(np.float64).reshape(self.ext[::-1])[o:-o, o:-o, o:-o])
+
+    def sweeps(self, stream=None):
+        lo = (PADDING,) * 3
+        hi = tuple(e - PADDING for e in self.ext)
+        for s in range(self.st_iter):
+            core.array_stencil(self.stencil, self.arr[s % 2], self.arr[1 - s % 2], self.ext, lo, hi, None, stream)
+
+    def period(self, stream=None):
+        """exchange + ST_ITER sweeps; single process (peers on the same host thread order themselves by the stream)"""
+        self.view.exchange(stream)
+        self.sweeps(stream)
+
+
 def shell_boxes(lo, hi, in_lo, in_hi):
     """the six slabs of box [lo,hi) minus inner box [in_lo,in_hi): two k-slabs, two j-slabs, two i-slabs"""
     out = []

@@ -16,6 +16,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <thread>
+#include "array-mpi.h"
 #include "common.h"
 
 namespace {
@@ -50,8 +51,11 @@ struct Shared {
   const StencilDef *st = nullptr;
   bool validate = false;
   bool no_fuse = false;  // -F: one sweep per pass (no temporal blocking)
+  bool no_array = false; // -A: skip the array-layout baseline ("Arr:" block)
   std::vector<bElem *> storage_ptr;  // rank -> device address of storage[0]
+  std::vector<bElem *> array_ptr;    // rank -> device address of the input array of the Arr: baseline
   std::vector<double> calc, call, wait, total;
+  std::vector<int> arr_match;        // rank -> brick result equals array result (compareBrick on the device)
   std::vector<bElem *> result;       // rank -> host copy of the interior after the run (validation)
   bElem *global_in = nullptr;
   std::atomic<int> failures{0};
@@ -91,6 +95,7 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
   unsigned *grid_dev = nullptr;
   copyToDevice(strideb, grid_dev, bDecomp.gridData());
 
+  bElem *arr_in_dev = nullptr, *arr_out_dev = nullptr;  // the Arr: baseline's arrays (the input doubles as the bricks' source)
   // input: this rank's block of a global random periodic field (interior only; ghosts come from the first exchange)
   {
     bElem *in_ptr;
@@ -105,12 +110,85 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     } else {
       in_ptr = randomArray(stride, 0x5EED + rank);
     }
-    bElem *arr_dev = nullptr;
-    copyToDevice(stride, arr_dev, in_ptr);
-    copyToBrickDevice(strideg, {PADDING, PADDING, PADDING}, {0, 0, 0}, arr_dev, grid_dev, bIn_dev);
+    copyToDevice(stride, arr_in_dev, in_ptr);
+    copyToBrickDevice(strideg, {PADDING, PADDING, PADDING}, {0, 0, 0}, arr_in_dev, grid_dev, bIn_dev);
     bkCheck(bk_device_sync());
-    bk_dev_free(arr_dev);
     free(in_ptr);
+  }
+
+  // ---- Arr: the array-layout baseline of the reference (weak/main.cu:161-213): exchangeArr + ST_ITER arr_kernel sweeps
+  // over the whole ghost-inclusive region, on the same input, timed with the same protocol as the bricks below
+  const std::vector<long> dom_l = {(long) dom[0], (long) dom[1], (long) dom[2]}, pad3 = {PADDING, PADDING, PADDING}, gz3 = {GZ, GZ, GZ};
+  if (!S.no_array) {
+    const size_t abytes = (size_t) stride[0] * stride[1] * stride[2] * sizeof(bElem);
+    void *tmp = nullptr;
+    bkCheck(bk_dev_alloc(&tmp, abytes));
+    arr_out_dev = (bElem *) tmp;
+    bkCheck(bk_dev_memset(arr_out_dev, 0, abytes, nullptr));
+    S.array_ptr[rank] = arr_in_dev;
+    bar.wait();
+    for (auto &kv : bDecomp.rank_map)
+      if (kv.second % ndev != dev) bkCheck(bk_peer_enable(kv.second % ndev));
+    ArrayExchangeView aev(arr_in_dev, bDecomp.rank_map, S.array_ptr, dom_l, pad3, gz3);
+    void *e0, *e1, *e2, *e3;
+    for (void **e : {&e0, &e1, &e2, &e3}) bkCheck(bk_event_create(e));
+    const std::vector<long> alo = pad3, ahi = {stride[0] - PADDING, stride[1] - PADDING, stride[2] - PADDING};
+    double a_calc = 0, a_call = 0, a_wait = 0;
+    auto arr_func = [&]() {
+      bkCheck(bk_device_sync());
+      double t0 = omp_get_wtime();
+      bar.wait();  // every rank's previous sweeps are complete before anyone pulls
+      a_wait += omp_get_wtime() - t0;
+      bkCheck(bk_event_record(e0, nullptr));
+      aev.exchange(nullptr);
+      bkCheck(bk_event_record(e1, nullptr));
+      bkCheck(bk_event_sync(e1));
+      float ms = 0;
+      bkCheck(bk_event_elapsed_ms(e0, e1, &ms));
+      a_call += ms / 1e3;
+      t0 = omp_get_wtime();
+      bar.wait();  // every pull has finished before the second sweep overwrites an input array
+      a_wait += omp_get_wtime() - t0;
+      bkCheck(bk_event_record(e2, nullptr));
+      for (int i = 0; i < st->st_iter / 2; ++i) {
+        arrayStencil(st->id, arr_in_dev, arr_out_dev, stride, alo, ahi);
+        arrayStencil(st->id, arr_out_dev, arr_in_dev, stride, alo, ahi);
+      }
+      bkCheck(bk_event_record(e3, nullptr));
+      bkCheck(bk_event_sync(e3));
+      bkCheck(bk_event_elapsed_ms(e2, e3, &ms));
+      a_calc += ms / 1e3;
+    };
+    arr_func();
+    a_calc = a_call = a_wait = 0;
+    bar.wait();
+    const double t_st = omp_get_wtime();
+    for (int i = 0; i < S.iters; ++i) arr_func();
+    bkCheck(bk_device_sync());
+    bar.wait();
+    const double per_period = (omp_get_wtime() - t_st) / S.iters;
+    const int cnt = S.iters * st->st_iter;
+    S.calc[rank] = a_calc / cnt, S.call[rank] = a_call / cnt, S.wait[rank] = a_wait / cnt, S.total[rank] = per_period / st->st_iter;
+    bar.wait();
+    if (rank == 0) {
+      const double tsize = 2.0 * aev.bytes;  // sent + received
+      mpi_stats calc_s = mpi_statistics(S.calc), call_s = mpi_statistics(S.call), wait_s = mpi_statistics(S.wait);
+      mpi_stats tot_s = mpi_statistics(S.total);
+      std::vector<double> spd(S.size), sz(S.size, tsize * 1e-6), zero(S.size, 0.0);
+      for (int r = 0; r < S.size; ++r) spd[r] = tsize / 1e9 / std::max(1e-12, (S.call[r] + S.wait[r]) * st->st_iter);
+      std::cout << "Arr: " << tot_s.max << std::endl;
+      std::cout << "calc " << calc_s << std::endl;
+      std::cout << "pack " << mpi_statistics(zero) << std::endl;
+      std::cout << "move " << mpi_statistics(zero) << std::endl;
+      std::cout << "call " << call_s << std::endl;
+      std::cout << "wait " << wait_s << std::endl;
+      std::cout << "  | MPI size (MB): " << mpi_statistics(sz) << std::endl;
+      std::cout << "  | MPI speed (GB/s): " << mpi_statistics(spd) << std::endl;
+      double tot_elems = (double) S.size * dom[0] * dom[1] * dom[2];
+      std::cout << "perf " << tot_elems * 1.0e-9 / tot_s.max << " GStencil/s" << std::endl << std::endl;
+    }
+    bar.wait();
+    for (void *e : {e0, e1, e2, e3}) bk_event_destroy(e);
   }
 
   // wire the neighbours: peer access + their storage addresses
@@ -203,6 +281,11 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     bk_dev_free(arr_dev);
     S.result[rank] = zero;
   }
+  if (!S.no_array) {  // the reference's closing check: the brick result equals the array result (weak/main.cu:325-327)
+    S.arr_match[rank] = compareBrickDevice(dom_l, pad3, gz3, arr_in_dev, grid_dev, (npass % 2) ? bOut_dev : bIn_dev, BRICK_TOLERANCE);
+    bk_dev_free(arr_out_dev);
+  }
+  bk_dev_free(arr_in_dev);
   bar.wait();
   if (rank == 0) {
     const size_t tsize = bDecomp.exchangeSize() * bSize * sizeof(bElem) * 2;  // sent + received, as weak/main.cpp:220-222
@@ -220,6 +303,12 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     double tot_elems = (double) S.size * dom[0] * dom[1] * dom[2];
     std::cout << "perf " << tot_elems * 1.0e-9 / tot_s.max << " GStencil/s" << std::endl;
     std::cout << "Total of " << bDecomp.ghost.size() << " parts" << std::endl;
+    if (!S.no_array) {
+      bool all = true;
+      for (int m : S.arr_match) all = all && m;
+      std::cout << (all ? "Arr == Bri: result match" : "Arr == Bri: result mismatch!") << std::endl;
+      if (!all) S.failures++;
+    }
   }
   freeBrickInfoDevice(bInfo_dev);
   bk_dev_free(grid_dev);
@@ -234,7 +323,7 @@ int main(int argc, char **argv) {
   int c, sel = 0;
   bool bin = false;
   if (const char *e = getenv("BRICK_RANKS")) S.size = atoi(e);
-  while ((c = getopt(argc, argv, "d:s:I:g:S:vbhF")) != -1) switch (c) {
+  while ((c = getopt(argc, argv, "d:s:I:g:S:vbhFA")) != -1) switch (c) {
       case 'b': bin = true; break;
       case 'd': parseTuple(optarg, S.dom), sel = sel ? -2 : 1; break;
       case 's': parseTuple(optarg, S.dom), sel = sel ? -2 : 2; break;
@@ -243,10 +332,12 @@ int main(int argc, char **argv) {
       case 'S': sname = optarg; break;
       case 'v': S.validate = true; break;
       case 'F': S.no_fuse = true; break;
+      case 'A': S.no_array = true; break;
       default:
         printf("Program options\n  -h: help\n  -b: process grid of powers of two\n  -d i,j,k: overall domain size\n"
                "  -s i,j,k: per-GPU domain size\n  -I n: exchange periods (default 100)\n  -g n: GPUs = ranks (default 1)\n"
-               "  -S name: 7pt mpi7pt mpi13pt mpi25pt mpi125pt\n  -v: validate against a CPU sweep\n");
+               "  -S name: 7pt mpi7pt mpi13pt mpi25pt mpi125pt\n  -v: validate against a CPU sweep\n  -F: one sweep per pass\n"
+               "  -A: skip the array-layout baseline (Arr: block)\n");
         return 0;
     }
   if (sel == -2) {
@@ -274,6 +365,8 @@ int main(int argc, char **argv) {
   std::cout << "d3pt" << S.st->points << " MPI decomp (" << S.st->script << ", one rank per GPU, NVLink pull exchange)" << std::endl;
 
   S.storage_ptr.assign(S.size, nullptr);
+  S.array_ptr.assign(S.size, nullptr);
+  S.arr_match.assign(S.size, 1);
   S.calc.assign(S.size, 0), S.call = S.wait = S.total = S.calc;
   S.result.assign(S.size, nullptr);
   const long G[3] = {(long) S.dom[0] * S.cart[2], (long) S.dom[1] * S.cart[1], (long) S.dom[2] * S.cart[0]};
@@ -320,5 +413,5 @@ int main(int argc, char **argv) {
     }
     std::cout << "result match (worst relative difference " << worst << " after " << steps << " steps)" << std::endl;
   }
-  return failed ? 1 : 0;
+  return (failed || S.failures) ? 1 : 0;
 }

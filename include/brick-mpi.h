@@ -141,9 +141,13 @@ class BrickDecomp {
   BrickComm comm;
   std::unordered_map<uint64_t, int> rank_map;
 
+  /// numfield interleaved fields share one storage: a brick id then names a chunk of numfield bricks (allocate the storage
+  /// with step = numfield * 512 and view field f as Brick(bInfo, storage, f * 512)); the numbering does not depend on it
+  /// (brick-mpi.h:304-350 uses it for page padding only, which is 0 for 4 KiB bricks), the exchange moves whole chunks
+  unsigned numfield;
   BrickDecomp(const std::vector<unsigned> &dims, const unsigned depth, unsigned numfield = 1)
-      : dims_cells(dims), depth(depth) {
-    if (numfield != 1) throw std::runtime_error("BrickDecomp: interleaved fields are not supported by this build");
+      : dims_cells(dims), depth(depth), numfield(numfield) {
+    if (numfield < 1) throw std::runtime_error("BrickDecomp: numfield must be at least 1");
   }
   BrickDecomp(const BrickDecomp &) = delete;
   ~BrickDecomp() {
@@ -212,6 +216,8 @@ class BrickDecomp {
   /// Pull plan for one DEVICE storage.  peers[r] = base address of rank r's storage as seen from this GPU (own
   /// address for r == comm.rank; a peer-enabled or IPC-mapped address otherwise).
   ExchangeView exchangeView(BrickStorage &bStorage_dev, const std::vector<bElem *> &peers) {
+    if (bStorage_dev.step % (512 * (size_t) numfield))
+      throw std::runtime_error("exchangeView: storage step is not a multiple of numfield bricks");
     std::vector<bk_seg_t> segs(ghost.size());
     for (size_t i = 0; i < ghost.size(); ++i) {
       const int src_rank = rank_map.at(ghost[i].neighbor.set);

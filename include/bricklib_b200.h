@@ -209,6 +209,11 @@ int bk_stencil_advance(int stencil, int steps, const bk_field_t *f, const unsign
 /* same over an explicit list of brick ids (inner / skin / ghost lists for overlap; any adjacency-defined set) */
 int bk_stencil_apply_list(int stencil, const bk_field_t *f, const unsigned *ids_dev, size_t n,
                           const double *coeff_host, void *stream);
+/* The reference's array-layout baseline kernel (arr_kernel, weak/main.cu:27-33; d3pt7_arr, stencils/3axis.cu): the same
+ * stencil over a plain padded array, out[p] = sum_t c_t in[p + offset_t] for the cell box lo <= (i,j,k) < hi; extent =
+ * cells per axis of the allocation (i first).  The box must keep the stencil radius inside the allocation. */
+int bk_array_stencil_apply(int stencil, const double *in_dev, double *out_dev, const long *extent, const long *lo,
+                           const long *hi, const double *coeff_host, void *stream);
 /* strong/main.cu:85-99 brick_kernel over `nsub` subdomains that share grid/adj: fields[s] per subdomain (host array) */
 int bk_stencil_apply_multi(int stencil, const bk_field_t *fields_dev, unsigned nsub, const unsigned *grid_dev,
                            const unsigned *gdims, const unsigned *lo, const unsigned *hi, const double *coeff_host,
@@ -268,6 +273,18 @@ typedef struct {
 } bk_seg_t;
 typedef struct bk_xplan bk_xplan_t;
 int bk_xplan_create(bk_xplan_t **plan, const bk_seg_t *segs_host, int nseg);
+/* Array-layout exchange -- the reference's exchangeArr (include/array-mpi.h:146-213: pack 26 regions, Isend/Irecv,
+ * unpack) as the same single pull kernel over strided 3-D boxes: cell (i,j,k) of a box lives at
+ * ptr[i + j*stride[0] + k*stride[1]] (elements); src may be a peer GPU's array.  No pack or unpack buffer exists.
+ * Runs through bk_xplan_run / _run_sync / _run_gate like a range plan. */
+typedef struct {
+  const double *src;
+  double *dst;
+  long n[3];          /* cells per axis, i first */
+  long src_stride[2]; /* elements between consecutive j rows / k planes of the source array */
+  long dst_stride[2];
+} bk_box_t;
+int bk_xplan_create_boxes(bk_xplan_t **plan, const bk_box_t *boxes_host, int nbox);
 int bk_xplan_destroy(bk_xplan_t *plan);
 size_t bk_xplan_bytes(const bk_xplan_t *plan);
 /* Launch shape of the pull kernel.  Default (0, 0): up to 8 CTAs of 256 threads per SM -- the fastest copy on an idle
