@@ -119,6 +119,7 @@ SIGNATURES = {
     "bk_stencil_compile_pointwise": (C.c_int, [C.POINTER(vp), C.POINTER(Tap), C.c_int, C.POINTER(Pointwise),
                                                C.POINTER(Pointwise)]),
     "bk_stencil_def_destroy": (C.c_int, [vp]),
+    "bk_stencil_def_source": (C.c_int, [vp, C.c_char_p, sz, C.POINTER(sz)]),
     "bk_stencil_def_info": (C.c_int, [vp, ip, ip, ip, ip, ip]),
     "bk_stencil_def_apply": (C.c_int, [vp, C.POINTER(Field), vp, up, up, up, C.c_uint, vp]),
     "bk_stencil_def_advance": (C.c_int, [vp, C.c_int, C.POINTER(Field), vp, up, up, up, up, up, C.c_int, C.c_uint, vp]),

@@ -67,4 +67,10 @@ struct CoefSpec {
 };
 int coef_spec_for(int stencil, const double *coeff_host, CoefSpec *out);
 
+// launch geometry of a generated marching kernel (bk_codegen.cu -> bk_stencil_tiled.cu: launch_generated)
+struct GenGeom {
+  int TI, TJ, ovh, threads;
+  size_t smem;
+};
+
 }  // namespace bk

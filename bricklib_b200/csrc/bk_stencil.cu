@@ -11,10 +11,14 @@
 // Summation order (fixed, documented in DESIGN.md): centre first, then by distance d = 1..R: +i,-i,+j,-j,+k,-k (star);
 // dz,dy,dx ascending (cube).  The reference's order is codegen-dependent, parity is to 1e-12 relative, not bitwise.
 #include "bk_common.h"
+#include "bk_codegen.h"
 #include <algorithm>
 #include <array>
 #include <cstdlib>
+#include <cstring>
 #include <map>
+#include <mutex>
+#include <string>
 #include <vector>
 
 namespace bk {
@@ -370,8 +374,12 @@ struct bk_stencil_def {
   int ntaps = 0;
   bk::CoefSpec spec;        // kind STAR / CUBE
   int krad = 0;             // kernel radius (1, 2 or 4)
+  std::vector<TapDev> taps_host;  // the tap table of k_taps, uploaded at its first launch (compiling needs no device)
   TapDev *taps_dev = nullptr;
+  std::mutex mu;
   bk_pointwise_t pre = {BK_OP_NONE, 0.0}, post = {BK_OP_NONE, 0.0};
+  bk::GenStencil *gen = nullptr;  // BK_KIND_GENERATED: the marching kernel generated for these taps (bk_codegen.cu)
+  std::string gen_why;            // why there is none
 };
 
 extern "C" {
@@ -448,15 +456,14 @@ int bk_stencil_compile_pointwise(bk_stencil_def_t **out, const bk_tap_t *taps, i
     return BK_OK;
   }
   d->kind = BK_KIND_TAPS;
-  const int W = 8 + 2 * d->krad;
-  std::vector<TapDev> host;
-  for (auto &kv : m) host.push_back({(kv.first[0] * W + kv.first[1]) * W + kv.first[2], kv.second});
-  if (cudaMalloc(&d->taps_dev, sizeof(TapDev) * host.size()) != cudaSuccess ||
-      cudaMemcpy(d->taps_dev, host.data(), sizeof(TapDev) * host.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
-    cudaError_t e = cudaGetLastError();
-    delete d;
-    return bk::cuda_fail(e, "tap table upload", __FILE__, __LINE__);
+  if (!getenv("BK_NO_CODEGEN")) {  // developer knob: keep the tap-table kernel
+    std::vector<bk::GenTap> gt;
+    for (auto &kv : m) gt.push_back({kv.first[2], kv.first[1], kv.first[0], kv.second});
+    d->gen = bk::gen_create(gt, d->pre, d->post, &d->gen_why);
+    if (d->gen) d->kind = BK_KIND_GENERATED;
   }
+  const int W = 8 + 2 * d->krad;
+  for (auto &kv : m) d->taps_host.push_back({(kv.first[0] * W + kv.first[1]) * W + kv.first[2], kv.second});
   *out = d;
   return BK_OK;
 }
@@ -464,6 +471,7 @@ int bk_stencil_compile_pointwise(bk_stencil_def_t **out, const bk_tap_t *taps, i
 int bk_stencil_def_destroy(bk_stencil_def_t *d) {
   if (!d) return BK_OK;
   if (d->taps_dev) cudaFree(d->taps_dev);
+  bk::gen_destroy(d->gen);
   delete d;
   return BK_OK;
 }
@@ -490,19 +498,45 @@ int bk_stencil_def_advance(const bk_stencil_def_t *d, int steps, const bk_field_
   BK_REQUIRE(f->in != f->out, "in-place sweep is not defined");
   BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
   cudaStream_t s = (cudaStream_t) stream;
-  if (d->kind != BK_KIND_TAPS) {
+  if (d->kind == BK_KIND_STAR || d->kind == BK_KIND_CUBE) {
     if (steps == 1 && part == BK_PART_ALL) return apply_spec(d->spec, f, grid, gdims, lo, hi, flags, s);
     return bk::launch_tiled(d->spec, *f, nullptr, 1, grid, gdims, lo, hi, s, part, ready_lo, ready_hi, steps);
+  }
+  if (d->kind == BK_KIND_GENERATED && steps == 1 && flags != BK_KERNEL_BRICK) {
+    const dim3 box(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
+    if (box.x == 0 || box.y == 0 || box.z == 0) return BK_OK;
+    const int rc = bk::gen_launch(d->gen, *f, grid, gdims, lo, hi, s, part, ready_lo, ready_hi);
+    if (rc != BK_EUNSUPPORTED || part != BK_PART_ALL || flags == BK_KERNEL_TILED) return rc;
   }
   if (steps != 1 || part != BK_PART_ALL) return BK_EUNSUPPORTED;  // general taps: whole-box single sweeps only
   const dim3 g(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
   if (g.x == 0 || g.y == 0 || g.z == 0) return BK_OK;
+  {
+    bk_stencil_def *md = const_cast<bk_stencil_def *>(d);
+    std::lock_guard<std::mutex> lk(md->mu);
+    if (!md->taps_dev) {
+      BK_CUDA(cudaMalloc(&md->taps_dev, sizeof(TapDev) * md->taps_host.size()));
+      BK_CUDA(cudaMemcpy(md->taps_dev, md->taps_host.data(), sizeof(TapDev) * md->taps_host.size(), cudaMemcpyHostToDevice));
+    }
+  }
   Select sel = {grid, nullptr, nullptr, gdims[0], gdims[1], {lo[0], lo[1], lo[2]}, 0};
   if (d->krad == 1) k_taps<1><<<g, 256, 0, s>>>(sel, *f, d->taps_dev, d->ntaps, d->pre, d->post);
   if (d->krad == 2) k_taps<2><<<g, 256, 0, s>>>(sel, *f, d->taps_dev, d->ntaps, d->pre, d->post);
   if (d->krad == 4) k_taps<4><<<g, 256, 0, s>>>(sel, *f, d->taps_dev, d->ntaps, d->pre, d->post);
   BK_LAUNCHED();
   return BK_OK;
+}
+
+int bk_stencil_def_source(const bk_stencil_def_t *d, char *buf, size_t cap, size_t *len) {
+  BK_REQUIRE(d, "null stencil");
+  const std::string &src = d->gen ? bk::gen_source(d->gen) : d->gen_why;
+  if (len) *len = src.size();
+  if (buf && cap) {
+    const size_t n = std::min(cap - 1, src.size());
+    memcpy(buf, src.data(), n);
+    buf[n] = 0;
+  }
+  return d->gen ? BK_OK : BK_EUNSUPPORTED;
 }
 
 int bk_stencil_def_apply(const bk_stencil_def_t *d, const bk_field_t *f, const unsigned *grid, const unsigned *gdims,

@@ -22,6 +22,7 @@
 // Summation order per output point (fixed): k-minus taps d=R..1, centre, i taps d=1..R (+d then -d), j taps d=1..R
 // (+d then -d), k-plus taps d=1..R.  Parity with the reference is to 1e-12 relative, not bitwise.
 #include "bk_common.h"
+#include <cstddef>
 #include <cstdint>
 #include <cstdlib>
 #include <type_traits>
@@ -38,78 +39,9 @@ namespace {
 
 using bk::StarCoef;
 
-struct TiledArgs {
-  const double *in;
-  double *out;
-  unsigned long long in_step, out_step;  // elements between consecutive bricks
-  const unsigned *grid;
-  int gx, gy, gz;  // grid extents in bricks
-  int lo[3], hi[3];
-  int ntx;  // tiles along i
-  int kl;   // brick layers per k segment
-  int kh, kt;  // split launches: thin head / tail segments (layers) that keep the ghost-dependent CTAs few; else 0
-  const bk_field_t *multi;  // strong-scaling launch: per-subdomain fields (device array), subdomain = blockIdx.z
-  // CTA enumeration: blockIdx.x runs through up to 6 boxes of the (tile i, tile j, k segment) space in order.  A plain
-  // launch has one box.  A split launch (bk_stencil_apply_part) runs either the CTAs whose whole read footprint lies
-  // inside the caller's "ready" brick box, or all the others -- the first part overlaps the ghost exchange, the second
-  // is enqueued behind it, and both use the tile decomposition of the full box (no thin slab launches).
-  int nbox;
-  struct Box {
-    int lo[3], dim[3], first;
-  } box[6];
-};
-
-// k range of segment `q`: [head of kh layers] [uniform segments of kl layers] [tail of kt layers]
-__host__ __device__ __forceinline__ void seg_range(const TiledArgs &a, int q, int &kb0, int &nl) {
-  const int nz = a.hi[2] - a.lo[2], mid = nz - a.kh - a.kt;
-  if (a.kh > 0) {
-    if (q == 0) {
-      kb0 = a.lo[2], nl = a.kh;
-      return;
-    }
-    --q;
-  }
-  if (q * a.kl < mid) {
-    kb0 = a.lo[2] + a.kh + q * a.kl;
-    nl = min(a.kl, mid - q * a.kl);
-  } else {
-    kb0 = a.hi[2] - a.kt, nl = a.kt;
-  }
-}
-
-// ---- PTX helpers ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      " .reg .pred p;\n"
-      " mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      " selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
+#include "bk_march_common.h"
+static_assert(sizeof(bk_field_dev) == sizeof(bk_field_t) && offsetof(bk_field_dev, out_step) == offsetof(bk_field_t, out_step),
+              "bk_field_dev restates bk_field_t");
 
 // ---- compile-time geometry --------------------------------------------------------------------------------------
 template <int R_, int YT_, int TI_, int TJ_, int G_, int D_, int MAXREG_ = 255, int NPW_ = 1, bool CUBE_ = false,
@@ -159,7 +91,7 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
   double *fout = a.out;
   size_t in_step = a.in_step, out_step = a.out_step;
   if (a.multi) {  // strong/main.cu:85-99: many subdomains share grid and adjacency, each has its own storages
-    const bk_field_t f = a.multi[blockIdx.z];
+    const bk_field_dev f = a.multi[blockIdx.z];
     fin = f.in, fout = f.out, in_step = f.in_step, out_step = f.out_step;
   }
   const int tid = threadIdx.x;
@@ -591,7 +523,7 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_star2(const __grid_constant_
   double *fout = a.out;
   size_t in_step = a.in_step, out_step = a.out_step;
   if (a.multi) {
-    const bk_field_t f = a.multi[blockIdx.z];
+    const bk_field_dev f = a.multi[blockIdx.z];
     fin = f.in, fout = f.out, in_step = f.in_step, out_step = f.out_step;
   }
   const int tid = threadIdx.x;
@@ -994,41 +926,19 @@ int pick_segment_layers(long tiles, int nz, int slots, int ovh) {
   return best_kl;
 }
 
-template <class C>
-int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, unsigned nsub, int part,
-               const int *rdy_lo, const int *rdy_hi) {
-  void (*kern)(const TiledArgs, const typename C::Coef);
-  if constexpr (C::FUSED) kern = k_star2<C>;
-  else if constexpr (C::CREG > 0) kern = k_star_rebal<C>;
-  else if constexpr (C::MAXREG < 255) kern = k_star_capped<C>;
-  else kern = k_star<C>;
-  BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
-  if (getenv("BK_DEBUG")) {
-    cudaFuncAttributes fa;
-    int nb = -1;
-    cudaFuncGetAttributes(&fa, kern);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::NT, C::SMEM);
-    fprintf(stderr, "[bk] %s R=%d YT=%d tile=%dx%d D=%d: %d thr, %d regs, %zu B smem, %zu B local, %d CTA/SM\n",
-            C::FUSED ? "k_star2" : "k_star", C::R, C::YT, C::TI, C::TJ, C::D, C::NT, fa.numRegs, C::SMEM, fa.localSizeBytes, nb);
-  }
+// The launch of a marching kernel of tile TI x TJ bricks: k segments (cost model above), the CTA boxes of a whole or
+// split launch, then `launch(grid, args)`.  Shared by the compiled-in kernels (launch_cfg) and the generated ones.
+struct Geom {
+  int TI, TJ, OVH;
+};
+template <class LaunchFn>
+int launch_geom(const Geom &g, int slots, const TiledArgs &a0, unsigned nsub, int part, const int *rdy_lo, const int *rdy_hi,
+                LaunchFn &&launch) {
   TiledArgs a = a0;
   const int nx = a.hi[0] - a.lo[0], ny = a.hi[1] - a.lo[1], nz = a.hi[2] - a.lo[2];
   if (nx <= 0 || ny <= 0 || nz <= 0) return BK_OK;
-  a.ntx = (nx + C::TI - 1) / C::TI;
-  const int nty = (ny + C::TJ - 1) / C::TJ;
-  // k segments: every CTA streams kl*8 + 2*RUP planes and the launch takes ceil(CTAs / resident slots) rounds, so pick
-  // the segment count that minimises rounds * planes (long segments amortise the halo planes, short ones fill the
-  // last round)
-  static std::atomic<int> slots_cached{0};  // several rank threads (drivers/*) may get here at once: benign double init
-  int slots = slots_cached.load(std::memory_order_relaxed);
-  if (!slots) {
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, C::NT, C::SMEM);
-    slots = sms * (per_sm > 0 ? per_sm : 1);
-    slots_cached.store(slots, std::memory_order_relaxed);
-  }
+  a.ntx = (nx + g.TI - 1) / g.TI;
+  const int nty = (ny + g.TJ - 1) / g.TJ;
   // split launches: the layers whose CTAs read not-yet-ready bricks get thin segments of their own, so that the READY
   // part (which overlaps the exchange) is as large as possible
   a.kh = a.kt = 0;
@@ -1040,14 +950,17 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, 
     if (nz - a.kh - a.kt <= 0) a.kh = a.kt = 0;
   }
   const int nmid = nz - a.kh - a.kt;
-  a.kl = pick_segment_layers((long) a.ntx * nty * nsub, nmid, slots, C::OVH);
+  // k segments: every CTA streams kl*8 + 2*RUP planes and the launch takes ceil(CTAs / resident slots) rounds, so pick
+  // the segment count that minimises rounds * planes (long segments amortise the halo planes, short ones fill the
+  // last round)
+  a.kl = pick_segment_layers((long) a.ntx * nty * nsub, nmid, slots, g.OVH);
   if (const char *e = getenv("BK_STAR_KL")) a.kl = atoi(e) > 0 ? atoi(e) : a.kl;  // developer knob
   const int segs = (nmid + a.kl - 1) / a.kl + (a.kh > 0) + (a.kt > 0);
   // CTA boxes.  "inner" = CTAs whose whole read footprint (tile + 1 brick all round) lies in the ready box
   int in_lo[3] = {0, 0, 0}, in_hi[3] = {0, 0, 0};
   const int ext[3] = {a.ntx, nty, segs};
   if (part != BK_PART_ALL) {
-    const int T[2] = {C::TI, C::TJ};
+    const int T[2] = {g.TI, g.TJ};
     for (int d = 0; d < 2; ++d) {
       int l = 0, h = ext[d];
       while (l < h && a.lo[d] + l * T[d] - 1 < rdy_lo[d]) ++l;
@@ -1087,10 +1000,46 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, 
     add_box(0, ext[0], 0, ext[1], in_hi[2], ext[2]);
   }
   if (first == 0) return BK_OK;
-  dim3 grid((unsigned) first, 1, nsub);
-  kern<<<grid, C::NT, C::SMEM, s>>>(a, cf);
-  BK_LAUNCHED();
-  return BK_OK;
+  return launch(dim3((unsigned) first, 1, nsub), a);
+}
+
+int device_slots(const void *kern, int threads, size_t smem) {
+  int dev = 0, sms = 148, per_sm = 1;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+  return sms * (per_sm > 0 ? per_sm : 1);
+}
+
+template <class C>
+int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, unsigned nsub, int part,
+               const int *rdy_lo, const int *rdy_hi) {
+  void (*kern)(const TiledArgs, const typename C::Coef);
+  if constexpr (C::FUSED) kern = k_star2<C>;
+  else if constexpr (C::CREG > 0) kern = k_star_rebal<C>;
+  else if constexpr (C::MAXREG < 255) kern = k_star_capped<C>;
+  else kern = k_star<C>;
+  BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
+  if (getenv("BK_DEBUG")) {
+    cudaFuncAttributes fa;
+    int nb = -1;
+    cudaFuncGetAttributes(&fa, kern);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, C::NT, C::SMEM);
+    fprintf(stderr, "[bk] %s R=%d YT=%d tile=%dx%d D=%d: %d thr, %d regs, %zu B smem, %zu B local, %d CTA/SM\n",
+            C::FUSED ? "k_star2" : "k_star", C::R, C::YT, C::TI, C::TJ, C::D, C::NT, fa.numRegs, C::SMEM, fa.localSizeBytes, nb);
+  }
+  static std::atomic<int> slots_cached{0};  // several rank threads (drivers/*) may get here at once: benign double init
+  int slots = slots_cached.load(std::memory_order_relaxed);
+  if (!slots) {
+    slots = device_slots((const void *) kern, C::NT, C::SMEM);
+    slots_cached.store(slots, std::memory_order_relaxed);
+  }
+  const Geom g = {C::TI, C::TJ, C::OVH};
+  return launch_geom(g, slots, a0, nsub, part, rdy_lo, rdy_hi, [&](dim3 grid, const TiledArgs &a) -> int {
+    kern<<<grid, C::NT, C::SMEM, s>>>(a, cf);
+    BK_LAUNCHED();
+    return BK_OK;
+  });
 }
 
 }  // namespace
@@ -1107,7 +1056,7 @@ int launch_tiled(const CoefSpec &spec, const bk_field_t &f, const bk_field_t *mu
   a.gx = (int) gdims[0], a.gy = (int) gdims[1], a.gz = (int) gdims[2];
   for (int d = 0; d < 3; ++d) a.lo[d] = (int) lo[d], a.hi[d] = (int) hi[d];
   a.ntx = a.kl = a.kh = a.kt = 0;
-  a.multi = multi_dev;
+  a.multi = reinterpret_cast<const bk_field_dev *>(multi_dev);
   a.nbox = 0;
   int rdy_lo[3] = {0, 0, 0}, rdy_hi[3] = {0, 0, 0};
   if (part != BK_PART_ALL)
@@ -1163,5 +1112,35 @@ int launch_tiled(const CoefSpec &spec, const bk_field_t &f, const bk_field_t *mu
   }
   return launch_cfg<Cfg<4, 2, 6, 4, 2, 3, 255, 4, false, 152, 40>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
 }
+
+
+// A kernel generated by bk_codegen.cu (cudaKernel_t from cudaLibraryGetKernel): same launch descriptor, same CTA
+// enumeration, coefficients passed by value as the kernel's second parameter (`coef`, `coef_bytes`).
+int launch_generated(const void *kernel, const GenGeom &gg, const void *coef, const bk_field_t &f, const unsigned *grid,
+                     const unsigned *gdims, const unsigned *lo, const unsigned *hi, cudaStream_t s, int part,
+                     const unsigned *ready_lo, const unsigned *ready_hi) {
+  if (((size_t) f.in | (size_t) f.out) & 15 || (f.in_step & 1) || (f.out_step & 1)) return BK_EUNSUPPORTED;
+  TiledArgs a;
+  a.in = f.in, a.out = f.out, a.in_step = f.in_step, a.out_step = f.out_step, a.grid = grid;
+  a.gx = (int) gdims[0], a.gy = (int) gdims[1], a.gz = (int) gdims[2];
+  for (int d = 0; d < 3; ++d) a.lo[d] = (int) lo[d], a.hi[d] = (int) hi[d];
+  a.ntx = a.kl = a.kh = a.kt = 0;
+  a.multi = nullptr;
+  a.nbox = 0;
+  int rdy_lo[3] = {0, 0, 0}, rdy_hi[3] = {0, 0, 0};
+  if (part != BK_PART_ALL)
+    for (int d = 0; d < 3; ++d) rdy_lo[d] = (int) ready_lo[d], rdy_hi[d] = (int) ready_hi[d];
+  BK_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) gg.smem));
+  const int slots = device_slots(kernel, gg.threads, gg.smem);
+  const Geom g = {gg.TI, gg.TJ, gg.ovh};
+  return launch_geom(g, slots, a, 1, part, rdy_lo, rdy_hi, [&](dim3 cta_grid, const TiledArgs &args) -> int {
+    void *params[2] = {const_cast<TiledArgs *>(&args), const_cast<void *>(coef)};
+    BK_CUDA(cudaLaunchKernel(kernel, cta_grid, dim3((unsigned) gg.threads), params, gg.smem, s));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return BK_OK;
+  });
+}
+
+size_t tiled_args_bytes() { return sizeof(TiledArgs); }
 
 }  // namespace bk

@@ -124,7 +124,7 @@ def lower(name_or_path, consts=None):
 
 class CompiledStencil:
     """a stencil lowered from a script and compiled by bk_stencil_compile; apply() is the brick_kernel launch"""
-    KINDS = {0: "star", 1: "cube", 2: "taps"}
+    KINDS = {0: "star", 1: "cube", 2: "taps", 3: "generated"}
 
     def __init__(self, name_or_path, consts=None):
         taps, sc = lower(name_or_path, consts)
@@ -166,6 +166,16 @@ class CompiledStencil:
     def apply(self, grid, b_in, b_out, lo=None, hi=None, kernel=_lib.KERNEL_AUTO, stream=None):
         self.advance(1, grid, b_in, b_out, lo, hi, None, _lib.PART_ALL, kernel, stream)
 
+    def source(self):
+        """the CUDA source the library generated for this stencil (kind "generated": a marching kernel specialised to the
+        tap pattern, compiled with NVRTC -- the counterpart of the text codegen/vecscatter prints); None otherwise"""
+        n = C.c_size_t()
+        if load().bk_stencil_def_source(self._h, None, 0, C.byref(n)) != _lib.BK_OK:
+            return None
+        buf = C.create_string_buffer(n.value + 1)
+        check(load().bk_stencil_def_source(self._h, buf, n.value + 1, None))
+        return buf.value.decode()
+
     def __del__(self):
         try:
             load().bk_stencil_def_destroy(self._h)
@@ -197,13 +207,19 @@ def _main(argv):
     ap.add_argument("script")
     ap.add_argument("--const", action="append", default=[], metavar="NAME=VALUE[,VALUE...]")
     ap.add_argument("--emit-c", metavar="SYMBOL")
+    ap.add_argument("--emit-cuda", action="store_true", help="print the CUDA kernel the library generates for the script")
     a = ap.parse_args(argv)
     consts = {}
     for kv in a.const:
         k, v = kv.split("=", 1)
         vals = [float(x) for x in v.split(",")]
         consts[k] = vals if len(vals) > 1 else vals[0]
-    if a.emit_c:
+    if a.emit_cuda:
+        src = CompiledStencil(a.script, consts).source()
+        if src is None:
+            raise SystemExit("this script lowers to a built-in kernel (star / symmetric cube): nothing is generated")
+        sys.stdout.write(src)
+    elif a.emit_c:
         sys.stdout.write(emit_c(a.script, a.emit_c, consts))
     else:
         import json

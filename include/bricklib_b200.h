@@ -225,7 +225,12 @@ int bk_stencil_apply_multi(int stencil, const bk_field_t *fields_dev, unsigned n
  * (bricklib_b200/dsl.py evaluates the same scripts) and bk_stencil_compile picks the kernel family:
  *   BK_KIND_STAR  taps on the axes only, radius <= 4, ANY coefficients  -> marching kernels (k_star / k_star2)
  *   BK_KIND_CUBE  radius <= 2, coefficient a function of the sorted (|di|,|dj|,|dk|) -> marching cube kernel
- *   BK_KIND_TAPS  anything else with radius <= 4 -> per-brick kernel walking a tap table (k_taps)
+ *   BK_KIND_GENERATED  anything else with radius <= 4: the library EMITS CUDA source for a marching kernel specialised to
+ *                 the tap pattern (tap loop unrolled into straight-line FMAs, coefficient values stay kernel
+ *                 parameters), compiles it for sm_100a with NVRTC and launches it through the same CTA enumeration as
+ *                 the built-in kernels -- the role codegen/vecscatter:145-175 + codegen/st/codegen/backend/cuda.py play
+ *                 in the reference.  bk_stencil_def_source returns the text.
+ *   BK_KIND_TAPS  fallback when NVRTC is unavailable (or BK_NO_CODEGEN is set): per-brick kernel walking a tap table
  * Repeated offsets are merged, zero coefficients dropped.  BK_EUNSUPPORTED for radius > 4. */
 typedef struct {
   int di, dj, dk;
@@ -235,11 +240,12 @@ typedef struct bk_stencil_def bk_stencil_def_t;
 #define BK_KIND_STAR 0
 #define BK_KIND_CUBE 1
 #define BK_KIND_TAPS 2
+#define BK_KIND_GENERATED 3 /* a marching kernel GENERATED for this tap pattern and compiled with NVRTC (see below) */
 int bk_stencil_compile(bk_stencil_def_t **def, const bk_tap_t *taps_host, int ntaps);
 /* The two non-linearities a stencil script may carry and a kernel applies for free (stencils/cond.py uses both):
  *     out = post( sum_t c_t * pre( in(. + d_t) ) )
  * pre clamps every value read (cond.py: max(in, 0.0)), post clamps the sum (cond.py: If(calc > 0, calc, -calc) = abs).
- * NULL or op BK_OP_NONE = identity.  Such stencils always run on the per-brick tap-table kernel (BK_KIND_TAPS). */
+ * NULL or op BK_OP_NONE = identity.  Such stencils run on a generated kernel (BK_KIND_GENERATED) or the tap-table kernel. */
 #define BK_OP_NONE 0
 #define BK_OP_MAX 1 /* max(x, c) */
 #define BK_OP_MIN 2 /* min(x, c) */
@@ -251,6 +257,9 @@ typedef struct {
 int bk_stencil_compile_pointwise(bk_stencil_def_t **def, const bk_tap_t *taps_host, int ntaps, const bk_pointwise_t *pre,
                                  const bk_pointwise_t *post);
 int bk_stencil_def_destroy(bk_stencil_def_t *def);
+/* the generated CUDA source of a BK_KIND_GENERATED stencil, NUL-terminated, truncated to cap; *len = full length.  For
+ * other kinds: BK_EUNSUPPORTED and the reason no kernel was generated (empty for star / cube). */
+int bk_stencil_def_source(const bk_stencil_def_t *def, char *buf, size_t cap, size_t *len);
 /* any out pointer may be NULL; st_iter = 8 / radius (sweeps per exchange at ghost depth 8); fused_steps as bk_stencil_fused_steps */
 int bk_stencil_def_info(const bk_stencil_def_t *def, int *kind, int *radius, int *ntaps, int *st_iter, int *fused_steps);
 /* = bk_stencil_apply / bk_stencil_advance for a compiled stencil (flags: BK_KERNEL_*) */

@@ -126,6 +126,24 @@ def test_nonlinear_and_malformed_scripts_are_refused(tmp_path):
         dsl.lower(str(p))
 
 
+def test_generator_emits_and_compiles_a_specialised_kernel_without_a_gpu(monkeypatch):
+    """a script that is neither a star nor the symmetric cube becomes CUDA source specialised to its taps, compiled for
+    sm_100a by NVRTC at bk_stencil_compile time (no device needed); BK_NO_CODEGEN keeps the tap-table kernel"""
+    cs = bk.compile_stencil(os.path.join(HERE, "box27_skewed.py"))
+    assert cs.kind == "generated" and cs.ntaps == 27
+    src = cs.source()
+    assert 'extern "C" __global__' in src and "bk_gen" in src and "cp.async.bulk" in src
+    assert src.count("fma(cf.c[") == 27 * 2 * 2 * 3          # taps x cells of an x-pair x rows per thread x k slots
+    assert "cf.c[26]" in src and "cf.c[27]" not in src and "#define WS 3" in src
+    up = bk.compile_stencil(os.path.join(HERE, "upwind.py"), {"W": 0.3})
+    assert up.kind == "generated" and "#define WS 7" in up.source() and "#define RY 2" in up.source()
+    cond = bk.compile_stencil("cond", {"coeff": COEFF7})
+    assert cond.kind == "generated" and "fmax(" in cond.source() and "fabs(" in cond.source()
+    assert bk.compile_stencil("mpi13pt").source() is None      # built-in star kernel: nothing generated
+    monkeypatch.setenv("BK_NO_CODEGEN", "1")
+    assert bk.compile_stencil(os.path.join(HERE, "box27_skewed.py")).kind == "taps"
+
+
 # ---- GPU: compiled stencils against the oracle ---------------------------------------------------------------------
 PAD = GZ = 8
 
@@ -159,8 +177,8 @@ def rel(a, b):
     ("mpi25pt", None, "star", 4), ("mpi125pt", None, "cube", 2),
     (os.path.join(HERE, "star3.py"), {"c": [0.05 * (n + 1) for n in range(19)]}, "star", 3),
     (os.path.join(HERE, "box27.py"), {"w0": 0.2, "w1": 0.05, "w2": 0.02, "w3": 0.0325}, "cube", 1),
-    (os.path.join(HERE, "box27_skewed.py"), None, "taps", 1),
-    (os.path.join(HERE, "upwind.py"), {"W": 0.3}, "taps", 3),
+    (os.path.join(HERE, "box27_skewed.py"), None, "generated", 1),
+    (os.path.join(HERE, "upwind.py"), {"W": 0.3}, "generated", 3),
 ])
 def test_compiled_stencils_against_the_oracle(script, consts, kind, radius):
     from oracle import schedule as S
@@ -178,13 +196,78 @@ def test_compiled_stencils_against_the_oracle(script, consts, kind, radius):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(6))
+def test_generated_kernels_for_random_tap_sets(seed):
+    """random offsets (asymmetric k ranges, plane-only stencils, corners or not) and coefficients: generated marching
+    kernel == per-brick tap-table kernel == numpy, including a split (READY + REST) launch of the generated kernel"""
+    from oracle import schedule as S
+    rng = np.random.default_rng(100 + seed)
+    rx, ry = rng.integers(0, 5), rng.integers(0, 5)
+    zlo, zhi = sorted(rng.integers(-4, 5, size=2))
+    if seed == 0:
+        zlo = zhi = 0                      # a purely in-plane stencil
+    if seed == 1:
+        rx, ry, zlo, zhi = 1, 1, -1, 1     # the dense 27-point box
+    if seed == 1:
+        offs = [(i, j, k) for k in (-1, 0, 1) for j in (-1, 0, 1) for i in (-1, 0, 1)]
+    else:
+        n = int(rng.integers(3, 30))
+        offs = {(int(rng.integers(-rx, rx + 1)), int(rng.integers(-ry, ry + 1)), int(rng.integers(zlo, zhi + 1)))
+                for _ in range(n)}
+        offs = sorted(offs | {(int(rx), 0, int(zhi)), (0, -int(ry), int(zlo))})
+    taps = [(o, float(rng.uniform(0.05, 1))) for o in offs]   # positive weights: no cancellation, the relative metric is meaningful
+    from bricklib_b200 import _lib
+    import ctypes as C
+    arr_t = (_lib.Tap * len(taps))(*[_lib.Tap(o[0], o[1], o[2], c) for o, c in taps])
+    h = C.c_void_p()
+    _lib.check(bk.load().bk_stencil_compile(C.byref(h), arr_t, len(taps)))
+    kind = C.c_int()
+    bk.load().bk_stencil_def_info(h, C.byref(kind), None, None, None, None)
+    star = all(sum(x != 0 for x in o) <= 1 for o, _ in taps)
+    assert kind.value == (0 if star else 3)
+    dims = (40, 24, 32)
+    d = bk.BrickDecomp(dims, 8)
+    info, grid = d.getBrickInfo(), bk.DeviceGrid(d.grid)
+    s_in, s_a, s_b, s_c = (info.allocate(512) for _ in range(4))
+    host = rng.random(d.nbricks * 512)
+    host[:512] = 0
+    s_in.from_host(host)
+    b_in, b_a, b_b, b_c = (bk.Brick(info, s) for s in (s_in, s_a, s_b, s_c))
+    f_ab = bk.core._field(b_in, b_a)
+    t = grid.dims
+    lo, hi = (0, 0, 0), t
+    own = ((1, 1, 1), tuple(x - 1 for x in t))
+    u3 = bk.core._u3
+    L = bk.load()
+    _lib.check(L.bk_stencil_def_advance(h, 1, C.byref(f_ab), grid.dev.ptr, u3(t), u3(lo), u3(hi), None, None, 0, bk.KERNEL_AUTO, None))
+    f_b = bk.core._field(b_in, b_b)
+    _lib.check(L.bk_stencil_def_advance(h, 1, C.byref(f_b), grid.dev.ptr, u3(t), u3(lo), u3(hi), None, None, 0, bk.KERNEL_BRICK, None))
+    f_c = bk.core._field(b_in, b_c)
+    for part in (bk.PART_READY | bk.PART_THIN, bk.PART_REST | bk.PART_THIN):
+        _lib.check(L.bk_stencil_def_advance(h, 1, C.byref(f_c), grid.dev.ptr, u3(t), u3(lo), u3(hi), u3(own[0]), u3(own[1]), part,
+                                            bk.KERNEL_AUTO, None))
+    bk.device_sync()
+    a, b, c = s_a.to_host(), s_b.to_host(), s_c.to_host()
+    assert np.array_equal(a, c)                                       # split launch == whole launch, bit for bit
+    assert float(np.abs(a - b).max()) < 1e-13                          # generated == tap-table kernel
+    # against numpy on the interior bricks (the shell reads the null brick where the reference reads the same zeros)
+    g = d.grid
+    full = host.reshape(-1, 8, 8, 8)[g].transpose(0, 3, 1, 4, 2, 5).reshape(g.shape[0] * 8, g.shape[1] * 8, g.shape[2] * 8)
+    got = a.reshape(-1, 8, 8, 8)[g].transpose(0, 3, 1, 4, 2, 5).reshape(full.shape)
+    o = 8
+    want = S.taps_sweep(full, taps, (o, o, o), tuple(x - o for x in full.shape[::-1]))
+    assert rel(got[o:-o, o:-o, o:-o], want[o:-o, o:-o, o:-o]) < 1e-12
+    L.bk_stencil_def_destroy(h)
+
+
+@pytest.mark.gpu
 def test_compiled_cond_stencil_against_the_reference_fixture():
     """stencils/cond.py on the GPU against one sweep of the reference's own generated code (tests/golden/cond_sweep.npz,
     oracle/gen_golden_cond.py), and against the numpy restatement on a larger field"""
     from oracle import schedule as S
     z = np.load(os.path.join(ROOT, "tests", "golden", "cond_sweep.npz"))
     cs = bk.compile_stencil("cond", {"coeff": z["coeff"]})
-    assert cs.kind == "taps" and cs.pre == ("max", 0.0) and cs.post == ("abs", 0.0)
+    assert cs.kind == "generated" and cs.pre == ("max", 0.0) and cs.post == ("abs", 0.0)
     o = PAD + GZ
     got = run_compiled(cs, z["input"], (16, 16, 16))
     for label, res in got.items():

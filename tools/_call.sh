@@ -1,5 +1,5 @@
-timeout 900 python -m pytest tests/test_gpu_array.py -m gpu -x -q 2>&1 | tail -15 > gpurun_out/c7_pytest.log
-tail -15 gpurun_out/c7_pytest.log
-drivers/weak -s 512,512,512 -I 10 -g 1 -S mpi7pt 2>&1 | tee gpurun_out/c7_weak7.log | grep -E "^Arr|^Bri|perf|Arr =="
-drivers/weak -s 512,512,512 -I 10 -g 1 -S mpi25pt 2>&1 | tee gpurun_out/c7_weak25.log | grep -E "^Arr|^Bri|perf|Arr =="
-drivers/weak -s 512,512,512 -I 10 -g 1 -S mpi125pt 2>&1 | tee gpurun_out/c7_weak125.log | grep -E "^Arr|^Bri|perf|Arr =="
+timeout 600 python -m pytest tests/test_dsl.py -m gpu -x -q 2>&1 | tail -12 > gpurun_out/c8_pytest.log
+tail -12 gpurun_out/c8_pytest.log
+BK_DEBUG=1 python tools/gen_bench.py --brick 2>&1 | grep -v "k_star" | tee gpurun_out/c8_gen.log
+BK_GEN_MINB=1 BK_DEBUG=1 python tools/gen_bench.py 2>&1 | grep -v "k_star" | tee gpurun_out/c8_gen_minb1.log
+BK_GEN_MINB=2 BK_DEBUG=1 python tools/gen_bench.py 2>&1 | grep -v "k_star" | tee gpurun_out/c8_gen_minb2.log
