@@ -110,6 +110,7 @@ SIGNATURES = {
     "bk_synthetic_value": (C.c_double, [u64, u64]),
     "bk_compare_storage": (C.c_int, [vp, up, up, up, vp, sz, vp, sz, C.c_double, C.POINTER(C.c_ulonglong), dp, vp]),
     "bk_stencil_apply": (C.c_int, [C.c_int, C.POINTER(Field), vp, up, up, up, dp, C.c_uint, vp]),
+    "bk_adjacency_forget": (C.c_int, [vp]),
     "bk_stencil_apply_part": (C.c_int, [C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp]),
     "bk_stencil_advance": (C.c_int, [C.c_int, C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp]),
     "bk_stencil_apply_list": (C.c_int, [C.c_int, C.POINTER(Field), vp, sz, dp, vp]),

@@ -77,6 +77,7 @@ int bk_dev_alloc(void **dev, size_t bytes) {
   return BK_OK;
 }
 int bk_dev_free(void *dev) {
+  if (dev) bk_adjacency_forget(dev);  // verdicts about an adjacency list / grid at this address die with the allocation
   BK_CUDA(cudaFree(dev));
   return BK_OK;
 }

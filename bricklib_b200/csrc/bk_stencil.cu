@@ -16,6 +16,7 @@
 #include <array>
 #include <cstdlib>
 #include <cstring>
+#include <iterator>
 #include <map>
 #include <mutex>
 #include <string>
@@ -248,6 +249,90 @@ __global__ void __launch_bounds__(256) k_taps(Select sel, bk_field_t f, const Ta
   f.out[(size_t) b * f.out_step + e1] = pointwise(a1, post.op, post.c);
 }
 
+// ---- is the dense grid a faithful picture of the adjacency list? -------------------------------------------------------
+// The marching kernels (built-in and generated) take neighbour ids from the dense `grid` array and read brick 0 outside
+// it; the reference's accessor -- and k_brick / k_taps here -- follow BrickInfo::adj (include/brick.h:234-246).  The two
+// agree for every grid the drivers build (BrickDecomp, the interior of init_grid), but a caller may hand in ANY adjacency
+// (periodic wrap, holes).  So before a (adj, grid, box) triple is first swept by a marching kernel, one small kernel
+// checks  adj[grid[p]][s] == grid[p + delta_s]  (0 outside the grid) for every position p the launch's reads start from
+// and every neighbour slot s the stencil uses; the verdict is cached.  On a mismatch BK_KERNEL_AUTO falls back to the
+// adjacency-following family and BK_KERNEL_TILED reports BK_EUNSUPPORTED -- never silently different numbers.
+__global__ void __launch_bounds__(256) k_check_adj(const unsigned *__restrict__ adj, const unsigned *__restrict__ grid, int gx, int gy,
+                                                   int gz, int lx, int ly, int lz, int nx, int ny, int nz, unsigned slots,
+                                                   unsigned *bad) {
+  const long n = (long) nx * ny * nz * 27;
+  for (long t = blockIdx.x * 256L + threadIdx.x; t < n; t += (long) gridDim.x * 256) {
+    const int s = (int) (t % 27);
+    if (!((slots >> s) & 1)) continue;
+    long r = t / 27;
+    const int i = lx + (int) (r % nx), j = ly + (int) ((r / nx) % ny), k = lz + (int) (r / ((long) nx * ny));
+    const unsigned id = grid[((size_t) k * gy + j) * gx + i];
+    if (id == 0) continue;  // the null brick is never an output; what is read THROUGH it is zero either way
+    const int qi = i + s % 3 - 1, qj = j + (s / 3) % 3 - 1, qk = k + s / 9 - 1;
+    const bool in = qi >= 0 && qi < gx && qj >= 0 && qj < gy && qk >= 0 && qk < gz;
+    const unsigned want = in ? grid[((size_t) qk * gy + qj) * gx + qi] : 0u;
+    if (adj[(size_t) id * 27 + s] != want) atomicAdd(bad, 1u);
+  }
+}
+
+struct AdjKey {
+  const void *a, *g;
+  unsigned d[3], l[3], h[3], slots;
+  bool operator<(const AdjKey &o) const { return memcmp(this, &o, sizeof(AdjKey)) < 0; }
+};
+std::mutex adj_mu;
+std::map<AdjKey, int> adj_cache;
+
+constexpr unsigned kSlotsStar = (1u << 13) | (1u << 12) | (1u << 14) | (1u << 10) | (1u << 16) | (1u << 4) | (1u << 22);
+constexpr unsigned kSlotsAll = (1u << 27) - 1;
+
+// 1 = grid and adjacency agree on everything a marching launch over [lo,hi) reads (expanded by `grow` bricks for the
+// two-step kernel, whose first step runs on the neighbours too), 0 = they differ, negative = CUDA error
+int marching_matches_adjacency(const unsigned *adj, const unsigned *grid, const unsigned *gdims, const unsigned *lo,
+                               const unsigned *hi, int grow, unsigned slots, cudaStream_t s) {
+  if (getenv("BK_SKIP_ADJ_CHECK")) return 1;  // developer knob
+  using Key = AdjKey;
+  std::mutex &mu = adj_mu;
+  std::map<AdjKey, int> &cache = adj_cache;
+  Key key;
+  memset(&key, 0, sizeof(key));
+  key.a = adj, key.g = grid, key.slots = slots;
+  for (int d = 0; d < 3; ++d) {
+    key.d[d] = gdims[d];
+    key.l[d] = lo[d] > (unsigned) grow ? lo[d] - grow : 0;
+    key.h[d] = std::min(gdims[d], hi[d] + grow);
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+  }
+  const int nx = (int) (key.h[0] - key.l[0]), ny = (int) (key.h[1] - key.l[1]), nz = (int) (key.h[2] - key.l[2]);
+  int verdict = 1;
+  if (nx > 0 && ny > 0 && nz > 0) {
+    unsigned *bad = nullptr, host = 0;
+    BK_CUDA(cudaMalloc(&bad, sizeof(unsigned)));
+    BK_CUDA(cudaMemsetAsync(bad, 0, sizeof(unsigned), s));
+    const long n = (long) nx * ny * nz * 27;
+    k_check_adj<<<(unsigned) std::min<long>((n + 255) / 256, 148 * 16), 256, 0, s>>>(adj, grid, (int) gdims[0], (int) gdims[1],
+                                                                                  (int) gdims[2], (int) key.l[0], (int) key.l[1],
+                                                                                  (int) key.l[2], nx, ny, nz, slots, bad);
+    BK_LAUNCHED();
+    BK_CUDA(cudaMemcpyAsync(&host, bad, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    BK_CUDA(cudaStreamSynchronize(s));
+    BK_CUDA(cudaFree(bad));
+    verdict = host == 0;
+  }
+  std::lock_guard<std::mutex> lk(mu);
+  cache[key] = verdict;
+  return verdict;
+}
+
+int adjacency_mismatch() {
+  bk::set_error("the dense grid does not match the adjacency list: use bk_stencil_apply (it follows the adjacency) for this brick set");
+  return BK_EUNSUPPORTED;
+}
+
 int check_box(const unsigned *gdims, const unsigned *lo, const unsigned *hi) {
   for (int a = 0; a < 3; ++a)
     if (!(lo[a] <= hi[a] && hi[a] <= gdims[a])) return BK_EINVAL;
@@ -258,6 +343,13 @@ int check_box(const unsigned *gdims, const unsigned *lo, const unsigned *hi) {
 }  // namespace
 
 extern "C" {
+
+int bk_adjacency_forget(const void *adj_or_grid_dev) {
+  std::lock_guard<std::mutex> lk(adj_mu);
+  for (auto it = adj_cache.begin(); it != adj_cache.end();)
+    it = (!adj_or_grid_dev || it->first.a == adj_or_grid_dev || it->first.g == adj_or_grid_dev) ? adj_cache.erase(it) : std::next(it);
+  return BK_OK;
+}
 
 int bk_stencil_radius(int s) {
   static const int r[BK_ST_COUNT] = {1, 1, 2, 4, 2};
@@ -279,8 +371,15 @@ int bk_stencil_points(int s) {
 static int apply_spec(const bk::CoefSpec &spec, const bk_field_t *f, const unsigned *grid, const unsigned *gdims,
                       const unsigned *lo, const unsigned *hi, unsigned flags, cudaStream_t s) {
   if (flags != BK_KERNEL_BRICK) {
-    int rc = bk::launch_tiled(spec, *f, nullptr, 1, grid, gdims, lo, hi, s);
-    if (rc != BK_EUNSUPPORTED || flags == BK_KERNEL_TILED) return rc;
+    const int ok = marching_matches_adjacency(f->adj, grid, gdims, lo, hi, 0, spec.kind == 1 ? kSlotsAll : kSlotsStar, s);
+    if (ok < 0) return ok;
+    if (ok) {
+      int rc = bk::launch_tiled(spec, *f, nullptr, 1, grid, gdims, lo, hi, s);
+      if (rc != BK_EUNSUPPORTED || flags == BK_KERNEL_TILED) return rc;
+    } else if (flags == BK_KERNEL_TILED) {
+      bk::set_error("the dense grid does not match the adjacency list: the marching kernels would read other neighbours");
+      return BK_EUNSUPPORTED;
+    }
   }
   Select sel = {grid, nullptr, nullptr, gdims[0], gdims[1], {lo[0], lo[1], lo[2]}, 0};
   return launch_brick(spec, sel, *f, dim3(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]), s);
@@ -312,6 +411,8 @@ int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid
   // only the marching kernel has the split enumeration; the caller falls back to whole-box launches on EUNSUPPORTED
   bk::CoefSpec spec;
   if (bk::coef_spec_for(stencil, coeff, &spec) != BK_OK) return BK_EINVAL;
+  const int ok = marching_matches_adjacency(f->adj, grid, gdims, lo, hi, 0, spec.kind == 1 ? kSlotsAll : kSlotsStar, (cudaStream_t) stream);
+  if (ok <= 0) return ok < 0 ? ok : adjacency_mismatch();
   return bk::launch_tiled(spec, *f, nullptr, 1, grid, gdims, lo, hi, (cudaStream_t) stream, part, ready_lo, ready_hi);
 }
 
@@ -329,6 +430,9 @@ int bk_stencil_advance(int stencil, int steps, const bk_field_t *f, const unsign
   BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
   bk::CoefSpec spec;
   if (bk::coef_spec_for(stencil, coeff, &spec) != BK_OK) return BK_EINVAL;
+  const int ok = marching_matches_adjacency(f->adj, grid, gdims, lo, hi, steps - 1, spec.kind == 1 ? kSlotsAll : kSlotsStar,
+                                            (cudaStream_t) stream);
+  if (ok <= 0) return ok < 0 ? ok : adjacency_mismatch();
   return bk::launch_tiled(spec, *f, nullptr, 1, grid, gdims, lo, hi, (cudaStream_t) stream, part, ready_lo, ready_hi,
                           steps);
 }
@@ -500,13 +604,21 @@ int bk_stencil_def_advance(const bk_stencil_def_t *d, int steps, const bk_field_
   cudaStream_t s = (cudaStream_t) stream;
   if (d->kind == BK_KIND_STAR || d->kind == BK_KIND_CUBE) {
     if (steps == 1 && part == BK_PART_ALL) return apply_spec(d->spec, f, grid, gdims, lo, hi, flags, s);
+    const int ok = marching_matches_adjacency(f->adj, grid, gdims, lo, hi, steps - 1, d->kind == BK_KIND_CUBE ? kSlotsAll : kSlotsStar, s);
+    if (ok <= 0) return ok < 0 ? ok : adjacency_mismatch();
     return bk::launch_tiled(d->spec, *f, nullptr, 1, grid, gdims, lo, hi, s, part, ready_lo, ready_hi, steps);
   }
   if (d->kind == BK_KIND_GENERATED && steps == 1 && flags != BK_KERNEL_BRICK) {
     const dim3 box(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
     if (box.x == 0 || box.y == 0 || box.z == 0) return BK_OK;
-    const int rc = bk::gen_launch(d->gen, *f, grid, gdims, lo, hi, s, part, ready_lo, ready_hi);
-    if (rc != BK_EUNSUPPORTED || part != BK_PART_ALL || flags == BK_KERNEL_TILED) return rc;
+    const int ok = marching_matches_adjacency(f->adj, grid, gdims, lo, hi, 0, kSlotsAll, s);
+    if (ok < 0) return ok;
+    if (ok) {
+      const int rc = bk::gen_launch(d->gen, *f, grid, gdims, lo, hi, s, part, ready_lo, ready_hi);
+      if (rc != BK_EUNSUPPORTED || part != BK_PART_ALL || flags == BK_KERNEL_TILED) return rc;
+    } else if (part != BK_PART_ALL || flags == BK_KERNEL_TILED) {
+      return adjacency_mismatch();
+    }
   }
   if (steps != 1 || part != BK_PART_ALL) return BK_EUNSUPPORTED;  // general taps: whole-box single sweeps only
   const dim3 g(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);

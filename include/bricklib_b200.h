@@ -195,6 +195,15 @@ int bk_stencil_apply(int stencil, const bk_field_t *f, const unsigned *grid_dev,
 int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid_dev, const unsigned *gdims,
                           const unsigned *lo, const unsigned *hi, const double *coeff_host, const unsigned *ready_lo,
                           const unsigned *ready_hi, int part, void *stream);
+/* Grid vs adjacency.  The marching kernels (the fast path of every call above and below) take neighbour ids from the
+ * dense `grid_dev` array and read brick 0 outside it, where the reference's accessor follows BrickInfo::adj
+ * (include/brick.h:234-246).  Before a (adj, grid, box) triple is first swept that way, a small kernel verifies
+ * adj[grid[p]][s] == grid[p + delta_s] (0 outside the grid) for every position and neighbour slot the launch reads, and
+ * the verdict is cached (one stream synchronisation, once).  On a mismatch -- periodic or otherwise hand-made adjacency
+ * -- BK_KERNEL_AUTO uses the adjacency-following family instead, BK_KERNEL_TILED and the split / fused calls return
+ * BK_EUNSUPPORTED: never silently different numbers.  bk_dev_free forgets the verdicts of the freed address; call
+ * bk_adjacency_forget (NULL = all) after rewriting an adjacency list or grid in place. */
+int bk_adjacency_forget(const void *adj_or_grid_dev);
 /* `steps` time steps in ONE pass over HBM (temporal blocking; steps = 1 or 2).  Between two ghost exchanges the
  * reference applies ST_ITER sweeps that depend on nothing outside the subdomain's (ghost-inclusive) grid
  * (weak/main.cu:275-285), so consecutive sweeps can be fused.  steps = 2 is equivalent to

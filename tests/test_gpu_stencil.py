@@ -352,6 +352,49 @@ def test_full_size_matches_oracle_on_a_sampled_slab(big):
         assert rel(a_out[8:-8, 8:-8, 8:-8], want[8:-8, 8:-8, 8:-8]) < TOL, name
 
 
+def test_hand_made_periodic_adjacency_is_honoured_not_ignored():
+    """north_star: "its 26 adjacency-list neighbours".  A grid whose adjacency wraps PERIODICALLY (no null brick, no ghost
+    shell) differs from what the dense grid array says at every boundary brick: BK_KERNEL_AUTO must follow the adjacency
+    (results = periodic sweep), BK_KERNEL_TILED and the split / fused calls must refuse, none may return other numbers"""
+    P = oracle.port()
+    nb = (6, 4, 5)
+    n = nb[0] * nb[1] * nb[2]
+    grid_h = (np.arange(n, dtype=np.uint32) + 1).reshape(nb[::-1])          # ids 1..n, brick 0 stays the null brick
+    adj = np.zeros((n + 1, 27), dtype=np.uint32)
+    for k in range(nb[2]):
+        for j in range(nb[1]):
+            for i in range(nb[0]):
+                for s in range(27):
+                    q = ((k + s // 9 - 1) % nb[2], (j + (s // 3) % 3 - 1) % nb[1], (i + s % 3 - 1) % nb[0])
+                    adj[grid_h[k, j, i], s] = grid_h[q]
+    info, grid = bk.BrickInfo(adj), bk.DeviceGrid(grid_h)
+    rng = np.random.default_rng(4)
+    field = rng.random((nb[2] * 8, nb[1] * 8, nb[0] * 8))
+    s_in, s_out = info.allocate(512), info.allocate(512)
+    host = np.zeros((n + 1, 8, 8, 8))
+    host[1:] = field.reshape(nb[2], 8, nb[1], 8, nb[0], 8).transpose(0, 2, 4, 1, 3, 5).reshape(n, 8, 8, 8)
+    s_in.from_host(host.reshape(-1))
+    b_in, b_out = bk.Brick(info, s_in), bk.Brick(info, s_out)
+    for st in (1, 3, 4):
+        r = oracle.RADIUS[st]
+        want = P.sweep_array(st, np.pad(field, r, mode="wrap"), (r,) * 3, tuple(r + x for x in field.shape[::-1]))[r:-r, r:-r, r:-r]
+        for kernel in (bk.KERNEL_AUTO, bk.KERNEL_BRICK):
+            s_out.dat.zero()
+            bk.stencil(st, grid, b_in, b_out, kernel=kernel)
+            got = s_out.to_host().reshape(-1, 8, 8, 8)[1:].reshape(nb[2], nb[1], nb[0], 8, 8, 8).transpose(0, 3, 1, 4, 2, 5).reshape(field.shape)
+            assert rel(got, want) < TOL, (st, kernel)
+        with pytest.raises(bk.BrickError):
+            bk.stencil(st, grid, b_in, b_out, kernel=bk.KERNEL_TILED)
+    with pytest.raises(bk.Unsupported):
+        bk.stencil_advance(1, 2, grid, b_in, b_out)
+    # the interior of the same grid reads no wrapped neighbour: there the marching kernel is allowed and agrees
+    lo, hi = (1, 1, 1), tuple(x - 1 for x in nb)
+    bk.stencil(1, grid, b_in, b_out, lo, hi, kernel=bk.KERNEL_TILED)
+    a = s_out.to_host()
+    bk.stencil(1, grid, b_in, b_out, lo, hi, kernel=bk.KERNEL_BRICK)
+    assert rel(a, s_out.to_host()) < 1e-14
+
+
 def test_synthetic_field_on_the_device_equals_the_host_hash():
     """bk_fill_synthetic writes hash(global periodic cell coordinate) into the bricks: identical to core.synthetic_field,
     ghost shell wrapped periodically, null brick untouched"""
