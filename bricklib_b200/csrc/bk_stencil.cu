@@ -403,6 +403,8 @@ int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid
                           const unsigned *ready_hi, int part, void *stream) {
   BK_REQUIRE(stencil >= 0 && stencil < BK_ST_COUNT, "unknown stencil id");
   BK_REQUIRE(f && f->adj && f->in && f->out && grid && gdims && lo && hi && ready_lo && ready_hi, "null argument");
+  const bool trust_grid = (part & BK_PART_GRID_TOPOLOGY) != 0;
+  part &= ~BK_PART_GRID_TOPOLOGY;
   BK_REQUIRE((part & ~BK_PART_THIN) == BK_PART_READY || (part & ~BK_PART_THIN) == BK_PART_REST,
              "part must be BK_PART_READY or BK_PART_REST (optionally | BK_PART_THIN)");
   BK_REQUIRE(f->in_step >= 512 && f->out_step >= 512, "brick step smaller than a brick");
@@ -411,7 +413,7 @@ int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid
   // only the marching kernel has the split enumeration; the caller falls back to whole-box launches on EUNSUPPORTED
   bk::CoefSpec spec;
   if (bk::coef_spec_for(stencil, coeff, &spec) != BK_OK) return BK_EINVAL;
-  const int ok = marching_matches_adjacency(f->adj, grid, gdims, lo, hi, 0, spec.kind == 1 ? kSlotsAll : kSlotsStar, (cudaStream_t) stream);
+  const int ok = trust_grid ? 1 : marching_matches_adjacency(f->adj, grid, gdims, lo, hi, 0, spec.kind == 1 ? kSlotsAll : kSlotsStar, (cudaStream_t) stream);
   if (ok <= 0) return ok < 0 ? ok : adjacency_mismatch();
   return bk::launch_tiled(spec, *f, nullptr, 1, grid, gdims, lo, hi, (cudaStream_t) stream, part, ready_lo, ready_hi);
 }
@@ -422,6 +424,8 @@ int bk_stencil_advance(int stencil, int steps, const bk_field_t *f, const unsign
   BK_REQUIRE(stencil >= 0 && stencil < BK_ST_COUNT, "unknown stencil id");
   BK_REQUIRE(steps == 1 || steps == 2, "steps must be 1 or 2");
   BK_REQUIRE(f && f->adj && f->in && f->out && grid && gdims && lo && hi, "null argument");
+  const bool trust_grid = (part & BK_PART_GRID_TOPOLOGY) != 0;
+  part &= ~BK_PART_GRID_TOPOLOGY;
   BK_REQUIRE(part == BK_PART_ALL ||
                  (ready_lo && ready_hi && ((part & ~BK_PART_THIN) == BK_PART_READY || (part & ~BK_PART_THIN) == BK_PART_REST)),
              "bad part");
@@ -430,7 +434,7 @@ int bk_stencil_advance(int stencil, int steps, const bk_field_t *f, const unsign
   BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
   bk::CoefSpec spec;
   if (bk::coef_spec_for(stencil, coeff, &spec) != BK_OK) return BK_EINVAL;
-  const int ok = marching_matches_adjacency(f->adj, grid, gdims, lo, hi, steps - 1, spec.kind == 1 ? kSlotsAll : kSlotsStar,
+  const int ok = trust_grid ? 1 : marching_matches_adjacency(f->adj, grid, gdims, lo, hi, steps - 1, spec.kind == 1 ? kSlotsAll : kSlotsStar,
                                             (cudaStream_t) stream);
   if (ok <= 0) return ok < 0 ? ok : adjacency_mismatch();
   return bk::launch_tiled(spec, *f, nullptr, 1, grid, gdims, lo, hi, (cudaStream_t) stream, part, ready_lo, ready_hi,
@@ -595,6 +599,8 @@ int bk_stencil_def_advance(const bk_stencil_def_t *d, int steps, const bk_field_
                            const unsigned *ready_hi, int part, unsigned flags, void *stream) {
   BK_REQUIRE(d && f && f->adj && f->in && f->out && grid && gdims && lo && hi, "null argument");
   BK_REQUIRE(steps == 1 || steps == 2, "steps must be 1 or 2");
+  const bool trust_grid = (part & BK_PART_GRID_TOPOLOGY) != 0;
+  part &= ~BK_PART_GRID_TOPOLOGY;
   BK_REQUIRE(part == BK_PART_ALL ||
                  (ready_lo && ready_hi && ((part & ~BK_PART_THIN) == BK_PART_READY || (part & ~BK_PART_THIN) == BK_PART_REST)),
              "bad part");
@@ -603,15 +609,15 @@ int bk_stencil_def_advance(const bk_stencil_def_t *d, int steps, const bk_field_
   BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
   cudaStream_t s = (cudaStream_t) stream;
   if (d->kind == BK_KIND_STAR || d->kind == BK_KIND_CUBE) {
-    if (steps == 1 && part == BK_PART_ALL) return apply_spec(d->spec, f, grid, gdims, lo, hi, flags, s);
-    const int ok = marching_matches_adjacency(f->adj, grid, gdims, lo, hi, steps - 1, d->kind == BK_KIND_CUBE ? kSlotsAll : kSlotsStar, s);
+    if (steps == 1 && part == BK_PART_ALL && !trust_grid) return apply_spec(d->spec, f, grid, gdims, lo, hi, flags, s);
+    const int ok = trust_grid ? 1 : marching_matches_adjacency(f->adj, grid, gdims, lo, hi, steps - 1, d->kind == BK_KIND_CUBE ? kSlotsAll : kSlotsStar, s);
     if (ok <= 0) return ok < 0 ? ok : adjacency_mismatch();
     return bk::launch_tiled(d->spec, *f, nullptr, 1, grid, gdims, lo, hi, s, part, ready_lo, ready_hi, steps);
   }
   if (d->kind == BK_KIND_GENERATED && steps == 1 && flags != BK_KERNEL_BRICK) {
     const dim3 box(hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]);
     if (box.x == 0 || box.y == 0 || box.z == 0) return BK_OK;
-    const int ok = marching_matches_adjacency(f->adj, grid, gdims, lo, hi, 0, kSlotsAll, s);
+    const int ok = trust_grid ? 1 : marching_matches_adjacency(f->adj, grid, gdims, lo, hi, 0, kSlotsAll, s);
     if (ok < 0) return ok;
     if (ok) {
       const int rc = bk::gen_launch(d->gen, *f, grid, gdims, lo, hi, s, part, ready_lo, ready_hi);

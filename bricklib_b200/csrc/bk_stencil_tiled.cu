@@ -472,8 +472,9 @@ __global__ void __launch_bounds__(C::NT) __maxnreg__(C::MAXREG) k_star_capped(co
 // Semantics = bk_stencil_apply over the whole grid followed by bk_stencil_apply over [lo,hi): the intermediate is
 // computed at every in-grid cell the second step reads and is zero outside the grid (the null brick).
 template <int R_, int YT_, int TI_, int TJ_, int D_, int NPW_, int MINB_ = 1, int CREG_ = 0, int PREG_ = 40, bool LAG_ = false,
-          bool EW_ = false>
+          bool EW_ = false, int ABL_ = 0>
 struct FCfg {
+  static constexpr int ABL = ABL_;                     // developer ablations (WRONG results): 1 no strip, 2 no i-halo loads, 4 no masks, 8 no mid store
   static constexpr bool EW = EW_;                      // wait for the next input plane BEFORE stage B (no spin loop between B(n) and A(n+1))
   static constexpr bool LAG = LAG_;                    // stage B runs one plane behind stage A (independent work between barriers)
   static constexpr int MINB = MINB_;                   // CTAs per SM the register allocation must allow
@@ -738,6 +739,10 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_star2(const __grid_constant_
       } else {
 #pragma unroll
         for (int m = 1; m <= R; ++m) {  // odd row groups load right first: a half warp then covers all 32 banks
+          if constexpr (C::ABL & 2) {
+            line[R - m] = v[r].y, line[R + 1 + m] = v[r].x;
+            continue;
+          }
           const double q0 = *reinterpret_cast<const double *>(pr + ioffL[m - 1]);
           const double q1 = *reinterpret_cast<const double *>(pr + ioffR[m - 1]);
           line[R - m] = swp ? q1 : q0;
@@ -825,14 +830,21 @@ __global__ void __launch_bounds__(C::NT, C::MINB) k_star2(const __grid_constant_
             for (int r = 0; r < YT; ++r) vin[r] = *reinterpret_cast<const double2 *>(pbA + own_off + r * 64);
             star_plane(pbA, accA, u, vin);
             const int sF = ((u - R) % W + W) % W;
-            const bool ok = zin && own_in;
+            // cells outside the grid hold zero (null-brick semantics): only boundary tiles / planes ever mask, so the
+            // common case takes a warp-uniform branch around the selects
+            const bool ok = (C::ABL & 4) ? true : (zin && own_in);
+            if (__all_sync(0xffffffffu, ok)) {
 #pragma unroll
-            for (int r = 0; r < YT; ++r) {
-              vmid[r] = ok ? accA[sF][r] : make_double2(0.0, 0.0);
-              *reinterpret_cast<double2 *>(pm + own_off + r * 64) = vmid[r];
+              for (int r = 0; r < YT; ++r) vmid[r] = accA[sF][r];
+            } else {
+#pragma unroll
+              for (int r = 0; r < YT; ++r) vmid[r] = ok ? accA[sF][r] : make_double2(0.0, 0.0);
             }
+#pragma unroll
+            for (int r = 0; r < YT; ++r)
+              if (!(C::ABL & 8)) *reinterpret_cast<double2 *>(pm + own_off + r * 64) = vmid[r];
           }
-          if (has_strip) {
+          if (has_strip && !(C::ABL & 1)) {
             const int sF = ((u - R) % W + W) % W, s0 = u % W, sN = (u + R) % W;
             const double sv = *reinterpret_cast<const double *>(pbA + soff);
             accS[sF] = fma(cf.cp[2][R - 1], sv, accS[sF]);
@@ -1084,6 +1096,12 @@ int launch_tiled(const CoefSpec &spec, const bk_field_t &f, const bk_field_t *mu
       if (v == 5) return launch_cfg<FCfg<1, 4, 4, 4, 4, 2, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);                    // deeper ring
       if (v == 6) return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2, 0, 40, false, true>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);  // early wait
       if (v == 7) return launch_cfg<FCfg<1, 4, 4, 4, 4, 2, 2, 0, 40, false, true>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);  // both
+      if (v == 11) return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2, 0, 40, false, false, 1>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);   // ablations
+      if (v == 12) return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2, 0, 40, false, false, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+      if (v == 13) return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2, 0, 40, false, false, 4>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+      if (v == 14) return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2, 0, 40, false, false, 8>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+      if (v == 15) return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2, 0, 40, false, false, 15>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
+      if (v == 16) return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2, 0, 40, false, false, 3>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
       return launch_cfg<FCfg<1, 4, 4, 4, 3, 2, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
     }
     if (r == 2) return launch_cfg<FCfg<2, 2, 4, 4, 4, 4>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);

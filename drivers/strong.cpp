@@ -30,7 +30,7 @@ struct Shared {
   int size = 1, iters = 100;
   unsigned dom_size = 512, sdom_size = 128;
   const StencilDef *st = nullptr;
-  bool validate = false, no_stitch = false;
+  bool validate = false, no_stitch = false, no_overlap = false;
   unsigned long subdim = 4, allsubs = 64;
   std::vector<bElem *> base;  // rank -> device address of field 0 of its first subdomain
   std::vector<double> calc, call, wait, total, mbytes;
@@ -207,17 +207,65 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
   if (fuse < 1 || st->st_iter % fuse || (st->st_iter / fuse) % 2) fuse = 1;
   const int npass = st->st_iter / fuse;
 
+  // the exchange runs on its own high-priority stream so that the first pass can overlap it (stitched mode): the CTAs of
+  // pass 0 that read only bricks I own start at once on the compute stream (BK_PART_READY), the CTAs that touch the
+  // box surface's ghost bricks follow the pull on the exchange stream (BK_PART_REST) -- the weak driver's scheme
+  void *comm_stream, *evX;
+  bkCheck(bk_stream_create_priority(&comm_stream, 1));
+  bkCheck(bk_event_create(&evX));
+  std::vector<long> rdy_lo(3), rdy_hi(3);  // bricks that are final without the exchange: everything but real ghost shell
+  for (int d = 0; d < 3; ++d) rdy_lo[d] = wrap[d] ? 0 : 1, rdy_hi[d] = wrap[d] ? sgd[d] : sgd[d] - 1;
+  bool overlap = stitched && !S.no_overlap;
+  auto stitched_pass = [&](int p, int part, void *stream) -> bool {
+    const bool last = p == npass - 1;
+    Brick3D &src = (p % 2) ? sB : sA, &dst = (p % 2) ? sA : sB;
+    // the stitched grid aliases ghost positions onto other subdomains' bricks on purpose: it, not the per-subdomain
+    // adjacency list, is the topology of this launch (BK_PART_GRID_TOPOLOGY)
+    return brickAdvance(st->id, fuse, sgrid_dev, sgd, src, dst, last ? own_lo : sw_lo, last ? own_hi : sw_hi, rdy_lo, rdy_hi,
+                        part | BK_PART_GRID_TOPOLOGY, nullptr, stream);
+  };
+
   auto brick_func = [&]() {
     bkCheck(bk_event_record(evDone, nullptr));
     bkCheck(bk_event_sync(evDone));
     double t0 = omp_get_wtime();
     bar.wait();  // every rank's skins are final
     waittime += omp_get_wtime() - t0;
+    float ms = 0;
+    if (overlap && npass > 1) {
+      bkCheck(bk_event_record(x0, comm_stream));
+      ev.exchange(comm_stream);
+      bkCheck(bk_event_record(x1, comm_stream));
+      bkCheck(bk_event_record(c0, nullptr));
+      if (stitched_pass(0, BK_PART_READY, nullptr)) {
+        if (!stitched_pass(0, BK_PART_REST, comm_stream)) throw std::runtime_error("split pass unavailable");
+        bkCheck(bk_event_record(evX, comm_stream));
+        bkCheck(bk_stream_wait_event(nullptr, evX));
+      } else {  // no split kernel for this layout: the whole pass after the pull
+        overlap = false;
+        bkCheck(bk_event_record(evX, comm_stream));
+        bkCheck(bk_stream_wait_event(nullptr, evX));
+        if (!stitched_pass(0, BK_PART_ALL, nullptr)) throw std::runtime_error("marching kernel unavailable for the stitched grid: rerun with -M");
+      }
+      // pass 1 overwrites the storage whose skins the neighbours are pulling: wait until every pull has finished
+      bkCheck(bk_event_sync(evX));
+      bkCheck(bk_event_elapsed_ms(x0, x1, &ms));
+      calltime += ms / 1e3;
+      t0 = omp_get_wtime();
+      bar.wait();
+      waittime += omp_get_wtime() - t0;
+      for (int p = 1; p < npass; ++p)
+        if (!stitched_pass(p, BK_PART_ALL, nullptr)) throw std::runtime_error("pass unavailable");
+      bkCheck(bk_event_record(c1, nullptr));
+      bkCheck(bk_event_sync(c1));
+      bkCheck(bk_event_elapsed_ms(c0, c1, &ms));
+      calctime += ms / 1e3;  // includes the overlapped pull
+      return;
+    }
     bkCheck(bk_event_record(x0, nullptr));
     ev.exchange(nullptr);
     bkCheck(bk_event_record(x1, nullptr));
     bkCheck(bk_event_sync(x1));
-    float ms = 0;
     bkCheck(bk_event_elapsed_ms(x0, x1, &ms));
     calltime += ms / 1e3;
     t0 = omp_get_wtime();
@@ -227,13 +275,9 @@ void rank_main(int rank, Shared &S, Barrier &bar) {
     if (stitched) {
       // one sweep (or fused pass of two time steps) over the whole super grid; the shell is swept only along axes whose
       // shell is real ghost storage (communication avoiding, weak/main.cu:275-285), never where it aliases my interior
-      for (int p = 0; p < npass; ++p) {
-        const bool last = p == npass - 1;
-        Brick3D &src = (p % 2) ? sB : sA, &dst = (p % 2) ? sA : sB;
-        if (!brickAdvance(st->id, fuse, sgrid_dev, sgd, src, dst, last ? own_lo : sw_lo, last ? own_hi : sw_hi, own_lo,
-                          own_hi, BK_PART_ALL, nullptr, nullptr))
+      for (int p = 0; p < npass; ++p)
+        if (!stitched_pass(p, BK_PART_ALL, nullptr))
           throw std::runtime_error("marching kernel unavailable for the stitched grid: rerun with -M");
-      }
     } else {
       for (int sw = 0; sw < st->st_iter; ++sw) {
         const bool last = sw == st->st_iter - 1;
@@ -320,7 +364,7 @@ int main(int argc, char **argv) {
   std::string sname = "mpi7pt";
   int c;
   if (const char *e = getenv("BRICK_RANKS")) S.size = atoi(e);
-  while ((c = getopt(argc, argv, "d:s:I:g:S:vhM")) != -1) switch (c) {
+  while ((c = getopt(argc, argv, "d:s:I:g:S:vhMO")) != -1) switch (c) {
       case 'd': S.dom_size = std::stoi(optarg); break;
       case 's': S.sdom_size = std::stoi(optarg); break;
       case 'I': S.iters = std::stoi(optarg); break;
@@ -328,8 +372,9 @@ int main(int argc, char **argv) {
       case 'S': sname = optarg; break;
       case 'v': S.validate = true; break;
       case 'M': S.no_stitch = true; break;
+      case 'O': S.no_overlap = true; break;
       default:
-        printf("Program options\n  -h: help\n  -M: per-subdomain launches and ghost copies instead of the stitched super grid\n  -d n: global domain edge (default 512)\n  -s n: subdomain edge (default 128)\n"
+        printf("Program options\n  -h: help\n  -O: do not overlap the exchange with the first pass (stitched mode)\n  -M: per-subdomain launches and ghost copies instead of the stitched super grid\n  -d n: global domain edge (default 512)\n  -s n: subdomain edge (default 128)\n"
                "  -I n: exchange periods (default 100)\n  -g n: GPUs = ranks (default 1)\n  -S name: mpi7pt mpi13pt mpi25pt mpi125pt\n"
                "  -v: validate against a CPU sweep of the global periodic array\n");
         return 0;

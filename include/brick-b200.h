@@ -106,6 +106,7 @@ void copyFromDevice(const std::vector<long> &extent, T *dst_host, const T *src_d
 template <typename T>
 void copyToBrickDevice(const std::vector<long> &dimlist, const std::vector<long> &padding, const std::vector<long> &ghost,
                        const bElem *arr_dev, const unsigned *grid_dev, T &brick_dev, void *stream = nullptr) {
+  static_assert(T::ROW_MAJOR, "device bricks are row-major (Dim<8> / Dim<4,8>): refoldBrick() converts host data in other folds");
   bkCheck(bk_copy_to_brick(dimlist.data(), padding.data(), ghost.data(), arr_dev, grid_dev, brick_dev.dat, brick_dev.step,
                            stream));
 }
@@ -136,6 +137,7 @@ template <typename T>
 void brickStencil(int stencil, const unsigned *grid_dev, const std::vector<long> &gdims, T &bIn, T &bOut,
                   const std::vector<long> &lo, const std::vector<long> &hi, const bElem *coeff = nullptr,
                   void *stream = nullptr, unsigned kernel = BK_KERNEL_AUTO) {
+  static_assert(T::ROW_MAJOR, "device bricks are row-major (Dim<8> / Dim<4,8>): refoldBrick() converts host data in other folds");
   bk_field_t f = {&bIn.bInfo->adj[0][0], bIn.dat, bIn.step, bOut.dat, bOut.step};
   const unsigned g[3] = {(unsigned) gdims[0], (unsigned) gdims[1], (unsigned) gdims[2]};
   const unsigned l[3] = {(unsigned) lo[0], (unsigned) lo[1], (unsigned) lo[2]};
@@ -206,6 +208,7 @@ class BrickStencilDef {
   template <typename T>
   void launch(const unsigned *grid_dev, const std::vector<long> &gdims, T &bIn, T &bOut, const std::vector<long> &lo,
               const std::vector<long> &hi, void *stream = nullptr, unsigned kernel = BK_KERNEL_AUTO) const {
+    static_assert(T::ROW_MAJOR, "device bricks are row-major (Dim<8> / Dim<4,8>): refoldBrick() converts host data in other folds");
     bk_field_t f = {&bIn.bInfo->adj[0][0], bIn.dat, bIn.step, bOut.dat, bOut.step};
     unsigned g[3], l[3], h[3];
     for (int d = 0; d < 3; ++d) g[d] = (unsigned) gdims[d], l[d] = (unsigned) lo[d], h[d] = (unsigned) hi[d];

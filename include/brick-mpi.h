@@ -15,10 +15,13 @@
 #define BRICK_MPI_H
 
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
 #include <initializer_list>
 #include <iostream>
+#include <memory>
+#include <mutex>
 #include <unordered_map>
 #include <vector>
 #include "brick-b200.h"
@@ -68,13 +71,36 @@ inline std::vector<BitSet> make_skin3d_good() {
 }
 static const std::vector<BitSet> skin3d_good = make_skin3d_good();
 
+/// What the ranks of one job share when "ranks" are host threads, one per GPU: a barrier and one slot per rank for the
+/// statistics reductions (the stand-in for MPI_COMM_WORLD's collective machinery).
+struct BrickWorld {
+  int size;
+  std::mutex m;
+  std::condition_variable cv;
+  int waiting = 0, gen = 0;
+  std::vector<double> slot;
+  explicit BrickWorld(int size) : size(size), slot(size, 0.0) {}
+  void barrier() {
+    std::unique_lock<std::mutex> l(m);
+    const int g = gen;
+    if (++waiting == size) {
+      waiting = 0, ++gen;
+      cv.notify_all();
+    } else {
+      cv.wait(l, [&] { return g != gen; });
+    }
+  }
+};
+
 /// Stand-in for the periodic Cartesian MPI communicator (weak/args.cpp:105-108): dims/coords in MPI order
-/// (index 0 varies slowest and corresponds to axis k), one rank per GPU.
+/// (index 0 varies slowest and corresponds to axis k), one rank per GPU.  `world` is optional: set for jobs whose ranks
+/// call the collectives below (mpi_statistics(double, comm), MPI_Barrier-like comm.barrier()).
 struct BrickComm {
   int dims[3] = {1, 1, 1};
   int coords[3] = {0, 0, 0};
   int rank = 0, size = 1;
-  static BrickComm cart(const int *d, int rank) {
+  std::shared_ptr<BrickWorld> world;
+  static BrickComm cart(const int *d, int rank, std::shared_ptr<BrickWorld> world = nullptr) {
     BrickComm c;
     c.size = d[0] * d[1] * d[2];
     c.rank = rank;
@@ -82,9 +108,17 @@ struct BrickComm {
     c.coords[2] = rank % d[2];
     c.coords[1] = (rank / d[2]) % d[1];
     c.coords[0] = rank / (d[1] * d[2]);
+    c.world = std::move(world);
     return c;
   }
+  void barrier() const {
+    if (world) world->barrier();
+  }
 };
+#ifndef MPI_VERSION
+/// there is no MPI in a one-node build: reference call sites that say MPI_Comm name the stand-in
+typedef BrickComm MPI_Comm;
+#endif
 
 /// One fused pull of all ghost regions of one storage (reference: ExchangeView::exchange, brick-mpi.h:96-123)
 class ExchangeView {
@@ -239,9 +273,12 @@ class BrickDecomp {
   }
 };
 
-/// populate(comm, bDecomp, 0, 1, coo): fill rank_map with the rank of each of the 27 neighbour sets
+/// populate(comm, bDecomp, 0, 1, coo) -- same signature as the reference's (brick-mpi.h:730-753; there `neighbor` and `d`
+/// drive its recursion over the axes, here the whole 27-entry map comes from one bk_rank_map call, so any start values
+/// mean "all of it"): fill bDecomp.rank_map with the rank of each neighbour set on the periodic Cartesian grid `comm`
 template <unsigned dim, unsigned... BDims>
-void populate(BrickComm &comm, BrickDecomp<dim, BDims...> &bDecomp, BitSet = BitSet(), int = 1, int *coo = nullptr) {
+void populate(MPI_Comm &comm, BrickDecomp<dim, BDims...> &bDecomp, BitSet neighbor = BitSet(), int d = 1, int *coo = nullptr) {
+  (void) neighbor, (void) d;
   uint64_t sets[27];
   int ranks[27];
   bkCheck(bk_rank_map(comm.dims, coo ? coo : comm.coords, sets, ranks));
@@ -262,6 +299,17 @@ inline mpi_stats mpi_statistics(const std::vector<double> &per_rank) {
   for (double v : per_rank) sum += v, sq += v * v, r.min = std::min(r.min, v), r.max = std::max(r.max, v);
   r.avg = sum / n;
   r.sigma = std::sqrt(std::max(0.0, (sq - sum * sum / n) / std::max(n - 1, 1)));
+  return r;
+}
+/// mpi_statistics(stats, comm) -- the reference's collective form (brick-mpi.h:768-785: four MPI_Reduce calls): every
+/// rank of `comm` calls it with its own value and every rank gets the statistics (the reference returns them on rank 0)
+inline mpi_stats mpi_statistics(double stats, const MPI_Comm &comm) {
+  if (!comm.world) return mpi_statistics(std::vector<double>{stats});
+  BrickWorld &w = *comm.world;
+  w.slot[comm.rank] = stats;
+  w.barrier();
+  const mpi_stats r = mpi_statistics(w.slot);
+  w.barrier();  // nobody overwrites a slot before everybody has read it
   return r;
 }
 inline std::ostream &operator<<(std::ostream &os, const mpi_stats &s) {

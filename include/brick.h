@@ -129,8 +129,12 @@ struct Brick<Dim<BDims...>, Dim<Folds...>> {
   static constexpr unsigned DIMS = sizeof...(BDims);
   static constexpr unsigned VECLEN = cal_size<Folds...>::value;
   static constexpr unsigned BRICKSIZE = cal_size<BDims...>::value;
-  static_assert(brick_detail::row_major_fold<Dim<BDims...>, Dim<Folds...>>::value,
-                "bricklib_b200 keeps bricks row-major: use Dim<8> or Dim<4,8> folds");
+  /// is the in-brick order of this fold plain row-major (Dim<8>, Dim<4,8>)?  That is the layout the CUDA kernels read:
+  /// the device wrappers of brick-b200.h accept only such bricks.  Other folds (the reference's AVX2 fold Dim<2,2>,
+  /// include/brick.h:234-246, stencils/cpuvfold.h:12-40) are HOST views: the accessor below addresses them exactly like
+  /// the reference, and refoldBrick() rewrites a field from one fold into another so that such data can be moved.
+  static constexpr bool ROW_MAJOR = brick_detail::row_major_fold<Dim<BDims...>, Dim<Folds...>>::value;
+  static_assert(sizeof...(Folds) <= sizeof...(BDims), "more fold dimensions than brick dimensions");
 
   myBrickInfo *bInfo;
   size_t step;
@@ -154,14 +158,21 @@ struct Brick<Dim<BDims...>, Dim<Folds...>> {
   /// element `idx` (slowest axis first, each in [-B_d, 2*B_d)) seen from brick b -- HOST memory only
   inline bElem &elem(unsigned b, const int *idx) {
     constexpr unsigned ext[] = {BDims...};
-    unsigned slot = 0, off = 0;
+    constexpr unsigned nf = sizeof...(Folds);
+    constexpr unsigned fold_raw[] = {Folds..., 1};  // (the trailing 1 keeps the array non-empty for Dim<>)
+    unsigned slot = 0, nvec = 0, wvec = 0;
     for (unsigned d = 0; d < DIMS; ++d) {  // slowest axis first: slot digit weight 3^(DIMS-1-d)
       int i = idx[d], o = 1;
       if (i < 0) i += (int) ext[d], o = 0;
       else if (i >= (int) ext[d]) i -= (int) ext[d], o = 2;
       slot = slot * 3 + (unsigned) o;
-      off = off * ext[d] + (unsigned) i;
+      // the folds belong to the FASTEST nf axes; an axis without a fold has fold extent 1 (include/brick.h:234-246):
+      // element = (which vector) * VECLEN + (position inside the vector), both mixed-radix over the axes
+      const unsigned f = d + nf >= DIMS ? fold_raw[d + nf - DIMS] : 1u;
+      wvec = wvec * f + (unsigned) i % f;
+      nvec = nvec * (ext[d] / f) + (unsigned) i / f;
     }
+    const unsigned off = nvec * VECLEN + wvec;
     return dat[(size_t) bInfo->adj[b][slot] * step + off];
   }
 
@@ -174,5 +185,21 @@ struct Brick<Dim<BDims...>, Dim<Folds...>> {
     return &dat[(size_t) bInfo->adj[b][slot] * step];
   }
 };
+
+/// Rewrite one field from one fold into another (same brick extents, same adjacency): dst[b][k][j][i] = src[b][k][j][i] for
+/// every brick.  The way to bring host data kept in a vector fold (e.g. Dim<2,2>, the reference's AVX2 layout) into the
+/// row-major fold the device kernels read, and back.
+template <unsigned... BDims, unsigned... FA, unsigned... FB>
+void refoldBrick(Brick<Dim<BDims...>, Dim<FA...>> &src, Brick<Dim<BDims...>, Dim<FB...>> &dst) {
+  static_assert(sizeof...(BDims) == 3, "3-D bricks");
+  constexpr unsigned ext[] = {BDims...};
+  for (unsigned b = 0; b < src.bInfo->nbricks; ++b)
+    for (unsigned k = 0; k < ext[0]; ++k)
+      for (unsigned j = 0; j < ext[1]; ++j)
+        for (unsigned i = 0; i < ext[2]; ++i) {
+          const int idx[3] = {(int) k, (int) j, (int) i};
+          dst.elem(b, idx) = src.elem(b, idx);  // indices inside the brick: slot 13 = the brick itself
+        }
+}
 
 #endif  // BRICK_H

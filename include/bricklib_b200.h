@@ -192,6 +192,11 @@ int bk_stencil_apply(int stencil, const bk_field_t *f, const unsigned *grid_dev,
  * get thin k segments of their own, which raises the READY share of the sweep from ~45 % to ~70 % at 512^3 at the price
  * of a few per cent more halo planes.  Worth it when the exchange is slow (crosses NVLink), not for self-exchanges. */
 #define BK_PART_THIN 4
+/* OR-ed into `part` of bk_stencil_apply_part / bk_stencil_advance / bk_stencil_def_advance: the dense grid IS the topology
+ * of this launch -- skip the grid-vs-adjacency check described below.  For grids built on purpose to differ from the
+ * per-subdomain adjacency: the stitched super grid of the strong driver (bk_stitch_grid) aliases ghost positions onto
+ * other subdomains' bricks, which is exactly what the adjacency list of ONE subdomain cannot say. */
+#define BK_PART_GRID_TOPOLOGY 8
 int bk_stencil_apply_part(int stencil, const bk_field_t *f, const unsigned *grid_dev, const unsigned *gdims,
                           const unsigned *lo, const unsigned *hi, const double *coeff_host, const unsigned *ready_lo,
                           const unsigned *ready_hi, int part, void *stream);
