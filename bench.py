@@ -426,6 +426,33 @@ def workload_name(stencil, size, it):
     return f"weak {stencil} {size}^3 per GPU, 8^3 bricks, 1 exchange + {it} sweeps per step"
 
 
+def driver_env():
+    """environment of the C++ drivers (one host thread per GPU).  OMP_PROC_BIND must not leak into them: with binding on,
+    libgomp pins the initial thread to the first place at start-up and every rank thread created later inherits that
+    single core -- measured: 595 instead of 1090 GStencil/s for the strong leg at N = 2"""
+    env = dict(os.environ, OMP_NUM_THREADS=str(max(4, _host_cores() // 2)), OMP_PROC_BIND="false")
+    env.pop("OMP_PLACES", None)
+    return env
+
+
+def wait_for_quiet_gpus(n, timeout=20.0):
+    """block until no OTHER process holds a compute context on GPUs 0..n-1 (the torchrun workers that have finished)"""
+    try:
+        import pynvml as nv
+        nv.nvmlInit()
+        me = os.getpid()
+        t0 = time.time()
+        while time.time() - t0 < timeout:
+            busy = [p.pid for i in range(n) for p in nv.nvmlDeviceGetComputeRunningProcesses(nv.nvmlDeviceGetHandleByIndex(i))
+                    if p.pid != me]
+            if not busy:
+                return True
+            time.sleep(0.25)
+    except Exception:
+        time.sleep(3.0)
+    return False
+
+
 def strong_leg(n):
     """BASELINE.json configs[4]: 1024^3 global, 64^3 subdomains, Z-Morton sections over n GPUs -- the C++ strong driver
     on ALL n GPUs (one host thread per GPU), stitched super grid; at n = 1 also one GPU's 1/8 share (512^3) both
@@ -435,14 +462,14 @@ def strong_leg(n):
 
     def run(label, args, timeout):
         try:
-            env = dict(os.environ, OMP_NUM_THREADS="4")
-            r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=timeout, env=env)
+            r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=timeout, env=driver_env())
             perf = [ln for ln in r.stdout.splitlines() if ln.startswith("perf ")]
-            calc = [ln for ln in r.stdout.splitlines() if ln.startswith("calc ")]
             if perf:
                 out[label] = {"GStencil/s": float(perf[-1].split()[1]), "cmd": "drivers/strong " + " ".join(args)}
-                if calc:
-                    out[label]["calc"] = calc[-1].strip()
+                for key in ("calc ", "call ", "wait "):      # seconds per time step: [min, avg, max] over the ranks
+                    ln = [x for x in r.stdout.splitlines() if x.startswith(key)]
+                    if ln:
+                        out[label][key.strip()] = ln[-1].split(":", 1)[1].split("(")[0].strip()
             else:
                 out[label] = {"error": (r.stdout + r.stderr)[-300:]}
         except Exception as exc:
@@ -465,7 +492,7 @@ def array_baseline_leg(n):
     for name in ("mpi7pt", "mpi25pt"):
         try:
             r = subprocess.run([exe, "-s", "512,512,512", "-I", "10", "-g", str(n), "-S", name], capture_output=True, text=True,
-                               timeout=600, env=dict(os.environ, OMP_NUM_THREADS="4"))
+                               timeout=600, env=driver_env())
             perf = [float(ln.split()[1]) for ln in r.stdout.splitlines() if ln.startswith("perf ")]
             if len(perf) == 2:
                 out[name] = {"array_GStencil/s": perf[0], "brick_GStencil/s": perf[1],
@@ -482,7 +509,7 @@ def single_leg():
     storage, step 1024), through the C++ single driver: kernel-only sweep rate + the host array sweep it validates against"""
     exe = os.path.join(ROOT, "drivers", "single")
     try:
-        r = subprocess.run([exe, "-n", "512", "-s", "7pt", "-r", "50"], capture_output=True, text=True, timeout=180)
+        r = subprocess.run([exe, "-n", "512", "-s", "7pt", "-r", "50"], capture_output=True, text=True, timeout=180, env=driver_env())
         out = {"what": "drivers/single -n 512 -s 7pt -r 50 (one sweep per launch, interleaved storage)"}
         for ln in r.stdout.splitlines():
             f = ln.split()
@@ -645,27 +672,6 @@ def main():
                             "parity": parity_of(bk, d, dist)}
         d.stencil, d.st_iter = st, it
         line["others"] = others
-        # strong scaling (configs[4]) and the single driver (configs[0]): C++ drivers spawned by rank 0 on all N GPUs while
-        # the other ranks wait on a HOST-side barrier (no kernel of theirs is running)
-        bk.device_sync()
-        if dist is not None:
-            dist.barrier(group=host_group)
-        if rank == 0:
-            others["strong"] = strong_leg(n)
-            others["array_layout_baseline"] = array_baseline_leg(n)
-            if n == 1:
-                others["single_7pt_512"] = single_leg()
-        if dist is not None:
-            dist.barrier(group=host_group)
-        if rank == 0:
-            line["baseline_configs"] = {
-                "configs[0] single 7pt 512^3 (N=1 only)": others.get("single_7pt_512", {}).get("GStencil/s"),
-                "configs[1] 125pt 512^3 per GPU": others.get("mpi125pt", {}).get("GStencil/s"),
-                "configs[2] weak 7pt / 13pt 512^3 per GPU": [value, others.get("mpi13pt", {}).get("GStencil/s")],
-                "configs[3] weak 25pt 512^3 per GPU": others.get("mpi25pt", {}).get("GStencil/s"),
-                "configs[4] strong 1024^3 in 64^3 subdomains": others["strong"].get("global_1024_sub_64", {}).get("GStencil/s"),
-                "unit": f"GStencil/s, whole job on {n} GPU(s)",
-            }
         e2e_s, bi, bo = e2e_periods(bk, [d, make_domain(), make_domain()], 9)
         e2e_s = max_over_ranks(dist, e2e_s)
         line["e2e"] = {"value": pts * it * n / e2e_s / 1e9, "unit": "GStencil/s", "h2d_bytes_per_step": bi * n,
@@ -683,11 +689,33 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": "GStencil/s", "cores": 0, "kind": "port",
                                         "sample": f"unavailable: {exc}"}
 
-    if rank == 0:
-        print(json.dumps(line))
     if dist is not None:
         barrier(dist)
         dist.destroy_process_group()
+    if rank != 0:
+        return
+    if not args.no_extras:
+        # strong scaling (configs[4]), the array-layout baseline (8f#4) and the single driver (configs[0]) run through the
+        # C++ drivers, one host thread per GPU, on ALL n GPUs.  They come last: the other ranks have left and this rank's
+        # own device memory is released first, so the drivers have the GPUs to themselves.
+        others = line["others"]
+        d = None
+        import gc
+        gc.collect()
+        wait_for_quiet_gpus(n)
+        others["strong"] = strong_leg(n)
+        others["array_layout_baseline"] = array_baseline_leg(n)
+        if n == 1:
+            others["single_7pt_512"] = single_leg()
+        line["baseline_configs"] = {
+            "configs[0] single 7pt 512^3 (N=1 only)": others.get("single_7pt_512", {}).get("GStencil/s"),
+            "configs[1] 125pt 512^3 per GPU": others.get("mpi125pt", {}).get("GStencil/s"),
+            "configs[2] weak 7pt / 13pt 512^3 per GPU": [value, others.get("mpi13pt", {}).get("GStencil/s")],
+            "configs[3] weak 25pt 512^3 per GPU": others.get("mpi25pt", {}).get("GStencil/s"),
+            "configs[4] strong 1024^3 in 64^3 subdomains": others["strong"].get("global_1024_sub_64", {}).get("GStencil/s"),
+            "unit": f"GStencil/s, whole job on {n} GPU(s)",
+        }
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":

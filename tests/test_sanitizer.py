@@ -18,8 +18,6 @@ def test_small_case_is_clean_under_compute_sanitizer(tool):
     if not os.path.exists(exe):
         pytest.skip("compute-sanitizer is not installed")
     cmd = [exe, "--tool", tool, "--error-exitcode", "86", "--print-limit", "200"]
-    if tool == "initcheck":
-        cmd += ["--track-unused-memory", "no"]
     r = subprocess.run(cmd + [sys.executable, os.path.join(ROOT, "tools", "sanitize_case.py")], capture_output=True, text=True,
                        timeout=1500, cwd=ROOT)
     out = r.stdout + r.stderr
