@@ -28,6 +28,12 @@ def _host_cores():
         return os.cpu_count() or 1
 
 
+# One hardware work queue per stream (default: 8 shared by all streams).  The multi-GPU legs keep kernels that wait for a
+# peer's flag in flight on several streams; with shared queues a finite kernel of ANOTHER stream can sit behind such a
+# waiter (a false dependency) -- harmless for one domain, a possible cross-process deadlock for the three independent
+# domains of the end-to-end leg.  Must be set before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 if "reference" in sys.argv[1:]:
     os.environ["OMP_NUM_THREADS"] = str(_host_cores())
     os.environ["OMP_PROC_BIND"] = "close"
@@ -129,6 +135,45 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
+
+
+class Watchdog:
+    """The headline measurement comes first; parity, the other stencils, the end-to-end leg and the C++ driver legs are
+    EXTRAS.  If an extra hangs (a wedged GPU, a peer that died) the run must still end with its JSON line: a daemon
+    thread waits for the deadline, rank 0 prints the last complete snapshot of the line -- marked `extras_truncated` --
+    and every rank leaves with os._exit(0) (all ranks run the same clock, so torchrun sees N clean exits).  ctypes and
+    torch release the GIL while they block, so the thread runs even when the main thread sits in a synchronize."""
+
+    def __init__(self, rank, seconds):
+        self.rank, self.seconds, self.t0 = rank, seconds, time.time()
+        self.snapshot, self.stage, self.done = None, "start", False
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+
+    def left(self):
+        return self.seconds - (time.time() - self.t0)
+
+    def at(self, stage, line=None):
+        self.stage = stage
+        if line is not None:
+            self.snapshot = json.loads(json.dumps(line))
+
+    def finish(self):
+        self.done = True
+
+    def _run(self):
+        while not self.done and self.left() > 0:
+            time.sleep(0.25)
+        if self.done:
+            return
+        if self.rank == 0 and self.snapshot is not None:
+            snap = dict(self.snapshot)
+            snap["extras_truncated"] = {"stage": self.stage, "after_s": round(time.time() - self.t0, 1),
+                                        "why": "an optional leg did not finish inside the bench's own deadline; the headline "
+                                               "measurement above is complete"}
+            sys.stdout.write(json.dumps(snap) + "\n")
+            sys.stdout.flush()
+        os._exit(0 if self.snapshot is not None or self.rank != 0 else 3)
 
 
 def dist_setup(n_gpus):
@@ -453,7 +498,16 @@ def wait_for_quiet_gpus(n, timeout=20.0):
     return False
 
 
-def strong_leg(n):
+def leg_timeout(wd, cap):
+    """seconds a driver leg may take: `cap`, but never more than what is left of the extras' deadline (minus a margin to
+    print the line); 0 = skip the leg"""
+    if wd is None:
+        return cap
+    left = wd.left() - 15.0
+    return 0 if left < 20.0 else min(cap, left)
+
+
+def strong_leg(n, wd=None):
     """BASELINE.json configs[4]: 1024^3 global, 64^3 subdomains, Z-Morton sections over n GPUs -- the C++ strong driver
     on ALL n GPUs (one host thread per GPU), stitched super grid; at n = 1 also one GPU's 1/8 share (512^3) both
     stitched and with per-subdomain launches (-M, the reference CUDA driver's structure)"""
@@ -461,6 +515,10 @@ def strong_leg(n):
     out = {}
 
     def run(label, args, timeout):
+        timeout = leg_timeout(wd, timeout)
+        if not timeout:
+            out[label] = {"skipped": "no time left inside the bench's deadline for extras"}
+            return
         try:
             r = subprocess.run([exe, *args], capture_output=True, text=True, timeout=timeout, env=driver_env())
             perf = [ln for ln in r.stdout.splitlines() if ln.startswith("perf ")]
@@ -475,24 +533,28 @@ def strong_leg(n):
         except Exception as exc:
             out[label] = {"error": str(exc)[:300]}
 
-    run("global_1024_sub_64", ["-d", "1024", "-s", "64", "-I", "10", "-g", str(n), "-S", "mpi7pt"], 600)
-    run("global_1024_sub_64_mpi25pt", ["-d", "1024", "-s", "64", "-I", "10", "-g", str(n), "-S", "mpi25pt"], 600)
+    run("global_1024_sub_64", ["-d", "1024", "-s", "64", "-I", "10", "-g", str(n), "-S", "mpi7pt"], 150)
+    run("global_1024_sub_64_mpi25pt", ["-d", "1024", "-s", "64", "-I", "10", "-g", str(n), "-S", "mpi25pt"], 150)
     if n == 1:
-        run("share_512_stitched", ["-d", "512", "-s", "64", "-I", "20", "-g", "1", "-S", "mpi7pt"], 300)
-        run("share_512_per_subdomain", ["-d", "512", "-s", "64", "-I", "20", "-g", "1", "-S", "mpi7pt", "-M"], 300)
+        run("share_512_stitched", ["-d", "512", "-s", "64", "-I", "20", "-g", "1", "-S", "mpi7pt"], 90)
+        run("share_512_per_subdomain", ["-d", "512", "-s", "64", "-I", "20", "-g", "1", "-S", "mpi7pt", "-M"], 90)
     out["what"] = f"strong scaling: fixed 1024^3 global domain in 64^3 subdomains on {n} GPU(s); 10 exchange periods after 1 warm-up"
     return out
 
 
-def array_baseline_leg(n):
+def array_baseline_leg(n, wd=None):
     """the reference's `Arr:` vs `Bri:` comparison through the C++ weak driver on all n GPUs -- the same
     512^3-per-GPU job on a plain array layout (arr_kernel + exchangeArr as one strided-box pull) and on bricks"""
     exe = os.path.join(ROOT, "drivers", "weak")
     out = {"what": f"drivers/weak -s 512,512,512 -I 10 -g {n} -S <stencil>: array-layout loop, then the brick loop, same input"}
     for name in ("mpi7pt", "mpi25pt"):
+        timeout = leg_timeout(wd, 150)
+        if not timeout:
+            out[name] = {"skipped": "no time left inside the bench's deadline for extras"}
+            continue
         try:
             r = subprocess.run([exe, "-s", "512,512,512", "-I", "10", "-g", str(n), "-S", name], capture_output=True, text=True,
-                               timeout=600, env=driver_env())
+                               timeout=timeout, env=driver_env())
             perf = [float(ln.split()[1]) for ln in r.stdout.splitlines() if ln.startswith("perf ")]
             if len(perf) == 2:
                 out[name] = {"array_GStencil/s": perf[0], "brick_GStencil/s": perf[1],
@@ -504,12 +566,15 @@ def array_baseline_leg(n):
     return out
 
 
-def single_leg():
+def single_leg(wd=None):
     """BASELINE.json configs[0]: the single-GPU 7-point case of single/cuda.cpp (coeff[] stencil, in/out interleaved in one
     storage, step 1024), through the C++ single driver: kernel-only sweep rate + the host array sweep it validates against"""
     exe = os.path.join(ROOT, "drivers", "single")
+    timeout = leg_timeout(wd, 120)
+    if not timeout:
+        return {"skipped": "no time left inside the bench's deadline for extras"}
     try:
-        r = subprocess.run([exe, "-n", "512", "-s", "7pt", "-r", "50"], capture_output=True, text=True, timeout=180, env=driver_env())
+        r = subprocess.run([exe, "-n", "512", "-s", "7pt", "-r", "50"], capture_output=True, text=True, timeout=timeout, env=driver_env())
         out = {"what": "drivers/single -n 512 -s 7pt -r 50 (one sweep per launch, interleaved storage)"}
         for ln in r.stdout.splitlines():
             f = ln.split()
@@ -648,14 +713,20 @@ def main():
     }
     line["roofline"]["traffic_source"] = "ncu --set full capture of this kernel at this size (profiles/traffic.json), per launch"
 
+    wd = Watchdog(rank, float(os.environ.get("BENCH_EXTRAS_DEADLINE_S", "420")))
+    wd.at("headline done", line)
     if not args.no_extras:
         # what was timed is also checked: sampled boxes vs the oracle, fused pass vs two sweeps on the device
+        wd.at("parity")
         line["parity"] = parity_of(bk, d, dist)
+        wd.at("others", line)
         others = {}
+        line["others"] = others
         k_other = max(3, args.steps // 4)
         for name, sid in bk.STENCILS.items():
             if name in ("7pt", args.stencil):
                 continue
+            wd.at("others." + name)
             d.stencil, d.st_iter = sid, L.bk_stencil_st_iter(sid)
             d.fill_synthetic(0x5EED)
             s2, _ = time_periods(bk, d, k_other, 3, dist)
@@ -670,8 +741,9 @@ def main():
                             ("; the kernel EXECUTES ~50 flop per point (sign/permutation folds: 16 adds + 18 FMA), i.e. "
                              f"{50 * pts * ks / k2 / 1e12:.1f} TFLOP/s executed" if name == "mpi125pt" else ""),
                             "parity": parity_of(bk, d, dist)}
+            wd.at("others." + name + " done", line)
         d.stencil, d.st_iter = st, it
-        line["others"] = others
+        wd.at("e2e", line)
         e2e_s, bi, bo = e2e_periods(bk, [d, make_domain(), make_domain()], 9)
         e2e_s = max_over_ranks(dist, e2e_s)
         line["e2e"] = {"value": pts * it * n / e2e_s / 1e9, "unit": "GStencil/s", "h2d_bytes_per_step": bi * n,
@@ -680,7 +752,9 @@ def main():
                        "what": "per rank and step: H2D of the interior bricks from pinned host memory, exchange + sweeps, D2H "
                                "of the result bricks; three independent fields in flight, upload / compute / download on "
                                "separate streams; max over ranks"}
+        wd.at("e2e done", line)
         if n == 1:
+            wd.at("cpu_baseline")
             try:
                 cs, kind, cores, isa = reference_period_seconds(st, size, 2, 1)
                 line["cpu_baseline"] = {"value": pts * it / cs / 1e9, "unit": "GStencil/s", "cores": cores, "kind": kind,
@@ -688,25 +762,33 @@ def main():
             except Exception as exc:  # the checker is optional for the product arm
                 line["cpu_baseline"] = {"value": None, "unit": "GStencil/s", "cores": 0, "kind": "port",
                                         "sample": f"unavailable: {exc}"}
+            wd.at("cpu_baseline done", line)
 
     if dist is not None:
+        wd.at("leaving the process group")
         barrier(dist)
         dist.destroy_process_group()
     if rank != 0:
+        wd.finish()
         return
     if not args.no_extras:
         # strong scaling (configs[4]), the array-layout baseline (8f#4) and the single driver (configs[0]) run through the
         # C++ drivers, one host thread per GPU, on ALL n GPUs.  They come last: the other ranks have left and this rank's
-        # own device memory is released first, so the drivers have the GPUs to themselves.
+        # own device memory is released first, so the drivers have the GPUs to themselves.  Each leg gets what is left of
+        # the extras' deadline (and is skipped when that is too little): a stuck driver cannot take the line with it.
         others = line["others"]
         d = None
         import gc
         gc.collect()
+        wd.at("waiting for the other ranks to leave the GPUs", line)
         wait_for_quiet_gpus(n)
-        others["strong"] = strong_leg(n)
-        others["array_layout_baseline"] = array_baseline_leg(n)
+        wd.at("strong", line)
+        others["strong"] = strong_leg(n, wd)
+        wd.at("array baseline", line)
+        others["array_layout_baseline"] = array_baseline_leg(n, wd)
         if n == 1:
-            others["single_7pt_512"] = single_leg()
+            wd.at("single", line)
+            others["single_7pt_512"] = single_leg(wd)
         line["baseline_configs"] = {
             "configs[0] single 7pt 512^3 (N=1 only)": others.get("single_7pt_512", {}).get("GStencil/s"),
             "configs[1] 125pt 512^3 per GPU": others.get("mpi125pt", {}).get("GStencil/s"),
@@ -715,6 +797,7 @@ def main():
             "configs[4] strong 1024^3 in 64^3 subdomains": others["strong"].get("global_1024_sub_64", {}).get("GStencil/s"),
             "unit": f"GStencil/s, whole job on {n} GPU(s)",
         }
+    wd.finish()
     print(json.dumps(line))
 
 

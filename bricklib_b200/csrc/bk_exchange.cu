@@ -148,9 +148,22 @@ int sm_count() {
 
 uint64_t **flag_slot(bk_xplan *p) { return p->flagbuf_dev + (size_t) (p->flag_turn++ % kFlagSlots) * kFlagSlotLen; }
 
+// The wait for the peers' "my skin is final" flags is a ONE-CTA kernel (k_wait) launched just ahead of the pull on the same
+// stream, not a spin inside the pull itself: a wide pull whose every CTA spins holds all the CTA slots of the GPU for as
+// long as the slowest peer takes.  That (a) keeps the READY half of the split sweep off the SMs exactly when it should
+// overlap the exchange, and (b) can deadlock two processes that each keep several independent domains in flight (the
+// end-to-end leg of bench.py: domain 1's spinning pull fills GPU A and waits for B, while B's signal for domain 1 sits
+// behind B's spinning pull of domain 0, which waits for a signal A cannot schedule).  A spinner that holds one small CTA
+// never keeps another kernel from being scheduled.
 int launch_copy(bk_xplan *p, uint64_t *const *wait_dev, int nwait, cudaStream_t s, int nsignal = 0,
-                uint64_t *gate = nullptr, bool publish = false) {
+                uint64_t *gate = nullptr, bool publish = false, uint64_t epoch = 0) {
   if (p->nchunks == 0 && nwait == 0 && !publish) return BK_OK;
+  if (nwait > 0) {
+    k_wait<<<1, 64, 0, s>>>(wait_dev, nwait, epoch);
+    BK_LAUNCHED();
+    nwait = 0;
+    if (p->nchunks == 0 && !publish) return BK_OK;
+  }
   unsigned long long want = p->nchunks ? p->nchunks : 1;
   unsigned threads = kThreads;
   unsigned long long cap = (unsigned long long) sm_count() * 8;
@@ -269,7 +282,7 @@ int bk_xplan_run_sync(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwai
   for (int i = 0; i < nsignal; ++i) host[65 + i] = signal_flags[i];
   uint64_t **fb = flag_slot(p);
   BK_CUDA(cudaMemcpyAsync(fb, host, sizeof(host), cudaMemcpyHostToDevice, s));
-  int rc = launch_copy(p, fb, nwait, s);
+  int rc = launch_copy(p, fb, nwait, s, 0, nullptr, false, epoch);
   if (rc != BK_OK) return rc;
   if (nsignal > 0) {
     k_signal<<<1, 64, 0, s>>>(fb + 65, nsignal, epoch);
@@ -289,7 +302,7 @@ int bk_xplan_run_gate(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwai
   for (int i = 0; i < nsignal; ++i) host[65 + i] = signal_flags[i];
   uint64_t **fb = flag_slot(p);
   BK_CUDA(cudaMemcpyAsync(fb, host, sizeof(host), cudaMemcpyHostToDevice, s));
-  return launch_copy(p, fb, nwait, s, nsignal, gate, true);
+  return launch_copy(p, fb, nwait, s, nsignal, gate, true, epoch);
 }
 
 // The same plan with the big segments on the COPY ENGINES: no SM is taken from the sweep kernels, which matters because

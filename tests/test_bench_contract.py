@@ -68,3 +68,31 @@ def test_clock_sampler_degrades_without_a_gpu():
     s.start()
     out = s.stop()
     assert set(out) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_watchdog_prints_the_last_snapshot_when_an_extra_hangs():
+    """a hung optional leg must not take the JSON line with it: the watchdog prints the last complete snapshot (rank 0)
+    and every rank exits 0"""
+    code = ("import sys, time; sys.path.insert(0, %r); import bench\n"
+            "rank = int(sys.argv[1]); wd = bench.Watchdog(rank, 0.6)\n"
+            "wd.at('headline done', {'metric': 'GStencil/s', 'value': 1.0})\n"
+            "wd.at('e2e')\n"
+            "time.sleep(30)\n" % ROOT)
+    r0 = subprocess.run([sys.executable, "-c", code, "0"], capture_output=True, text=True, timeout=20)
+    assert r0.returncode == 0
+    d = json.loads(r0.stdout.strip().splitlines()[-1])
+    assert d["value"] == 1.0 and d["extras_truncated"]["stage"] == "e2e"
+    r1 = subprocess.run([sys.executable, "-c", code, "1"], capture_output=True, text=True, timeout=20)
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
+    # a finished run is left alone
+    code2 = ("import sys, time; sys.path.insert(0, %r); import bench\n"
+             "wd = bench.Watchdog(0, 0.3); wd.at('x', {'value': 2}); wd.finish(); time.sleep(0.8); print('end')\n" % ROOT)
+    r2 = subprocess.run([sys.executable, "-c", code2], capture_output=True, text=True, timeout=20)
+    assert r2.returncode == 0 and r2.stdout.strip() == "end"
+    import bench
+    assert bench.leg_timeout(None, 150) == 150
+    wd = bench.Watchdog(1, 1000.0)
+    assert 100 < bench.leg_timeout(wd, 150) <= 150
+    wd.seconds = 10.0
+    assert bench.leg_timeout(wd, 150) == 0
+    wd.finish()
