@@ -435,6 +435,68 @@ def e2e_periods(bk, doms, steps):
     return sec / steps, nbytes, nbytes
 
 
+def select_fused_kernel(bk, d, dist, rank, want):
+    """Which kernel advances two time steps per pass for the radius-1 stars: the staged one (k_star2, intermediate plane
+    in shared memory) or the composed one (one 25-point diamond update, bricklib_b200/csrc/bk_diamond.h)?  Measure, don't
+    guess: (1) rank 0 lets a CHILD process run the composed kernel first (tools/composed_trial.py: parity against two
+    plain sweeps over the whole interior, a few timed launches) -- a fault or hang there costs the child, not this run;
+    (2) every rank checks the composed kernel against two plain sweeps on the device and times both kernels on its own
+    domain; (3) the composed kernel is used only if every rank found it exact (< 1e-12, 0 mismatching cells) AND it is
+    faster (max over ranks).  Returns the record that goes into the JSON line."""
+    info = {"policy": want, "selected": "staged"}
+    if d.steps_per_pass() != 2:
+        info["why"] = "one sweep per pass for this stencil / these options"
+        return info
+    before = bk.fused_variant()
+    if want == "staged":
+        bk.fused_variant(bk.FUSED_STAGED)
+        info["why"] = "forced"
+        return info
+    try:
+        trial_ok = 1.0
+        if rank == 0:
+            trial_ok = 0.0
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "composed_trial.py"), "--device",
+                                    os.environ.get("LOCAL_RANK", "0"), "--size", str(d.dom[0]), "--stencil",
+                                    {v: k for k, v in bk.STENCILS.items()}[d.stencil]],
+                                   capture_output=True, text=True, timeout=150, cwd=ROOT)
+                lines = [x for x in r.stdout.splitlines() if x.startswith("{")]
+                if r.returncode == 0 and lines:
+                    info["child_trial"] = json.loads(lines[-1])
+                    trial_ok = 1.0 if info["child_trial"].get("ok") else 0.0
+                else:
+                    info["child_trial"] = {"ok": False, "rc": r.returncode, "tail": (r.stdout + r.stderr)[-400:]}
+            except Exception as exc:
+                info["child_trial"] = {"ok": False, "error": str(exc)[:300]}
+        if max_over_ranks(dist, 1.0 - trial_ok) > 0.0:       # rank 0's verdict, known to all
+            bk.fused_variant(bk.FUSED_STAGED)
+            info["why"] = "the composed kernel failed its trial in a child process"
+            return info
+        bk.fused_variant(bk.FUSED_STAGED)
+        t_staged = max_over_ranks(dist, time_sweeps(bk, d, 10)[0])
+        bk.fused_variant(bk.FUSED_COMPOSED)
+        bad, worst, pts = fused_vs_two_sweeps(bk, d)
+        bad, worst = sum_over_ranks(dist, bad), max_over_ranks(dist, worst)
+        t_comp = max_over_ranks(dist, time_sweeps(bk, d, 10)[0])
+        exact = bad == 0 and worst < PARITY_TOL
+        info.update({"staged_launch_ms": t_staged * 1e3, "composed_launch_ms": t_comp * 1e3,
+                     "composed_vs_two_sweeps": {"mismatches": int(bad), "max_rel": worst, "points_per_rank": int(pts)}})
+        if want == "composed" and exact:
+            info["selected"], info["why"] = "composed", "forced (and exact)"
+        elif exact and t_comp < t_staged:
+            info["selected"], info["why"] = "composed", "exact on every rank and faster"
+        else:
+            info["why"] = "not exact" if not exact else "exact but not faster"
+        bk.fused_variant(bk.FUSED_COMPOSED if info["selected"] == "composed" else bk.FUSED_STAGED)
+        d.fill_synthetic(0x5EED)
+        bk.device_sync()
+    except Exception as exc:
+        bk.fused_variant(before if before == bk.FUSED_STAGED else bk.FUSED_STAGED)
+        info["selected"], info["why"] = "staged", f"selection failed: {str(exc)[:200]}"
+    return info
+
+
 def reference_period_seconds(stencil_id, size, periods, warm=1, cart=(1, 1, 1)):
     """the reference's own CPU implementation of the path (oracle/_ref: its BrickDecomp, its exchange() over the
     in-process MPI stand-in, its generated AVX brick code) on all host threads; else the C port.  `cart` ranks are run
@@ -632,6 +694,9 @@ def main():
     ap.add_argument("--size", type=int, default=512, help="cells per axis per GPU")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="one sweep per pass (no temporal blocking)")
+    ap.add_argument("--fused", default="auto", choices=["auto", "staged", "composed"],
+                    help="kernel behind the two-steps-per-pass launches of the radius-1 stars: k_star2 (staged), the composed "
+                         "25-point diamond, or whichever is exact and faster on this box (auto)")
     ap.add_argument("--no-extras", action="store_true", help="skip other stencils / strong / e2e / cpu baseline / parity")
     ap.add_argument("--kernel", default="auto", choices=["auto", "brick", "tiled"])
     ap.add_argument("--transport", default="kernel", choices=["kernel", "ce"],
@@ -679,6 +744,9 @@ def main():
         return dm
 
     d = make_domain()
+    fused_info = select_fused_kernel(bk, d, dist, rank, args.fused)
+    if fused_info["selected"] == "composed":
+        os.environ["BK_FUSED_VARIANT"] = "composed"     # the C++ driver legs inherit the choice
 
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     if rank == 0:
@@ -691,9 +759,10 @@ def main():
     peak, peak_src = measured_peak()
     sweep_s, sweep_steps = time_sweeps(bk, d, 20)
     traffic = None
+    composed = sweep_steps == 2 and fused_info["selected"] == "composed"
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
-            args.stencil + ("_fused2" if sweep_steps == 2 else ""))
+            args.stencil + ("_composed2" if composed else "_fused2" if sweep_steps == 2 else ""))
     except Exception:
         pass
 
@@ -711,7 +780,12 @@ def main():
         "roofline": roofline_of(pts, sweep_s, sweep_steps, peak, peak_src, traffic),
         "clocks": clocks,
     }
-    line["roofline"]["traffic_source"] = "ncu --set full capture of this kernel at this size (profiles/traffic.json), per launch"
+    line["roofline"]["traffic_source"] = ("ncu --set full capture of this kernel at this size (profiles/traffic.json), per launch"
+                                          if traffic is not None else "no ncu capture of this kernel yet")
+    if composed:
+        line["roofline"]["kernel"] = ("k_star_capped<diamond> (two time steps as ONE composed 25-point update): one launch = "
+                                      f"{pts} interior points x 2 step(s) x 16 B")
+    line["fused_kernel"] = fused_info
 
     wd = Watchdog(rank, float(os.environ.get("BENCH_EXTRAS_DEADLINE_S", "420")))
     wd.at("headline done", line)

@@ -22,6 +22,7 @@
 // Summation order per output point (fixed): k-minus taps d=R..1, centre, i taps d=1..R (+d then -d), j taps d=1..R
 // (+d then -d), k-plus taps d=1..R.  Parity with the reference is to 1e-12 relative, not bitwise.
 #include "bk_common.h"
+#include "bk_diamond.h"
 #include <cstddef>
 #include <cstdint>
 #include <cstdlib>
@@ -51,7 +52,10 @@ struct Cfg {
   // 65536/NT registers per thread, the producer warpgroup shrinks to PREG and the consumer warpgroups grow to CREG
   [[maybe_unused]] static constexpr int CREG = CREG_, PREG = PREG_, FLAGS = FLAGS_;
   static constexpr bool CUBE = CUBE_;                 // (2R+1)^3 cube stencil instead of a star
-  using Coef = typename std::conditional<CUBE_, bk::CubeCoef, bk::StarCoef>::type;
+  // FLAGS & 2: the composed two-step update of a radius-1 star (bk_diamond.h) on the radius-2 geometry
+  static constexpr bool DIAM = (FLAGS_ & 2) != 0;
+  using Coef = typename std::conditional<CUBE_, bk::CubeCoef,
+                                         typename std::conditional<DIAM, bk::DiamondCoef, bk::StarCoef>::type>::type;
   static constexpr int R = R_, YT = YT_, TI = TI_, TJ = TJ_, G = G_, D = D_;
   static constexpr int W = 2 * R + 1;                 // partial outputs in flight per point
   static constexpr int RUP = ((R + G - 1) / G) * G;   // halo planes streamed before/after a segment (multiple of G)
@@ -63,7 +67,7 @@ struct Cfg {
   static constexpr int NCW = NCONS / 32;
   static constexpr int NPW = NPW_;                    // producer warps (bulk-copy issue is instruction bound)
   static constexpr int NT = NCONS + 32 * NPW;
-  static constexpr int NJH = CUBE ? TI + 2 : TI;      // j-halo columns: a cube stencil also needs the corner bricks
+  static constexpr int NJH = (CUBE || DIAM) ? TI + 2 : TI;  // j-halo columns: cube and diamond also need the corner bricks
   static constexpr int NCOPY = TI * TJ + 2 * TJ + 2 * NJH;  // copy jobs per stage (j-halo jobs issue G copies)
   static constexpr int JOBS = (NCOPY + 32 * NPW - 1) / (32 * NPW);
   [[maybe_unused]] static constexpr int MAXREG = MAXREG_;              // register cap (chosen so that the intended CTAs/SM fit)
@@ -71,6 +75,7 @@ struct Cfg {
   static constexpr int OVH = 2 * RUP + 2;             // cost-model overhead planes per segment (halo planes + fill)
   static constexpr bool FUSED = false;
   static_assert(8 % G == 0 && 8 % YT == 0 && TI % 2 == 0 && 2 * R <= 8, "geometry");
+  static_assert(!DIAM || (R == 2 && !CUBE), "the composed two-step update runs on the radius-2 star geometry");
   static_assert(CREG == 0 || (NCW % 4 == 0 && NPW == 4 && NCONS * CREG + 128 * PREG <= 65536), "setmaxnreg needs warpgroups");
   // SW is even, so the bank half of a slot depends on its column only: a quarter warp (4 x-pairs of 2 i-adjacent
   // bricks) reads 8 distinct 16-B bank groups
@@ -140,7 +145,7 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
       } else if ((job -= TI * TJ) < 2 * TJ) {
         kind[q] = 1, sbi[q] = (job & 1) ? TI + 1 : 0, sbj[q] = 1 + (job >> 1);
       } else if ((job -= 2 * TJ) < 2 * C::NJH) {
-        kind[q] = 2 + (job & 1), sbi[q] = (C::CUBE ? 0 : 1) + (job >> 1), sbj[q] = (job & 1) ? TJ + 1 : 0;
+        kind[q] = 2 + (job & 1), sbi[q] = ((C::CUBE || C::DIAM) ? 0 : 1) + (job >> 1), sbj[q] = (job & 1) ? TJ + 1 : 0;
       }
       // both j-halo kinds land in slot row 0: rows [8-R,8) from below (kind 2), rows [0,R) from above (kind 3)
       dsto[q] = C::slotoff(sbi[q], kind[q] >= 2 ? 0 : sbj[q]) + (kind[q] == 2 ? (8 - R) * 64 : 0);
@@ -238,6 +243,15 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
   const size_t glayer = (size_t) a.gy * a.gx;
   unsigned id_next = mine ? __ldg(gcol) : 0u;
   double *outp = fout;
+  [[maybe_unused]] unsigned edge_ij = 0;  // diamond: which of my cells lie on a grid face along i / j (bk_diamond.h)
+  if constexpr (C::DIAM) {
+    const int gi = i0 + bi, gj = j0 + bj;
+    if (gi == 0 && c == 0) edge_ij |= 1u;
+    if (gi == a.gx - 1 && c == 3) edge_ij |= 2u;
+#pragma unroll
+    for (int r = 0; r < YT; ++r)
+      if ((gj == 0 && y0 + r == 0) || (gj == a.gy - 1 && y0 + r == 7)) edge_ij |= 4u << r;
+  }
 
   double2 acc[W][YT];
 #pragma unroll
@@ -329,6 +343,17 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
             acc[sp1][r].x += p1.x, acc[sp1][r].y += p1.y;
             acc[sN][r] = p2;
           }
+          store_plane(acc[sF]);
+        } else if constexpr (C::DIAM) {
+          // two time steps of a radius-1 star as one composed update (bk_diamond.h); plane tb+u is absolute plane zt
+          static_assert(!C::DIAM || (W == 5 && R == 2), "diamond_plane keeps five partial outputs");
+          double2 v[YT];
+#pragma unroll
+          for (int r = 0; r < YT; ++r) v[r] = *reinterpret_cast<const double2 *>(pb + own_off + r * 64);
+          const int zt = kb0 * 8 - RUP + tb + u;
+          const unsigned edge = edge_ij | ((zt == 0 || zt == a.gz * 8 - 1) ? bk::kDiamondEdgeK : 0u);
+          bk::diamond_plane<YT>(pb, own_off, joff[0], joff[1], joff[2 * R - 2], joff[2 * R - 1], ioffL[0], ioffR[0], cf, acc, u,
+                                edge, v);
           store_plane(acc[sF]);
         } else {
           double2 v[YT];
@@ -1054,7 +1079,29 @@ int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, 
   });
 }
 
+std::atomic<int> g_fused_variant{-1};  // -1: not initialised (the environment decides at first use)
+int fused_variant() {
+  int v = g_fused_variant.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char *e = getenv("BK_FUSED_VARIANT");
+    v = (e && (e[0] == 'c' || e[0] == 'C' || e[0] == '1')) ? BK_FUSED_COMPOSED : BK_FUSED_STAGED;
+    int expect = -1;
+    if (!g_fused_variant.compare_exchange_strong(expect, v)) v = expect;
+  }
+  return v;
+}
+
 }  // namespace
+
+extern "C" {
+int bk_stencil_fused_variant_set(int variant) {
+  BK_REQUIRE(variant == BK_FUSED_STAGED || variant == BK_FUSED_COMPOSED, "BK_FUSED_STAGED or BK_FUSED_COMPOSED");
+  const int before = fused_variant();
+  g_fused_variant.store(variant, std::memory_order_relaxed);
+  return before;
+}
+int bk_stencil_fused_variant_get(void) { return fused_variant(); }
+}
 
 namespace bk {
 
@@ -1088,6 +1135,12 @@ int launch_tiled(const CoefSpec &spec, const bk_field_t &f, const bk_field_t *mu
   const StarCoef &sc = spec.sc;
   const int r = spec.radius;
   if (steps == 2) {  // two time steps per pass: (R, YT, TI, TJ, D, producer warps)
+    if (r == 1 && fused_variant() == BK_FUSED_COMPOSED) {
+      // the composed operator on the radius-2 star geometry: 4x4-brick tiles, 4 consumer + 2 producer warps, 2 CTAs per SM
+      const bk::DiamondCoef dc = bk::diamond_coef(sc.c0, sc.cp[0][0], sc.cm[0][0], sc.cp[1][0], sc.cm[1][0], sc.cp[2][0], sc.cm[2][0]);
+      if (v == 1) return launch_cfg<Cfg<2, 2, 4, 4, 2, 3, 128, 2, false, 0, 40, 2>>(a, dc, s, nsub, part, rdy_lo, rdy_hi);
+      return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 168, 2, false, 0, 40, 2>>(a, dc, s, nsub, part, rdy_lo, rdy_hi);
+    }
     if (r == 1) {
       if (v == 1) return launch_cfg<FCfg<1, 4, 8, 4, 4, 4>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);
       if (v == 2) return launch_cfg<FCfg<1, 2, 4, 4, 3, 2, 2>>(a, sc, s, nsub, part, rdy_lo, rdy_hi);

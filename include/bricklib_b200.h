@@ -46,6 +46,16 @@ int bk_stencil_st_iter(int stencil); /* sweeps per ghost exchange: 8,8,4,2,4 (= 
 int bk_stencil_points(int stencil);  /* 7,7,13,25,125 */
 int bk_stencil_fused_steps(int stencil); /* `steps` of bk_stencil_advance that is fastest: 2,2,1,1,1 (radius 2 can fuse, but its
                                             two-step kernel is slower than two sweeps) */
+/* Which kernel runs bk_stencil_advance(steps = 2) for the radius-1 stars (7pt, mpi7pt and compiled radius-1 stars):
+ *   BK_FUSED_STAGED   (default) k_star2: two stencil stages per plane, the intermediate plane in shared memory;
+ *   BK_FUSED_COMPOSED the composed operator S(S u), a 25-point diamond, as ONE radius-2 marching update
+ *                     (bricklib_b200/csrc/bk_diamond.h) -- same semantics incl. the zero intermediate outside the grid.
+ * Process-wide; the environment variable BK_FUSED_VARIANT=staged|composed sets the initial value.  _set returns the
+ * previous value, or BK_EINVAL. */
+#define BK_FUSED_STAGED 0
+#define BK_FUSED_COMPOSED 1
+int bk_stencil_fused_variant_set(int variant);
+int bk_stencil_fused_variant_get(void);
 
 /* ---- device plumbing (stands in for include/brick-gpu.h:43-103 movBrickInfo/movBrickStorage, cudaarray.h:11-31) - */
 int bk_device_count(int *n);

@@ -96,3 +96,67 @@ def test_watchdog_prints_the_last_snapshot_when_an_extra_hangs():
     wd.seconds = 10.0
     assert bench.leg_timeout(wd, 150) == 0
     wd.finish()
+
+
+class _FakeDomain:
+    dom, stencil = (512, 512, 512), 1
+
+    def __init__(self, steps=2):
+        self.steps, self.filled = steps, 0
+
+    def steps_per_pass(self):
+        return self.steps
+
+    def fill_synthetic(self, seed):
+        self.filled += 1
+
+
+class _FakeBk:
+    FUSED_STAGED, FUSED_COMPOSED, STENCILS = 0, 1, {"7pt": 0, "mpi7pt": 1}
+
+    def __init__(self):
+        self.variant = 0
+
+    def fused_variant(self, v=None):
+        before = self.variant
+        if v is not None:
+            self.variant = v
+        return before
+
+    def device_sync(self):
+        pass
+
+
+def test_fused_kernel_selection_policy(monkeypatch):
+    """bench.select_fused_kernel: the composed kernel is used only when its child trial passed, it is exact on the device
+    and it is faster; whatever goes wrong leaves the proven staged kernel in place (no GPU needed: everything mocked)"""
+    import bench
+
+    class R:
+        def __init__(self, rc, out):
+            self.returncode, self.stdout, self.stderr = rc, out, ""
+
+    def scenario(child, t_staged, t_comp, parity=(0, 1e-16, 10), want="auto", steps=2):
+        fake, dom = _FakeBk(), _FakeDomain(steps)
+        monkeypatch.setattr(bench.subprocess, "run", lambda *a, **k: child() if callable(child) else child)
+        monkeypatch.setattr(bench, "time_sweeps", lambda bk, d, reps: ((t_comp if bk.variant else t_staged), 2))
+        monkeypatch.setattr(bench, "fused_vs_two_sweeps", lambda bk, d: parity)
+        info = bench.select_fused_kernel(fake, dom, None, 0, want)
+        assert (fake.variant == 1) == (info["selected"] == "composed")
+        return info
+
+    ok = R(0, 'noise\n{"ok": true, "composed": {"launch_ms": 0.39}}\n')
+    assert scenario(ok, 0.46e-3, 0.39e-3)["selected"] == "composed"
+    assert scenario(ok, 0.46e-3, 0.50e-3)["why"] == "exact but not faster"
+    assert scenario(ok, 0.46e-3, 0.39e-3, parity=(3, 0.2, 10))["why"] == "not exact"
+    assert scenario(ok, 0.46e-3, 0.39e-3, parity=(0, 1e-9, 10))["selected"] == "staged"
+    assert scenario(R(-11, ""), 0.46e-3, 0.39e-3)["selected"] == "staged"                      # the child crashed
+    assert scenario(R(0, '{"ok": false}'), 0.46e-3, 0.39e-3)["selected"] == "staged"           # the child found a mismatch
+
+    def hang():
+        raise bench.subprocess.TimeoutExpired("trial", 150)
+    assert scenario(hang, 0.46e-3, 0.39e-3)["selected"] == "staged"                            # the child hung
+    assert scenario(ok, 0.46e-3, 0.39e-3, want="staged")["why"] == "forced"
+    assert scenario(ok, 0.46e-3, 0.50e-3, want="composed")["selected"] == "composed"           # forced, still has to be exact
+    assert scenario(ok, 0.46e-3, 0.39e-3, parity=(1, 1.0, 10), want="composed")["selected"] == "staged"
+    assert scenario(ok, 0.46e-3, 0.39e-3, steps=1)["selected"] == "staged"                     # nothing to select
