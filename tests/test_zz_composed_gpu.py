@@ -14,8 +14,35 @@ def rel(a, b):
     return float((np.abs(a - b) / (np.abs(a) + np.abs(b) + 1e-300)).max())
 
 
+@pytest.fixture(scope="module")
+def first_contact():
+    """the kernel's first run happens in a CHILD process (tools/composed_trial.py: every launch shape on a small
+    decomposition, then parity and timing at 128^3): a fault or a hang there must not take this pytest process -- and the
+    record of the whole suite -- with it.  The in-process tests below run only when the child came back clean."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    try:
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "composed_trial.py"), "--size", "128"], capture_output=True,
+                           text=True, timeout=240, cwd=root)
+    except subprocess.TimeoutExpired:
+        return {"ok": False, "why": "the child trial did not finish in 240 s"}
+    lines = [x for x in r.stdout.splitlines() if x.startswith("{")]
+    if r.returncode != 0 or not lines:
+        return {"ok": False, "why": f"rc {r.returncode}: {(r.stdout + r.stderr)[-1500:]}"}
+    return json.loads(lines[-1])
+
+
+def test_first_contact_in_a_child_process(first_contact):
+    assert first_contact["ok"], first_contact
+
+
 @pytest.fixture
-def composed():
+def composed(first_contact):
+    if not first_contact["ok"]:
+        pytest.skip("the composed kernel failed its first contact (see test_first_contact_in_a_child_process)")
     before = bk.fused_variant(bk.FUSED_COMPOSED)
     yield
     bk.fused_variant(before)
@@ -115,3 +142,35 @@ def test_full_size_composed_pass_equals_two_sweeps_on_a_random_field(composed):
     assert bad == 0 and worst < 1e-12 and pts == 512 ** 3
     got, n = bench.sampled_parity(bk, d)
     assert got < 1e-12 and n > 0
+
+
+def _driver_composed(*args):
+    """a C++ driver in a process of its own with BK_FUSED_VARIANT=composed: self-validating against a CPU sweep of the
+    global periodic array, like the reference's drivers"""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "drivers", args[0])
+    if not os.path.exists(exe):
+        pytest.fail(f"{exe} is not built: run __graft_entry__.build()")
+    r = subprocess.run([exe, *args[1:]], capture_output=True, text=True, timeout=300, env=dict(os.environ, BK_FUSED_VARIANT="composed"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+@pytest.mark.parametrize("ranks,dom", [(1, "32,32,32"), (4, "32,24,40")])
+def test_cpp_weak_driver_through_the_composed_kernel(first_contact, ranks, dom):
+    if not first_contact["ok"]:
+        pytest.skip("the composed kernel failed its first contact")
+    out = _driver_composed("weak", "-s", dom, "-I", "2", "-g", str(ranks), "-S", "mpi7pt", "-v")
+    assert "result match (worst relative difference" in out and "Arr == Bri: result match" in out
+
+
+@pytest.mark.parametrize("ranks,d,s", [(1, 64, 32), (8, 128, 32), (2, 128, 64)])
+def test_cpp_strong_driver_stitched_grid_through_the_composed_kernel(first_contact, ranks, d, s):
+    """the stitched super grid aliases shell positions onto other subdomains' bricks: the composed kernel resolves every
+    neighbour through grid POSITIONS exactly like the staged one, so the periodic result must come out the same"""
+    if not first_contact["ok"]:
+        pytest.skip("the composed kernel failed its first contact")
+    out = _driver_composed("strong", "-d", str(d), "-s", str(s), "-I", "2", "-g", str(ranks), "-S", "mpi7pt", "-v")
+    assert "result match (worst relative difference" in out and f"stitched ranks {ranks} of {ranks}" in out

@@ -12,6 +12,47 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def small_boxes(bk):
+    """every launch shape the library issues, on a small decomposition: whole grid (all six grid faces), interior, an
+    off-centre box, and the READY / REST halves of a split launch with and without thin segments -- composed kernel
+    against two plain sweeps; returns the worst relative difference"""
+    import numpy as np
+    rng = np.random.default_rng(3)
+    d = bk.BrickDecomp((40, 24, 32), 8)
+    info = d.getBrickInfo()
+    grid = bk.DeviceGrid(d.grid)
+    s_in, s_tmp, s_ref, s_got = (info.allocate(512) for _ in range(4))
+    h = rng.random(d.nbricks * 512)
+    h[:512] = 0.0
+    s_in.from_host(h)
+    b_in, b_tmp, b_ref, b_got = (bk.Brick(info, s) for s in (s_in, s_tmp, s_ref, s_got))
+    t = grid.dims
+    own = ((1, 1, 1), tuple(x - 1 for x in t))
+    worst = 0.0
+
+    def rel(a, b):
+        return float((np.abs(a - b) / (np.abs(a) + np.abs(b) + 1e-300)).max())
+
+    for lo, hi in [((0, 0, 0), t), own, ((1, 0, 1), (t[0], t[1] - 1, t[2]))]:
+        bk.stencil(1, grid, b_in, b_tmp, kernel=bk.KERNEL_TILED)
+        s_ref.dat.zero()
+        bk.stencil(1, grid, b_tmp, b_ref, lo, hi, kernel=bk.KERNEL_TILED)
+        s_got.dat.zero()
+        bk.stencil_advance(1, 2, grid, b_in, b_got, lo, hi)
+        bk.device_sync()
+        want = s_ref.to_host()
+        worst = max(worst, rel(s_got.to_host(), want))
+        for thin in (0, bk.PART_THIN):
+            parts = []
+            for part in (bk.PART_READY, bk.PART_REST):
+                s_got.dat.zero()
+                bk.stencil_advance(1, 2, grid, b_in, b_got, lo, hi, own, part | thin)
+                bk.device_sync()
+                parts.append(s_got.to_host())
+            worst = max(worst, rel(parts[0] + parts[1], want))
+    return worst
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--device", type=int, default=0)
@@ -21,6 +62,8 @@ def main():
     import bench
     import bricklib_b200 as bk
     bk._lib.check(bk.load().bk_set_device(a.device))
+    bk.fused_variant(bk.FUSED_COMPOSED)
+    small = small_boxes(bk)
     d = bk.WeakDomain((a.size,) * 3, bk.STENCILS[a.stencil])
     d.connect()
     out = {}
@@ -31,7 +74,8 @@ def main():
         out[name] = {"mismatches": int(bad), "max_rel": float(worst), "points": int(pts), "launch_ms": sec * 1e3,
                      "steps_per_launch": steps}
     c = out["composed"]
-    out["ok"] = bool(c["mismatches"] == 0 and c["max_rel"] < 1e-12 and c["steps_per_launch"] == 2)
+    out["small_boxes_max_rel"] = small
+    out["ok"] = bool(c["mismatches"] == 0 and c["max_rel"] < 1e-12 and c["steps_per_launch"] == 2 and small < 1e-13)
     print(json.dumps(out))
 
 
