@@ -435,64 +435,75 @@ def e2e_periods(bk, doms, steps):
     return sec / steps, nbytes, nbytes
 
 
+FUSED_NAMES = {"staged": 0, "composed": 1, "wide": 2}     # bricklib_b200.FUSED_STAGED / _COMPOSED / _COMPOSED_WIDE
+
+
 def select_fused_kernel(bk, d, dist, rank, want):
     """Which kernel advances two time steps per pass for the radius-1 stars: the staged one (k_star2, intermediate plane
-    in shared memory) or the composed one (one 25-point diamond update, bricklib_b200/csrc/bk_diamond.h)?  Measure, don't
-    guess: (1) rank 0 lets a CHILD process run the composed kernel first (tools/composed_trial.py: parity against two
+    in shared memory) or the composed one (one 25-point diamond update, bricklib_b200/csrc/bk_diamond.h; on 4x4-brick
+    tiles = "composed", on 8x4-brick tiles = "wide")?  Measure, don't guess: (1) rank 0 lets a CHILD process run the
+    composed kernels first (tools/composed_trial.py: every launch shape on a small decomposition, parity against two
     plain sweeps over the whole interior, a few timed launches) -- a fault or hang there costs the child, not this run;
-    (2) every rank checks the composed kernel against two plain sweeps on the device and times both kernels on its own
-    domain; (3) the composed kernel is used only if every rank found it exact (< 1e-12, 0 mismatching cells) AND it is
-    faster (max over ranks).  Returns the record that goes into the JSON line."""
+    (2) every rank checks each candidate that survived against two plain sweeps on the device and times it on its own
+    domain; (3) a composed kernel is used only if every rank found it exact (< 1e-12, 0 mismatching cells) AND it is the
+    fastest candidate (max over ranks).  Returns the record that goes into the JSON line."""
     info = {"policy": want, "selected": "staged"}
     if d.steps_per_pass() != 2:
         info["why"] = "one sweep per pass for this stencil / these options"
         return info
-    before = bk.fused_variant()
     if want == "staged":
-        bk.fused_variant(bk.FUSED_STAGED)
+        bk.fused_variant(FUSED_NAMES["staged"])
         info["why"] = "forced"
         return info
     try:
-        trial_ok = 1.0
+        alive = {"composed": 1.0, "wide": 1.0}
         if rank == 0:
-            trial_ok = 0.0
+            alive = {"composed": 0.0, "wide": 0.0}
             try:
                 r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "composed_trial.py"), "--device",
                                     os.environ.get("LOCAL_RANK", "0"), "--size", str(d.dom[0]), "--stencil",
                                     {v: k for k, v in bk.STENCILS.items()}[d.stencil]],
-                                   capture_output=True, text=True, timeout=150, cwd=ROOT)
+                                   capture_output=True, text=True, timeout=180, cwd=ROOT)
                 lines = [x for x in r.stdout.splitlines() if x.startswith("{")]
                 if r.returncode == 0 and lines:
                     info["child_trial"] = json.loads(lines[-1])
-                    trial_ok = 1.0 if info["child_trial"].get("ok") else 0.0
+                    for name in alive:
+                        alive[name] = 1.0 if info["child_trial"].get(name, {}).get("ok") else 0.0
                 else:
                     info["child_trial"] = {"ok": False, "rc": r.returncode, "tail": (r.stdout + r.stderr)[-400:]}
             except Exception as exc:
                 info["child_trial"] = {"ok": False, "error": str(exc)[:300]}
-        if max_over_ranks(dist, 1.0 - trial_ok) > 0.0:       # rank 0's verdict, known to all
-            bk.fused_variant(bk.FUSED_STAGED)
-            info["why"] = "the composed kernel failed its trial in a child process"
+        for name in sorted(alive):                              # rank 0's verdict, known to all
+            alive[name] = 0.0 if max_over_ranks(dist, 1.0 - alive[name]) > 0.0 else 1.0
+        if want in alive:
+            alive = {k: (v if k == want else 0.0) for k, v in alive.items()}
+        bk.fused_variant(FUSED_NAMES["staged"])
+        if not any(alive.values()):
+            info["why"] = "no composed kernel passed its trial in a child process"
             return info
-        bk.fused_variant(bk.FUSED_STAGED)
-        t_staged = max_over_ranks(dist, time_sweeps(bk, d, 10)[0])
-        bk.fused_variant(bk.FUSED_COMPOSED)
-        bad, worst, pts = fused_vs_two_sweeps(bk, d)
-        bad, worst = sum_over_ranks(dist, bad), max_over_ranks(dist, worst)
-        t_comp = max_over_ranks(dist, time_sweeps(bk, d, 10)[0])
-        exact = bad == 0 and worst < PARITY_TOL
-        info.update({"staged_launch_ms": t_staged * 1e3, "composed_launch_ms": t_comp * 1e3,
-                     "composed_vs_two_sweeps": {"mismatches": int(bad), "max_rel": worst, "points_per_rank": int(pts)}})
-        if want == "composed" and exact:
-            info["selected"], info["why"] = "composed", "forced (and exact)"
-        elif exact and t_comp < t_staged:
-            info["selected"], info["why"] = "composed", "exact on every rank and faster"
-        else:
-            info["why"] = "not exact" if not exact else "exact but not faster"
-        bk.fused_variant(bk.FUSED_COMPOSED if info["selected"] == "composed" else bk.FUSED_STAGED)
+        times = {"staged": max_over_ranks(dist, time_sweeps(bk, d, 10)[0])}
+        info["launch_ms"] = {"staged": times["staged"] * 1e3}
+        info["vs_two_sweeps"] = {}
+        for name in sorted(k for k, v in alive.items() if v):
+            bk.fused_variant(FUSED_NAMES[name])
+            bad, worst, pts = fused_vs_two_sweeps(bk, d)
+            bad, worst = sum_over_ranks(dist, bad), max_over_ranks(dist, worst)
+            t = max_over_ranks(dist, time_sweeps(bk, d, 10)[0])
+            info["launch_ms"][name] = t * 1e3
+            info["vs_two_sweeps"][name] = {"mismatches": int(bad), "max_rel": worst, "points_per_rank": int(pts)}
+            if bad == 0 and worst < PARITY_TOL:
+                times[name] = t
+        best = min(times, key=times.get)
+        if want in ("composed", "wide"):
+            best = want if want in times else "staged"
+        info["selected"] = best
+        info["why"] = ("forced (and exact)" if best == want else "fastest of the exact candidates" if best != "staged" else
+                       "no composed kernel was both exact and faster")
+        bk.fused_variant(FUSED_NAMES[best])
         d.fill_synthetic(0x5EED)
         bk.device_sync()
     except Exception as exc:
-        bk.fused_variant(before if before == bk.FUSED_STAGED else bk.FUSED_STAGED)
+        bk.fused_variant(FUSED_NAMES["staged"])
         info["selected"], info["why"] = "staged", f"selection failed: {str(exc)[:200]}"
     return info
 
@@ -694,9 +705,10 @@ def main():
     ap.add_argument("--size", type=int, default=512, help="cells per axis per GPU")
     ap.add_argument("--no-overlap", action="store_true")
     ap.add_argument("--no-fuse", action="store_true", help="one sweep per pass (no temporal blocking)")
-    ap.add_argument("--fused", default="auto", choices=["auto", "staged", "composed"],
+    ap.add_argument("--fused", default="auto", choices=["auto", "staged", "composed", "wide"],
                     help="kernel behind the two-steps-per-pass launches of the radius-1 stars: k_star2 (staged), the composed "
-                         "25-point diamond, or whichever is exact and faster on this box (auto)")
+                         "25-point diamond on 4x4- (composed) or 8x4-brick tiles (wide), or whichever is exact and fastest on "
+                         "this box (auto)")
     ap.add_argument("--no-extras", action="store_true", help="skip other stencils / strong / e2e / cpu baseline / parity")
     ap.add_argument("--kernel", default="auto", choices=["auto", "brick", "tiled"])
     ap.add_argument("--transport", default="kernel", choices=["kernel", "ce"],
@@ -745,8 +757,8 @@ def main():
 
     d = make_domain()
     fused_info = select_fused_kernel(bk, d, dist, rank, args.fused)
-    if fused_info["selected"] == "composed":
-        os.environ["BK_FUSED_VARIANT"] = "composed"     # the C++ driver legs inherit the choice
+    if fused_info["selected"] != "staged":
+        os.environ["BK_FUSED_VARIANT"] = fused_info["selected"]     # the C++ driver legs inherit the choice
 
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     if rank == 0:
@@ -759,7 +771,7 @@ def main():
     peak, peak_src = measured_peak()
     sweep_s, sweep_steps = time_sweeps(bk, d, 20)
     traffic = None
-    composed = sweep_steps == 2 and fused_info["selected"] == "composed"
+    composed = sweep_steps == 2 and fused_info["selected"] != "staged"
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
             args.stencil + ("_composed2" if composed else "_fused2" if sweep_steps == 2 else ""))
@@ -783,8 +795,8 @@ def main():
     line["roofline"]["traffic_source"] = ("ncu --set full capture of this kernel at this size (profiles/traffic.json), per launch"
                                           if traffic is not None else "no ncu capture of this kernel yet")
     if composed:
-        line["roofline"]["kernel"] = ("k_star_capped<diamond> (two time steps as ONE composed 25-point update): one launch = "
-                                      f"{pts} interior points x 2 step(s) x 16 B")
+        line["roofline"]["kernel"] = (f"march_body<diamond, {fused_info['selected']}> (two time steps as ONE composed 25-point update): "
+                                      f"one launch = {pts} interior points x 2 step(s) x 16 B")
     line["fused_kernel"] = fused_info
 
     wd = Watchdog(rank, float(os.environ.get("BENCH_EXTRAS_DEADLINE_S", "420")))

@@ -4,7 +4,7 @@ The product is libbrick_b200.so (CUDA kernels for sm_100a behind the C ABI in in
 the thin host-side mirror of the reference interface used by tests/, bench.py and the weak-scaling loop; the C++
 template surface lives in include/*.h and the drivers in drivers/.
 """
-from ._lib import (BK_OK, FUSED_COMPOSED, FUSED_STAGED, KERNEL_AUTO, KERNEL_BRICK, KERNEL_TILED, PART_ALL, PART_READY, PART_REST, PART_THIN, STENCILS,  # noqa: F401
+from ._lib import (BK_OK, FUSED_COMPOSED, FUSED_COMPOSED_WIDE, FUSED_STAGED, KERNEL_AUTO, KERNEL_BRICK, KERNEL_TILED, PART_ALL, PART_READY, PART_REST, PART_THIN, STENCILS,  # noqa: F401
                    BrickError, load)
 from .core import (BRICK, Brick, BrickDecomp, BrickInfo, BrickStorage, DeviceBuffer, DeviceGrid, Event,  # noqa: F401
                    ExchangeView, ArrayExchangeView, array_stencil, bitset_of, StitchedGrid, compareBrick, copyFromBrick, copyToBrick, device_sync, init_grid, stencil,
@@ -19,8 +19,8 @@ def have_gpu():
 
 
 def fused_variant(variant=None):
-    """the kernel behind stencil_advance(steps=2) for radius-1 stars: FUSED_STAGED (k_star2) or FUSED_COMPOSED (the
-    composed 25-point diamond); sets it when given, returns the previous / current value"""
+    """the kernel behind stencil_advance(steps=2) for radius-1 stars: FUSED_STAGED (k_star2), FUSED_COMPOSED or
+    FUSED_COMPOSED_WIDE (the composed 25-point diamond on 4x4- / 8x4-brick tiles); sets it when given, returns the previous / current value"""
     L = load()
     if variant is None:
         return L.bk_stencil_fused_variant_get()

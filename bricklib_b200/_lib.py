@@ -12,7 +12,7 @@ ST_7PT, ST_MPI7PT, ST_MPI13PT, ST_MPI25PT, ST_MPI125PT = range(5)
 STENCILS = {"7pt": 0, "mpi7pt": 1, "mpi13pt": 2, "mpi25pt": 3, "mpi125pt": 4}
 KERNEL_AUTO, KERNEL_BRICK, KERNEL_TILED = 0, 1, 2
 PART_ALL, PART_READY, PART_REST, PART_THIN, PART_GRID_TOPOLOGY = 0, 1, 2, 4, 8
-FUSED_STAGED, FUSED_COMPOSED = 0, 1   # bk_stencil_fused_variant_set: k_star2 / the composed 25-point diamond
+FUSED_STAGED, FUSED_COMPOSED, FUSED_COMPOSED_WIDE = 0, 1, 2   # bk_stencil_fused_variant_set: k_star2 / the composed diamond (4x4 | 8x4 tiles)
 IPC_HANDLE_BYTES = 64
 
 vp, sz, u64 = C.c_void_p, C.c_size_t, C.c_uint64

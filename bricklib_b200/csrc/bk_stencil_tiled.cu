@@ -1084,7 +1084,9 @@ int fused_variant() {
   int v = g_fused_variant.load(std::memory_order_relaxed);
   if (v < 0) {
     const char *e = getenv("BK_FUSED_VARIANT");
-    v = (e && (e[0] == 'c' || e[0] == 'C' || e[0] == '1')) ? BK_FUSED_COMPOSED : BK_FUSED_STAGED;
+    v = BK_FUSED_STAGED;  // "staged" | "composed" | "wide" (or 0 | 1 | 2)
+    if (e && (e[0] == 'c' || e[0] == 'C' || e[0] == '1')) v = BK_FUSED_COMPOSED;
+    if (e && (e[0] == 'w' || e[0] == 'W' || e[0] == '2')) v = BK_FUSED_COMPOSED_WIDE;
     int expect = -1;
     if (!g_fused_variant.compare_exchange_strong(expect, v)) v = expect;
   }
@@ -1095,7 +1097,8 @@ int fused_variant() {
 
 extern "C" {
 int bk_stencil_fused_variant_set(int variant) {
-  BK_REQUIRE(variant == BK_FUSED_STAGED || variant == BK_FUSED_COMPOSED, "BK_FUSED_STAGED or BK_FUSED_COMPOSED");
+  BK_REQUIRE(variant == BK_FUSED_STAGED || variant == BK_FUSED_COMPOSED || variant == BK_FUSED_COMPOSED_WIDE,
+             "BK_FUSED_STAGED, BK_FUSED_COMPOSED or BK_FUSED_COMPOSED_WIDE");
   const int before = fused_variant();
   g_fused_variant.store(variant, std::memory_order_relaxed);
   return before;
@@ -1135,10 +1138,14 @@ int launch_tiled(const CoefSpec &spec, const bk_field_t &f, const bk_field_t *mu
   const StarCoef &sc = spec.sc;
   const int r = spec.radius;
   if (steps == 2) {  // two time steps per pass: (R, YT, TI, TJ, D, producer warps)
-    if (r == 1 && fused_variant() == BK_FUSED_COMPOSED) {
-      // the composed operator on the radius-2 star geometry: 4x4-brick tiles, 4 consumer + 2 producer warps, 2 CTAs per SM
+    if (r == 1 && fused_variant() != BK_FUSED_STAGED) {
+      // the composed operator on the radius-2 star geometry.  BK_FUSED_COMPOSED: 4x4-brick tiles, 4 consumer + 2 producer
+      // warps, 2 CTAs per SM (the 13-point kernel's shape); BK_FUSED_COMPOSED_WIDE: 8x4-brick tiles, 8 consumer + 4
+      // producer warps with register re-balancing, 1 CTA per SM (the 25-point kernel's shape: fewer halo bricks per point)
       const bk::DiamondCoef dc = bk::diamond_coef(sc.c0, sc.cp[0][0], sc.cm[0][0], sc.cp[1][0], sc.cm[1][0], sc.cp[2][0], sc.cm[2][0]);
       if (v == 1) return launch_cfg<Cfg<2, 2, 4, 4, 2, 3, 128, 2, false, 0, 40, 2>>(a, dc, s, nsub, part, rdy_lo, rdy_hi);
+      if (fused_variant() == BK_FUSED_COMPOSED_WIDE)
+        return launch_cfg<Cfg<2, 4, 8, 4, 2, 3, 255, 4, false, 232, 40, 2>>(a, dc, s, nsub, part, rdy_lo, rdy_hi);
       return launch_cfg<Cfg<2, 4, 4, 4, 2, 3, 168, 2, false, 0, 40, 2>>(a, dc, s, nsub, part, rdy_lo, rdy_hi);
     }
     if (r == 1) {

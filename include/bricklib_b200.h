@@ -49,11 +49,14 @@ int bk_stencil_fused_steps(int stencil); /* `steps` of bk_stencil_advance that i
 /* Which kernel runs bk_stencil_advance(steps = 2) for the radius-1 stars (7pt, mpi7pt and compiled radius-1 stars):
  *   BK_FUSED_STAGED   (default) k_star2: two stencil stages per plane, the intermediate plane in shared memory;
  *   BK_FUSED_COMPOSED the composed operator S(S u), a 25-point diamond, as ONE radius-2 marching update
- *                     (bricklib_b200/csrc/bk_diamond.h) -- same semantics incl. the zero intermediate outside the grid.
- * Process-wide; the environment variable BK_FUSED_VARIANT=staged|composed sets the initial value.  _set returns the
+ *                     (bricklib_b200/csrc/bk_diamond.h) -- same semantics incl. the zero intermediate outside the grid;
+ *                     4x4-brick tiles, two CTAs per SM;
+ *   BK_FUSED_COMPOSED_WIDE the same update on 8x4-brick tiles, one CTA per SM with register re-balancing.
+ * Process-wide; the environment variable BK_FUSED_VARIANT=staged|composed|wide sets the initial value.  _set returns the
  * previous value, or BK_EINVAL. */
 #define BK_FUSED_STAGED 0
 #define BK_FUSED_COMPOSED 1
+#define BK_FUSED_COMPOSED_WIDE 2
 int bk_stencil_fused_variant_set(int variant);
 int bk_stencil_fused_variant_get(void);
 

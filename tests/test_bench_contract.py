@@ -112,7 +112,7 @@ class _FakeDomain:
 
 
 class _FakeBk:
-    FUSED_STAGED, FUSED_COMPOSED, STENCILS = 0, 1, {"7pt": 0, "mpi7pt": 1}
+    STENCILS = {"7pt": 0, "mpi7pt": 1}
 
     def __init__(self):
         self.variant = 0
@@ -128,35 +128,42 @@ class _FakeBk:
 
 
 def test_fused_kernel_selection_policy(monkeypatch):
-    """bench.select_fused_kernel: the composed kernel is used only when its child trial passed, it is exact on the device
-    and it is faster; whatever goes wrong leaves the proven staged kernel in place (no GPU needed: everything mocked)"""
+    """bench.select_fused_kernel: a composed kernel is used only when its child trial passed, it is exact on the device and
+    it is the fastest candidate; whatever goes wrong leaves the proven staged kernel in place (no GPU needed: mocked)"""
     import bench
 
     class R:
         def __init__(self, rc, out):
             self.returncode, self.stdout, self.stderr = rc, out, ""
 
-    def scenario(child, t_staged, t_comp, parity=(0, 1e-16, 10), want="auto", steps=2):
+    def scenario(child, times, parity=None, want="auto", steps=2):
+        """times / parity: by variant number 0 staged, 1 composed, 2 wide"""
         fake, dom = _FakeBk(), _FakeDomain(steps)
+        parity = parity or {}
         monkeypatch.setattr(bench.subprocess, "run", lambda *a, **k: child() if callable(child) else child)
-        monkeypatch.setattr(bench, "time_sweeps", lambda bk, d, reps: ((t_comp if bk.variant else t_staged), 2))
-        monkeypatch.setattr(bench, "fused_vs_two_sweeps", lambda bk, d: parity)
+        monkeypatch.setattr(bench, "time_sweeps", lambda bk, d, reps: (times[bk.variant], 2))
+        monkeypatch.setattr(bench, "fused_vs_two_sweeps", lambda bk, d: parity.get(bk.variant, (0, 1e-16, 10)))
         info = bench.select_fused_kernel(fake, dom, None, 0, want)
-        assert (fake.variant == 1) == (info["selected"] == "composed")
+        assert fake.variant == bench.FUSED_NAMES[info["selected"]]
         return info
 
-    ok = R(0, 'noise\n{"ok": true, "composed": {"launch_ms": 0.39}}\n')
-    assert scenario(ok, 0.46e-3, 0.39e-3)["selected"] == "composed"
-    assert scenario(ok, 0.46e-3, 0.50e-3)["why"] == "exact but not faster"
-    assert scenario(ok, 0.46e-3, 0.39e-3, parity=(3, 0.2, 10))["why"] == "not exact"
-    assert scenario(ok, 0.46e-3, 0.39e-3, parity=(0, 1e-9, 10))["selected"] == "staged"
-    assert scenario(R(-11, ""), 0.46e-3, 0.39e-3)["selected"] == "staged"                      # the child crashed
-    assert scenario(R(0, '{"ok": false}'), 0.46e-3, 0.39e-3)["selected"] == "staged"           # the child found a mismatch
+    both = R(0, 'noise\n{"ok": true, "composed": {"ok": true}, "wide": {"ok": true}}\n')
+    only_wide = R(0, '{"ok": true, "composed": {"ok": false}, "wide": {"ok": true}}')
+    T = {0: 0.46e-3, 1: 0.39e-3, 2: 0.41e-3}
+    assert scenario(both, T)["selected"] == "composed"
+    assert scenario(both, {0: 0.46e-3, 1: 0.42e-3, 2: 0.40e-3})["selected"] == "wide"
+    assert scenario(both, {0: 0.46e-3, 1: 0.50e-3, 2: 0.47e-3})["selected"] == "staged"
+    assert scenario(both, T, parity={1: (3, 0.2, 10)})["selected"] == "wide"            # composed wrong, wide exact and faster
+    assert scenario(both, T, parity={1: (0, 1e-9, 10), 2: (1, 1.0, 10)})["selected"] == "staged"
+    assert scenario(only_wide, T)["selected"] == "wide"
+    assert "composed" not in scenario(only_wide, T)["launch_ms"]                        # never run in this process
+    assert scenario(R(-11, ""), T)["selected"] == "staged"                              # the child crashed
+    assert scenario(R(0, '{"ok": false}'), T)["selected"] == "staged"                   # the child found mismatches
 
     def hang():
-        raise bench.subprocess.TimeoutExpired("trial", 150)
-    assert scenario(hang, 0.46e-3, 0.39e-3)["selected"] == "staged"                            # the child hung
-    assert scenario(ok, 0.46e-3, 0.39e-3, want="staged")["why"] == "forced"
-    assert scenario(ok, 0.46e-3, 0.50e-3, want="composed")["selected"] == "composed"           # forced, still has to be exact
-    assert scenario(ok, 0.46e-3, 0.39e-3, parity=(1, 1.0, 10), want="composed")["selected"] == "staged"
-    assert scenario(ok, 0.46e-3, 0.39e-3, steps=1)["selected"] == "staged"                     # nothing to select
+        raise bench.subprocess.TimeoutExpired("trial", 180)
+    assert scenario(hang, T)["selected"] == "staged"                                    # the child hung
+    assert scenario(both, T, want="staged")["why"] == "forced"
+    assert scenario(both, {0: 0.46e-3, 1: 0.50e-3, 2: 0.40e-3}, want="composed")["selected"] == "composed"   # forced, exact
+    assert scenario(both, T, parity={2: (1, 1.0, 10)}, want="wide")["selected"] == "staged"                   # forced, wrong
+    assert scenario(both, T, steps=1)["selected"] == "staged"                           # nothing to select

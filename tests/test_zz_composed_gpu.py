@@ -37,14 +37,17 @@ def first_contact():
 
 def test_first_contact_in_a_child_process(first_contact):
     assert first_contact["ok"], first_contact
+    assert first_contact["composed"]["ok"] and first_contact["wide"]["ok"], first_contact
 
 
-@pytest.fixture
-def composed(first_contact):
-    if not first_contact["ok"]:
-        pytest.skip("the composed kernel failed its first contact (see test_first_contact_in_a_child_process)")
-    before = bk.fused_variant(bk.FUSED_COMPOSED)
-    yield
+@pytest.fixture(params=["composed", "wide"])
+def composed(first_contact, request):
+    """both shapes of the composed kernel (4x4-brick tiles / 8x4-brick tiles), each only if its child trial came back clean"""
+    if not first_contact.get(request.param, {}).get("ok"):
+        pytest.skip(f"the {request.param} kernel failed its first contact (see test_first_contact_in_a_child_process)")
+    variant = {"composed": bk.FUSED_COMPOSED, "wide": bk.FUSED_COMPOSED_WIDE}[request.param]
+    before = bk.fused_variant(variant)
+    yield variant
     bk.fused_variant(before)
 
 
@@ -107,7 +110,7 @@ def test_composed_and_staged_kernels_agree(composed):
     bk.stencil_advance(1, 2, grid, b_in, b_a)
     bk.fused_variant(bk.FUSED_STAGED)
     bk.stencil_advance(1, 2, grid, b_in, b_b)
-    bk.fused_variant(bk.FUSED_COMPOSED)
+    bk.fused_variant(composed)
     bk.device_sync()
     assert rel(s_a.to_host(), s_b.to_host()) < 1e-14
 
@@ -144,7 +147,7 @@ def test_full_size_composed_pass_equals_two_sweeps_on_a_random_field(composed):
     assert got < 1e-12 and n > 0
 
 
-def _driver_composed(*args):
+def _driver_composed(variant, *args):
     """a C++ driver in a process of its own with BK_FUSED_VARIANT=composed: self-validating against a CPU sweep of the
     global periodic array, like the reference's drivers"""
     import os
@@ -153,24 +156,26 @@ def _driver_composed(*args):
     exe = os.path.join(root, "drivers", args[0])
     if not os.path.exists(exe):
         pytest.fail(f"{exe} is not built: run __graft_entry__.build()")
-    r = subprocess.run([exe, *args[1:]], capture_output=True, text=True, timeout=300, env=dict(os.environ, BK_FUSED_VARIANT="composed"))
+    r = subprocess.run([exe, *args[1:]], capture_output=True, text=True, timeout=300, env=dict(os.environ, BK_FUSED_VARIANT=variant))
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     return r.stdout
 
 
+@pytest.mark.parametrize("variant", ["composed", "wide"])
 @pytest.mark.parametrize("ranks,dom", [(1, "32,32,32"), (4, "32,24,40")])
-def test_cpp_weak_driver_through_the_composed_kernel(first_contact, ranks, dom):
-    if not first_contact["ok"]:
-        pytest.skip("the composed kernel failed its first contact")
-    out = _driver_composed("weak", "-s", dom, "-I", "2", "-g", str(ranks), "-S", "mpi7pt", "-v")
+def test_cpp_weak_driver_through_the_composed_kernel(first_contact, ranks, dom, variant):
+    if not first_contact.get(variant, {}).get("ok"):
+        pytest.skip(f"the {variant} kernel failed its first contact")
+    out = _driver_composed(variant, "weak", "-s", dom, "-I", "2", "-g", str(ranks), "-S", "mpi7pt", "-v")
     assert "result match (worst relative difference" in out and "Arr == Bri: result match" in out
 
 
+@pytest.mark.parametrize("variant", ["composed", "wide"])
 @pytest.mark.parametrize("ranks,d,s", [(1, 64, 32), (8, 128, 32), (2, 128, 64)])
-def test_cpp_strong_driver_stitched_grid_through_the_composed_kernel(first_contact, ranks, d, s):
+def test_cpp_strong_driver_stitched_grid_through_the_composed_kernel(first_contact, ranks, d, s, variant):
     """the stitched super grid aliases shell positions onto other subdomains' bricks: the composed kernel resolves every
     neighbour through grid POSITIONS exactly like the staged one, so the periodic result must come out the same"""
-    if not first_contact["ok"]:
-        pytest.skip("the composed kernel failed its first contact")
-    out = _driver_composed("strong", "-d", str(d), "-s", str(s), "-I", "2", "-g", str(ranks), "-S", "mpi7pt", "-v")
+    if not first_contact.get(variant, {}).get("ok"):
+        pytest.skip(f"the {variant} kernel failed its first contact")
+    out = _driver_composed(variant, "strong", "-d", str(d), "-s", str(s), "-I", "2", "-g", str(ranks), "-S", "mpi7pt", "-v")
     assert "result match (worst relative difference" in out and f"stitched ranks {ranks} of {ranks}" in out
