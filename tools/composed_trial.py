@@ -31,7 +31,8 @@ def small_boxes(bk):
     worst = 0.0
 
     def rel(a, b):
-        return float((np.abs(a - b) / (np.abs(a) + np.abs(b) + 1e-300)).max())
+        r = float((np.abs(a - b) / (np.abs(a) + np.abs(b) + 1e-300)).max())
+        return r if r == r else float("inf")     # NaN anywhere is a failure, not "no difference"
 
     for lo, hi in [((0, 0, 0), t), own, ((1, 0, 1), (t[0], t[1] - 1, t[2]))]:
         bk.stencil(1, grid, b_in, b_tmp, kernel=bk.KERNEL_TILED)
