@@ -381,7 +381,8 @@ def e2e_periods(bk, doms, steps):
     host memory (H2D), runs one period (exchange + ST_ITER sweeps) and downloads the result bricks (D2H) -- all inside
     the timed region.  Steps are independent fields, so three are kept in flight (one uploading, one computing, one
     downloading), as a user streaming fields through the GPU would do.  Each slot has its own upload, compute and
-    download stream, so both PCIe directions are busy all the time: the step time is bounded by one direction's copy.  Returns (seconds per step, h2d bytes, d2h bytes)."""
+    download stream, so both PCIe directions are busy all the time: the step time is bounded by one direction's copy; the
+    periods themselves run one after the other.  Returns (seconds per step, h2d bytes, d2h bytes)."""
     import ctypes as C
     L = bk.load()
     ck = bk._lib.check
@@ -401,14 +402,23 @@ def e2e_periods(bk, doms, steps):
         slots.append((d, hin, hout, st, ev))
     bk.device_sync()
 
+    last_run = [None]
+
     def step(i):
         d, hin, hout, (s_up, s_run, s_down), (e_up, e_run, e_down) = slots[i % len(slots)]
         ck(L.bk_stream_wait_event(s_up, e_down.h))         # this slot's previous result has left the device
         ck(L.bk_memcpy_h2d(d.storage[0].dat.ptr + off, hin, nbytes, s_up))
         e_up.record(s_up)
         ck(L.bk_stream_wait_event(s_run, e_up.h))
+        # ONE period in flight per GPU: a period (2 ms next to 25 ms of copies) starts when the previous step's period has
+        # finished, so every rank runs the periods of all slots in one global order -- the ordering the single-domain loop
+        # is proven with.  Periods of different slots in flight at once would put kernels that wait for a peer's flag on
+        # several streams, and two ranks could then wait for each other (cross-slot, through shared hardware queues).
+        if last_run[0] is not None:
+            ck(L.bk_stream_wait_event(s_run, last_run[0].h))
         d.period(s_run)
         e_run.record(s_run)
+        last_run[0] = e_run
         ck(L.bk_stream_wait_event(s_down, e_run.h))
         ck(L.bk_memcpy_d2h(hout, d.storage[0].dat.ptr + off, nbytes, s_down))
         e_down.record(s_down)
@@ -553,30 +563,12 @@ def driver_env():
     return env
 
 
-def wait_for_quiet_gpus(n, timeout=20.0):
-    """block until no OTHER process holds a compute context on GPUs 0..n-1 (the torchrun workers that have finished)"""
-    try:
-        import pynvml as nv
-        nv.nvmlInit()
-        me = os.getpid()
-        t0 = time.time()
-        while time.time() - t0 < timeout:
-            busy = [p.pid for i in range(n) for p in nv.nvmlDeviceGetComputeRunningProcesses(nv.nvmlDeviceGetHandleByIndex(i))
-                    if p.pid != me]
-            if not busy:
-                return True
-            time.sleep(0.25)
-    except Exception:
-        time.sleep(3.0)
-    return False
-
-
 def leg_timeout(wd, cap):
-    """seconds a driver leg may take: `cap`, but never more than what is left of the extras' deadline (minus a margin to
-    print the line); 0 = skip the leg"""
+    """seconds a driver leg may take: `cap`, but never more than what is left of the extras' deadline minus a reserve for the
+    legs that follow; 0 = skip the leg"""
     if wd is None:
         return cap
-    left = wd.left() - 15.0
+    left = wd.left() - 75.0      # reserve: the end-to-end leg, the CPU baseline and printing the line
     return 0 if left < 20.0 else min(cap, left)
 
 
@@ -829,6 +821,33 @@ def main():
                             "parity": parity_of(bk, d, dist)}
             wd.at("others." + name + " done", line)
         d.stencil, d.st_iter = st, it
+
+        # strong scaling (configs[4]), the array-layout baseline (8f#4) and the single driver (configs[0]) run through the
+        # C++ drivers, one host thread per GPU, on ALL n GPUs: rank 0 runs them while the other ranks sit in a HOST
+        # barrier (gloo: no kernel on any GPU; their contexts are idle).  They come before the end-to-end leg, which is
+        # the one extra that keeps several domains with device-side handshakes in flight: whatever happens there, these
+        # numbers are already in the snapshot.  Each leg gets what is left of the extras' deadline minus a reserve for the
+        # legs that follow (and is skipped when that is too little).
+        if rank == 0:
+            wd.at("strong", line)
+            others["strong"] = strong_leg(n, wd)
+            wd.at("array baseline", line)
+            others["array_layout_baseline"] = array_baseline_leg(n, wd)
+            if n == 1:
+                wd.at("single", line)
+                others["single_7pt_512"] = single_leg(wd)
+            line["baseline_configs"] = {
+                "configs[0] single 7pt 512^3 (N=1 only)": others.get("single_7pt_512", {}).get("GStencil/s"),
+                "configs[1] 125pt 512^3 per GPU": others.get("mpi125pt", {}).get("GStencil/s"),
+                "configs[2] weak 7pt / 13pt 512^3 per GPU": [value, others.get("mpi13pt", {}).get("GStencil/s")],
+                "configs[3] weak 25pt 512^3 per GPU": others.get("mpi25pt", {}).get("GStencil/s"),
+                "configs[4] strong 1024^3 in 64^3 subdomains": others["strong"].get("global_1024_sub_64", {}).get("GStencil/s"),
+                "unit": f"GStencil/s, whole job on {n} GPU(s)",
+            }
+        wd.at("host barrier after the driver legs", line)
+        if dist is not None:
+            dist.barrier(group=host_group)
+
         wd.at("e2e", line)
         e2e_s, bi, bo = e2e_periods(bk, [d, make_domain(), make_domain()], 9)
         e2e_s = max_over_ranks(dist, e2e_s)
@@ -851,38 +870,12 @@ def main():
             wd.at("cpu_baseline done", line)
 
     if dist is not None:
-        wd.at("leaving the process group")
+        wd.at("leaving the process group", line)
         barrier(dist)
         dist.destroy_process_group()
     if rank != 0:
         wd.finish()
         return
-    if not args.no_extras:
-        # strong scaling (configs[4]), the array-layout baseline (8f#4) and the single driver (configs[0]) run through the
-        # C++ drivers, one host thread per GPU, on ALL n GPUs.  They come last: the other ranks have left and this rank's
-        # own device memory is released first, so the drivers have the GPUs to themselves.  Each leg gets what is left of
-        # the extras' deadline (and is skipped when that is too little): a stuck driver cannot take the line with it.
-        others = line["others"]
-        d = None
-        import gc
-        gc.collect()
-        wd.at("waiting for the other ranks to leave the GPUs", line)
-        wait_for_quiet_gpus(n)
-        wd.at("strong", line)
-        others["strong"] = strong_leg(n, wd)
-        wd.at("array baseline", line)
-        others["array_layout_baseline"] = array_baseline_leg(n, wd)
-        if n == 1:
-            wd.at("single", line)
-            others["single_7pt_512"] = single_leg(wd)
-        line["baseline_configs"] = {
-            "configs[0] single 7pt 512^3 (N=1 only)": others.get("single_7pt_512", {}).get("GStencil/s"),
-            "configs[1] 125pt 512^3 per GPU": others.get("mpi125pt", {}).get("GStencil/s"),
-            "configs[2] weak 7pt / 13pt 512^3 per GPU": [value, others.get("mpi13pt", {}).get("GStencil/s")],
-            "configs[3] weak 25pt 512^3 per GPU": others.get("mpi25pt", {}).get("GStencil/s"),
-            "configs[4] strong 1024^3 in 64^3 subdomains": others["strong"].get("global_1024_sub_64", {}).get("GStencil/s"),
-            "unit": f"GStencil/s, whole job on {n} GPU(s)",
-        }
     wd.finish()
     print(json.dumps(line))
 
