@@ -572,6 +572,32 @@ def leg_timeout(wd, cap):
     return 0 if left < 20.0 else min(cap, left)
 
 
+def drivers_accept_fused_variant(n):
+    """The C++ driver legs inherit the fused kernel this run selected (BK_FUSED_VARIANT).  Before any of them is timed that
+    way, both drivers run a small SELF-VALIDATING case with it (-v: against a CPU sweep of the global periodic array; the
+    strong one on the stitched super grid, whose shell aliases other subdomains' bricks).  On any failure the legs fall back
+    to the staged kernel.  Returns the record for the JSON line."""
+    variant = os.environ.get("BK_FUSED_VARIANT")
+    if not variant:
+        return None
+    out = {"variant": variant, "ok": True}
+    cases = {"strong": ["-d", "128", "-s", "32", "-I", "2", "-g", str(n), "-S", "mpi7pt", "-v"],
+             "weak": ["-s", "32,32,32", "-I", "2", "-g", str(n), "-S", "mpi7pt", "-v"]}
+    for name, args in cases.items():
+        try:
+            r = subprocess.run([os.path.join(ROOT, "drivers", name), *args], capture_output=True, text=True, timeout=120,
+                               env=driver_env())
+            good = r.returncode == 0 and "result match (worst relative difference" in r.stdout
+            out[name] = "result match" if good else (r.stdout + r.stderr)[-300:]
+        except Exception as exc:
+            good, out[name] = False, str(exc)[:300]
+        out["ok"] = out["ok"] and good
+    if not out["ok"]:
+        os.environ.pop("BK_FUSED_VARIANT", None)
+        out["fallback"] = "driver legs run with the staged kernel"
+    return out
+
+
 def strong_leg(n, wd=None):
     """BASELINE.json configs[4]: 1024^3 global, 64^3 subdomains, Z-Morton sections over n GPUs -- the C++ strong driver
     on ALL n GPUs (one host thread per GPU), stitched super grid; at n = 1 also one GPU's 1/8 share (512^3) both
@@ -829,6 +855,10 @@ def main():
         # numbers are already in the snapshot.  Each leg gets what is left of the extras' deadline minus a reserve for the
         # legs that follow (and is skipped when that is too little).
         if rank == 0:
+            wd.at("drivers: validation with the selected fused kernel", line)
+            accepted = drivers_accept_fused_variant(n)
+            if accepted is not None:
+                line["fused_kernel"]["drivers"] = accepted
             wd.at("strong", line)
             others["strong"] = strong_leg(n, wd)
             wd.at("array baseline", line)

@@ -167,3 +167,21 @@ def test_fused_kernel_selection_policy(monkeypatch):
     assert scenario(both, {0: 0.46e-3, 1: 0.50e-3, 2: 0.40e-3}, want="composed")["selected"] == "composed"   # forced, exact
     assert scenario(both, T, parity={2: (1, 1.0, 10)}, want="wide")["selected"] == "staged"                   # forced, wrong
     assert scenario(both, T, steps=1)["selected"] == "staged"                           # nothing to select
+
+
+def test_driver_legs_fall_back_to_the_staged_kernel_when_validation_fails(monkeypatch):
+    import bench
+
+    class R:
+        def __init__(self, rc, out):
+            self.returncode, self.stdout, self.stderr = rc, out, ""
+
+    monkeypatch.delenv("BK_FUSED_VARIANT", raising=False)
+    assert bench.drivers_accept_fused_variant(2) is None
+    monkeypatch.setenv("BK_FUSED_VARIANT", "composed")
+    monkeypatch.setattr(bench.subprocess, "run", lambda *a, **k: R(0, "perf 1\nresult match (worst relative difference 4e-16 after 24 steps)\n"))
+    ok = bench.drivers_accept_fused_variant(2)
+    assert ok["ok"] and ok["strong"] == ok["weak"] == "result match" and os.environ["BK_FUSED_VARIANT"] == "composed"
+    monkeypatch.setattr(bench.subprocess, "run", lambda *a, **k: R(2, "result mismatch! (12 cells)\n"))
+    bad = bench.drivers_accept_fused_variant(2)
+    assert not bad["ok"] and "fallback" in bad and "BK_FUSED_VARIANT" not in os.environ
