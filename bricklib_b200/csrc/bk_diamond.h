@@ -75,10 +75,15 @@ BK_HD double2 diamond_ld2(const unsigned char *p) { return *reinterpret_cast<con
 //   pb       base of the plane in the shared-memory stage
 //   own_off  my x-pair in my first row;  jo0..jo3: my x-pair in rows y0-2, y0-1, y0+YT, y0+YT+1
 //   iL, iR   from an x-pair to the 16-byte chunks left / right of it (cells x0-2,x0-1 / x0+2,x0+3) in the same row
+//   swp      odd row group of the half warp (see below)
 //   acc      five partial outputs per point; slot (u + 3) % 5 is COMPLETE on return (output t-2), the caller stores it
 //   v        my own cells of this plane
+// Rows y0-1 and y0+YT only feed the diagonal taps: one cell left (x0-1) and one cell right (x0+2) of my x-pair.  Those are
+// 64-bit loads at a 16-byte lane stride -- all "x0-1" cells sit in the odd 8-byte bank positions, all "x0+2" cells in the
+// even ones -- so the odd row groups of a half warp load the RIGHT cell first and the left one second: each instruction
+// then covers all 32 banks (2 wavefronts instead of 4; tests/cpp/diamond_emulation.cpp has the bank model).
 template <int YT>
-BK_HD void diamond_plane(const unsigned char *pb, int own_off, int jo0, int jo1, int jo2, int jo3, int iL, int iR,
+BK_HD void diamond_plane(const unsigned char *pb, int own_off, int jo0, int jo1, int jo2, int jo3, int iL, int iR, const bool swp,
                          const DiamondCoef &cf, double2 (&acc)[5][YT], const int u, const unsigned edge,
                          const double2 (&v)[YT]) {
   const int sF = (u + 3) % 5, sM = (u + 4) % 5, s0 = u % 5, sP = (u + 1) % 5, sN = (u + 2) % 5;
@@ -92,10 +97,18 @@ BK_HD void diamond_plane(const unsigned char *pb, int own_off, int jo0, int jo1,
 #pragma unroll
   for (int r = 0; r < YT; ++r) rows[2 + r] = v[r];
   rows[YT + 2] = diamond_ld2(pb + jo2), rows[YT + 3] = diamond_ld2(pb + jo3);
-  double2 lf[YT + 2], rg[YT + 2];  // the chunks left / right of my x-pair in rows y0-1 .. y0+YT
+  // cells x0-2, x0-1 (lf) and x0+2, x0+3 (rg) of rows y0-1 .. y0+YT; of the first and the last row only lf.y and rg.x
+  double2 lf[YT + 2], rg[YT + 2];
+  {
+    const int first = swp ? iR : iL + 8, second = swp ? iL + 8 : iR;
+    const double a0 = *reinterpret_cast<const double *>(pb + jo1 + first), b0 = *reinterpret_cast<const double *>(pb + jo1 + second);
+    const double a1 = *reinterpret_cast<const double *>(pb + jo2 + first), b1 = *reinterpret_cast<const double *>(pb + jo2 + second);
+    lf[0] = make_double2(0.0, swp ? b0 : a0), rg[0] = make_double2(swp ? a0 : b0, 0.0);
+    lf[YT + 1] = make_double2(0.0, swp ? b1 : a1), rg[YT + 1] = make_double2(swp ? a1 : b1, 0.0);
+  }
 #pragma unroll
-  for (int q = 0; q < YT + 2; ++q) {
-    const unsigned char *pr = (q == 0) ? pb + jo1 : (q == YT + 1) ? pb + jo2 : pb + own_off + (q - 1) * 64;
+  for (int q = 1; q <= YT; ++q) {
+    const unsigned char *pr = pb + own_off + (q - 1) * 64;
     lf[q] = diamond_ld2(pr + iL);
     rg[q] = diamond_ld2(pr + iR);
   }

@@ -352,8 +352,8 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
           for (int r = 0; r < YT; ++r) v[r] = *reinterpret_cast<const double2 *>(pb + own_off + r * 64);
           const int zt = kb0 * 8 - RUP + tb + u;
           const unsigned edge = edge_ij | ((zt == 0 || zt == a.gz * 8 - 1) ? bk::kDiamondEdgeK : 0u);
-          bk::diamond_plane<YT>(pb, own_off, joff[0], joff[1], joff[2 * R - 2], joff[2 * R - 1], ioffL[0], ioffR[0], cf, acc, u,
-                                edge, v);
+          bk::diamond_plane<YT>(pb, own_off, joff[0], joff[1], joff[2 * R - 2], joff[2 * R - 1], ioffL[0], ioffR[0],
+                                ((tid >> 3) & 1) != 0, cf, acc, u, edge, v);
           store_plane(acc[sF]);
         } else {
           double2 v[YT];

@@ -156,7 +156,8 @@ void run_cta(const Grid &g, const std::vector<double> &in, std::vector<double> &
         for (int r = 0; r < C::YT; ++r) v[r] = bk::diamond_ld2(pb + own_off + r * 64);
         const int zt = kb0 * 8 - C::RUP + tb + u;
         const unsigned edge = edge_ij | ((zt == 0 || zt == g.gz * 8 - 1) ? bk::kDiamondEdgeK : 0u);
-        bk::diamond_plane<C::YT>(pb, own_off, joff[0], joff[1], joff[2 * R - 2], joff[2 * R - 1], ioffL, ioffR, cf, acc, u, edge, v);
+        bk::diamond_plane<C::YT>(pb, own_off, joff[0], joff[1], joff[2 * R - 2], joff[2 * R - 1], ioffL, ioffR, ((tid >> 3) & 1) != 0, cf,
+                                 acc, u, edge, v);
         if (orel >= 0 && orel < nout) {  // store_plane
           const int oz = orel & 7;
           if (oz == 0) {
@@ -172,6 +173,95 @@ void run_cta(const Grid &g, const std::vector<double> &in, std::vector<double> &
         ++orel;
       }
   }
+}
+
+// ---- shared-memory bank model of the consumer loads --------------------------------------------------------------
+// 32 banks x 4 B.  A 128-bit load is served a quarter warp at a time (8 lanes x 16 B = 128 B: one wavefront if the eight
+// chunks fall into eight different 16-byte bank groups), a 64-bit load half a warp at a time (16 lanes x 8 B).  Lanes that
+// read the SAME address share a wavefront.  Returns wavefronts per warp-instruction, summed over the instruction list.
+template <class C>
+void bank_report(const char *geo) {
+  const int i0 = 0, j0 = 0;
+  (void) i0, (void) j0;
+  long total = 0, ideal = 0;
+  int worst = 0;
+  for (int warp = 0; warp < C::NCONS / 32; ++warp) {
+    struct Ld {
+      int off[32];
+      int bytes;
+    };
+    std::vector<Ld> loads;
+    for (int which = 0; which < 24; ++which) {
+      Ld ld;
+      ld.bytes = 16;
+      bool used = true;
+      for (int lane = 0; lane < 32; ++lane) {
+        const int tid = warp * 32 + lane;
+        const int c = tid & 3, e = (tid >> 2) & 1;
+        int rest = tid >> 3;
+        const int y0 = (rest % (8 / C::YT)) * C::YT;
+        rest /= (8 / C::YT);
+        const int bi = (rest % (C::TI / 2)) * 2 + e, bj = rest / (C::TI / 2);
+        const int own_slot = C::slotoff(bi + 1, bj + 1), own_off = own_slot + y0 * 64 + c * 16;
+        int joff[4];
+        for (int h = 0; h < 4; ++h) {
+          const int ya = (h < R) ? y0 - R + h : y0 + C::YT + (h - R);
+          int base;
+          if (ya < 0) base = C::slotoff(bi + 1, bj) + (8 + ya) * 64;
+          else if (ya >= 8) base = C::slotoff(bi + 1, (bj == C::TJ - 1) ? 0 : bj + 2) + (ya - 8) * 64;
+          else base = own_slot + ya * 64;
+          joff[h] = base + c * 16;
+        }
+        const int dl = C::slotoff(bi, bj + 1) - own_slot, dr = C::slotoff(bi + 2, bj + 1) - own_slot;
+        const int iL = -16 + ((c - 1 < 0) ? dl + 64 : 0), iR = 16 + ((c + 1 > 3) ? dr - 64 : 0);
+        // instruction list of diamond_plane: YT own rows, 4 halo rows, then left / right chunks of rows y0-1 .. y0+YT
+        // (the two halo rows of that range only feed one cell each: 64-bit loads, see bk_diamond.h)
+        int o = 0;
+        if (which < C::YT) o = own_off + which * 64;
+        else if (which < C::YT + 4) o = joff[which - C::YT];
+        else {
+          const int q = (which - C::YT - 4) / 2, side = (which - C::YT - 4) % 2;
+          if (q >= C::YT + 2) {
+            used = false;
+            break;
+          }
+          const int row = (q == 0) ? joff[1] : (q == C::YT + 1) ? joff[2] : own_off + (q - 1) * 64;
+          o = row + (side ? iR : iL);
+          if (q == 0 || q == C::YT + 1) {   // 64-bit loads of lf.y / rg.x; odd row groups load the right cell first
+            const bool swp = ((tid >> 3) & 1) != 0;
+            const int first = swp ? iR : iL + 8, second = swp ? iL + 8 : iR;
+            ld.bytes = 8, o = row + (side ? second : first);
+          }
+        }
+        ld.off[lane] = o;
+      }
+      if (used) loads.push_back(ld);
+    }
+    for (const Ld &ld : loads) {
+      const int lanes = ld.bytes == 16 ? 8 : 16, groups = 128 / ld.bytes;
+      int wf = 0;
+      for (int ph = 0; ph < 32 / lanes; ++ph) {
+        int mult[16] = {0};
+        std::vector<int> seen;
+        for (int l = 0; l < lanes; ++l) {
+          const int a = ld.off[ph * lanes + l];
+          bool dup = false;
+          for (int x : seen) dup = dup || x == a;
+          if (dup) continue;
+          seen.push_back(a);
+          ++mult[(a / ld.bytes) % groups];
+        }
+        int m = 0;
+        for (int gidx = 0; gidx < groups; ++gidx) m = std::max(m, mult[gidx]);
+        wf += m;
+      }
+      total += wf, ideal += 32 * ld.bytes / 128;
+      worst = std::max(worst, wf);
+    }
+  }
+  const int warps = C::NCONS / 32;
+  printf("bank model %-24s %ld wavefronts per plane-tile for the consumer loads (%.1f per warp; conflict-free would be %ld; worst "
+         "instruction %d), %.3f per point\n", geo, total, (double) total / warps, ideal, worst, (double) total / (C::TI * C::TJ * 64));
 }
 
 struct Star {
@@ -274,6 +364,9 @@ int main() {
   all_cases<Geo<4, 4, 4, 2>>("BK_FUSED_COMPOSED      Cfg<2,4,4,4,2,3,168,2,..,2>");
   all_cases<Geo<4, 8, 4, 2>>("BK_FUSED_COMPOSED_WIDE Cfg<2,4,8,4,2,3,255,4,..,232,40,2>");
   all_cases<Geo<2, 4, 4, 2>>("developer variant      Cfg<2,2,4,4,2,3,128,2,..,2>");
+  bank_report<Geo<4, 4, 4, 2>>("4x4 tiles, 4 rows");
+  bank_report<Geo<4, 8, 4, 2>>("8x4 tiles, 4 rows");
+  bank_report<Geo<2, 4, 4, 2>>("4x4 tiles, 2 rows");
   if (failures) {
     printf("FAILED (%d)\n", failures);
     return 1;
