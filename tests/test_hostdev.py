@@ -1,0 +1,178 @@
+"""The Python above the C ABI that only ever runs on a GPU box -- the weak loop with its device-side flag handshake, the
+end-to-end pipeline of bench.py, tools/handshake_case.py, tools/composed_trial.py, bench.py's main() -- executed here on
+tests/hostdev.py, a CPU stand-in for the device side of the library (streams as queues that run when the host blocks,
+events, kernels that wait for a flag, hardware queues shared by a process's streams, seeded schedules, deadlock
+DETECTION).  What this checks is orchestration: that every rank's operations are issued in an order that can complete
+under any schedule, that the scripts are right as Python, that the numbers they move end up where the oracle says.  The
+arithmetic of the stand-in is the oracle's own, so numerical agreement here says nothing about the CUDA kernels."""
+import importlib.util
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import bricklib_b200 as bk  # noqa: E402
+import hostdev  # noqa: E402
+import oracle  # noqa: E402
+from oracle import schedule as S  # noqa: E402
+
+
+def load_script(name):
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("st", [1, 2, 3, 4])
+@pytest.mark.parametrize("overlap", [False, True])
+def test_weak_loop_runs_on_the_stand_in_device(st, overlap):
+    rng = np.random.default_rng(st)
+    dom = (32, 24, 16)
+    field = rng.random(dom[::-1])
+    with hostdev.installed(policy="random", seed=st) as dev:
+        d = bk.WeakDomain(dom, st)
+        d.connect()
+        if overlap:
+            d.enable_overlap()
+        d.load_interior(field)
+        launches = sum(d.period() for _ in range(2))
+        bk.device_sync()
+        got = d.read_interior(0)
+        assert launches > 0 and dev.launches >= launches
+    want = S.periodic_steps(st, field, 2 * oracle.ST_ITER[st])
+    assert float((np.abs(got - want) / (np.abs(got) + np.abs(want))).max()) < 1e-12
+
+
+@pytest.mark.parametrize("ranks,extra,kw", [
+    (2, [], {}), (4, [], {}), (2, ["--no-overlap"], {}),
+    (8, [], {"policy": "random", "seed": 3}),
+    (4, [], {"hw_queues": 1}),                                  # ONE hardware queue per rank: the most adversarial valid model
+    (8, [], {"hw_queues": 1, "policy": "random", "seed": 5}),
+    (8, ["--no-overlap"], {"hw_queues": 2, "policy": "random", "seed": 9}),
+])
+def test_handshake_case_script_completes_under_every_schedule(monkeypatch, capsys, ranks, extra, kw):
+    """tools/handshake_case.py as it will run on the box (tests/test_zx_handshake_gpu.py), here on the stand-in: ranks
+    ordered by the device-side flags alone; within a rank the submission order is a valid serial order, so even one
+    hardware queue per rank cannot deadlock it"""
+    hs = load_script("handshake_case")
+    monkeypatch.setattr(sys, "argv", ["handshake_case.py", "--ranks", str(ranks), "--size", "16", "--periods", "3", "--stencils",
+                                      "mpi7pt,mpi25pt", *extra])
+    with hostdev.installed(**kw):
+        hs.main()
+    assert f"handshake ok: {ranks} ranks" in capsys.readouterr().out
+
+
+def test_composed_trial_script_reports_every_variant(monkeypatch, capsys):
+    """tools/composed_trial.py (the child process bench.py and the GPU tests run before the composed kernel is allowed
+    near anything else) as Python: every launch shape, the three variants, the JSON keys the callers read"""
+    ct = load_script("composed_trial")
+    monkeypatch.setattr(sys, "argv", ["composed_trial.py", "--size", "32"])
+    before = bk.fused_variant()
+    with hostdev.installed():
+        ct.main()
+    bk.fused_variant(before)
+    out = json.loads([x for x in capsys.readouterr().out.splitlines() if x.startswith("{")][-1])
+    assert out["ok"] and out["composed"]["ok"] and out["wide"]["ok"]
+    for name in ("staged", "composed", "wide"):
+        assert out[name]["mismatches"] == 0 and out[name]["steps_per_launch"] == 2 and out[name]["points"] == 32 ** 3
+    assert out["composed"]["small_boxes_max_rel"] < 1e-13
+
+
+def test_bench_main_on_the_stand_in_device(monkeypatch, capsys):
+    """bench.py's product arm with its REAL WeakDomain / E2EPipeline / parity code on the stand-in (only the C++ driver
+    binaries, the child trial and the CPU reference timing are replaced): one complete line, parity green"""
+    import bench
+    from test_bench_dryrun import fake_run
+    monkeypatch.setattr(bench.subprocess, "run", fake_run)
+    monkeypatch.setattr(bench, "reference_period_seconds", lambda *a, **k: (0.26, "reference", 16, "avx512"))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--size", "32", "--steps", "2"])
+    monkeypatch.delenv("BK_FUSED_VARIANT", raising=False)
+    before = bk.fused_variant()
+    with hostdev.installed() as dev:
+        bench.main()
+    bk.fused_variant(before)
+    os.environ.pop("BK_FUSED_VARIANT", None)
+    d = json.loads([x for x in capsys.readouterr().out.splitlines() if x.startswith("{")][-1])
+    assert "extras_truncated" not in d and d["steps"] == 2 and d["warmup"] == 3
+    assert d["gpu_launches"] == 2 * 6                       # per period: pull, READY + REST of pass 0, three more passes
+    assert d["parity"]["ok"] and d["parity"]["fused_vs_two_sweeps"]["mismatches"] == 0
+    assert all(d["others"][k]["parity"]["ok"] for k in ("mpi13pt", "mpi25pt", "mpi125pt"))
+    assert d["e2e"]["h2d_bytes_per_step"] == d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["fused_kernel"]["vs_two_sweeps"]["composed"]["mismatches"] == 0
+    assert dev.launches > 100
+
+
+def _two_rank_pipelines(dev, ranks, one_period_in_flight, steps, issue_seed):
+    """`ranks` emulated ranks, each an E2EPipeline of three fields in flight (bench.py's end-to-end leg), issuing their
+    steps independently (a seeded interleaving, each rank in step order)"""
+    import bench
+    from bricklib_b200.weak import Handshake
+    cart = {2: (2, 1, 1), 4: (2, 2, 1)}[ranks]
+    coords = S.cart_coords(cart)
+    slots, dom = 3, (16, 16, 16)
+    doms = [[bk.WeakDomain(dom, 1, cart, coords[r], r) for r in range(ranks)] for _ in range(slots)]
+    for s in range(slots):      # slot s of every rank forms one distributed field: own storages, flags, epochs
+        ptrs = {r: doms[s][r].storage[0].dat.ptr for r in range(ranks)}
+        hs = [Handshake(ranks) for _ in range(ranks)]
+        for r in range(ranks):
+            dev.process = r
+            for q in range(ranks):
+                hs[r].peer[q] = hs[q].buf.ptr
+            doms[s][r].connect(ptrs, hs[r])
+            doms[s][r].enable_overlap()
+            doms[s][r].fill_synthetic(7 + s)
+    bk.device_sync()
+    pipes = []
+    for r in range(ranks):
+        dev.process = r
+        pipes.append(bench.E2EPipeline(bk, [doms[s][r] for s in range(slots)], one_period_in_flight=one_period_in_flight))
+    rng = np.random.default_rng(issue_seed)
+    nxt = [0] * ranks
+    while any(n < steps for n in nxt):
+        r = int(rng.choice([q for q in range(ranks) if nxt[q] < steps]))
+        pipes[r].step(nxt[r])
+        nxt[r] += 1
+    for p in pipes:
+        p.sync()
+    return doms
+
+
+@pytest.mark.parametrize("kw", [{}, {"hw_queues": 1}, {"hw_queues": 2, "policy": "random", "seed": 1}, {"policy": "random", "seed": 4},
+                                {"wide_pull_spin": True, "policy": "random", "seed": 2}])
+@pytest.mark.parametrize("ranks", [2, 4])
+def test_end_to_end_pipelines_of_several_ranks_cannot_deadlock(kw, ranks):
+    """as shipped (one period in flight per GPU): completes under shared hardware queues, random schedules, random issue
+    orders -- even if the pull still spun in every CTA"""
+    for issue_seed in range(3):
+        with hostdev.installed(**kw) as dev:
+            _two_rank_pipelines(dev, ranks, True, 7, issue_seed)
+
+
+def test_the_hang_of_the_round_2_bench_reproduced():
+    """round 2's bench.py kept the periods of all three fields in flight AND its pull spun in every CTA while it waited
+    for the peers' flags.  Its only 8-GPU run hung.  On the stand-in that combination deadlocks as soon as the schedule
+    is not strictly oldest-first: on each GPU one field's spinning pull holds the SMs and waits for a flag whose k_signal
+    sits, on the peer, behind ANOTHER field's spinning pull.  Either change made since -- the one-CTA wait kernel, or one
+    period in flight -- removes it."""
+    deadlocks = 0
+    for issue_seed in range(4):
+        try:
+            with hostdev.installed(wide_pull_spin=True, policy="random", seed=2) as dev:
+                _two_rank_pipelines(dev, 2, False, 7, issue_seed)
+        except hostdev.Deadlock as e:
+            deadlocks += 1
+            assert "pull that spins in every CTA" in str(e) and "k_signal" in str(e)
+    assert deadlocks == 4
+    for issue_seed in range(4):         # the narrow wait kernel alone is enough ...
+        with hostdev.installed(policy="random", seed=2) as dev:
+            _two_rank_pipelines(dev, 2, False, 7, issue_seed)
+    for issue_seed in range(4):         # ... and so is one period in flight alone
+        with hostdev.installed(wide_pull_spin=True, policy="random", seed=2) as dev:
+            _two_rank_pipelines(dev, 2, True, 7, issue_seed)

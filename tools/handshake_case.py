@@ -73,14 +73,15 @@ def main():
         # (2) every rank on its own streams, ordered by the device-side flags only
         doms, ptrs = build(st)
         hs = [Handshake(a.ranks) for _ in range(a.ranks)]
+        streams = []
         for r, x in enumerate(doms):
+            if hasattr(L, "process"):
+                L.process = r        # tests/hostdev.py (the CPU stand-in for the device): whose streams these are
             for q in range(a.ranks):
                 hs[r].peer[q] = hs[q].buf.ptr
             x.connect(ptrs, hs[r])
             if not a.no_overlap:
                 x.enable_overlap()
-        streams = []
-        for _ in doms:
             s = C.c_void_p()
             bk._lib.check(L.bk_stream_create(C.byref(s)))
             streams.append(s)
