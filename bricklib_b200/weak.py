@@ -10,6 +10,7 @@ CTAs that touch the ghost shell run on the high-priority exchange stream right b
 run concurrently; later sweeps wait for both.  Stream-ordered only: nothing spins on the device for the sweep.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -77,6 +78,8 @@ class WeakDomain:
         self.thin = None
         self.trace = None    # developer aid: a list collects (label, Event) marks of one period (tools/period_trace.py)
         self.fuse = 2        # time steps per pass where a fused kernel exists (7/13-point); 1 = one sweep per pass
+        # submit the READY half of pass 0 ahead of the pull (see period()); BK_READY_FIRST=1 makes it the default
+        self.ready_first = os.environ.get("BK_READY_FIRST", "0") not in ("", "0")
 
     # ---- wiring -------------------------------------------------------------------------------------------------
     def connect(self, peer_storage_ptrs=None, handshake=None):
@@ -152,7 +155,15 @@ class WeakDomain:
     def _sweep(self, src, dst, lo, hi, stream):
         core.stencil(self.stencil, self.grid, self.bricks[src], self.bricks[dst], lo, hi, None, self.kernel, stream)
 
-    def _exchange(self, stream, fused_signal=False):
+    def _announce(self, stream):
+        """tell every peer that my skin is final for this epoch (no-op without peers)"""
+        if self.hs is None or not self.peers:
+            return
+        sig = (C.c_void_p * len(self.peers))(*[self.hs.ready_flag_on(p, self.rank) for p in self.peers])
+        check(load().bk_flags_signal(sig, len(self.peers), self.epoch, stream))
+
+    def _pull(self, stream, fused_signal=False):
+        """pull the neighbours' skins once they have announced them, then tell them I am done reading"""
         hs, e = self.hs, self.epoch
         ce = self._remote() and fused_signal      # only next to overlapped sweeps; else the kernel is faster
         if hs is None or not self.peers:
@@ -161,9 +172,6 @@ class WeakDomain:
             else:
                 self.view.exchange(stream)
             return
-        # tell every peer my skin is final, pull theirs once they say the same, then tell them I am done reading
-        sig = (C.c_void_p * len(self.peers))(*[hs.ready_flag_on(p, self.rank) for p in self.peers])
-        check(load().bk_flags_signal(sig, len(self.peers), e, stream))
         waits = [hs.ready_flag_on(self.rank, p) for p in self.peers]
         dones = [hs.done_flag_on(p, self.rank) for p in self.peers]
         if ce:
@@ -172,6 +180,10 @@ class WeakDomain:
             self.view.exchange_gate(waits, dones, None, e, stream)
         else:
             self.view.exchange_sync(waits, dones, e, stream)
+
+    def _exchange(self, stream, fused_signal=False):
+        self._announce(stream)
+        self._pull(stream, fused_signal)
 
     def _remote(self):
         """does the exchange run on the copy engines (and the split sweep with thin ghost-dependent segments)?"""
@@ -212,8 +224,23 @@ class WeakDomain:
         if cs is not None:
             self.ev_comp.record(stream)
             check(load().bk_stream_wait_event(cs, self.ev_comp.h))  # previous period's sweeps wrote the skin
-        self._exchange(cs if cs is not None else stream, fused_signal=cs is not None)
-        self._mark("exchange done", cs if cs is not None else stream)
+        xs = cs if cs is not None else stream
+        self._announce(xs)
+        # ready_first: the READY half of pass 0 is SUBMITTED before the pull (same streams, same dependencies -- only the
+        # order in which the two independent streams are fed changes): its CTAs are on the SMs when the pull's arrive, and
+        # the high-priority pull trickles in as they retire instead of taking the machine first.  Which order is faster
+        # is a measurement (bench.py times both); correctness does not depend on it.
+        early = False
+        if self.ready_first and overlap and fuse < self.st_iter:
+            try:
+                thin = _lib.PART_THIN if self._thin() else 0
+                self._advance(fuse, 0, 1, full[0], full[1], own, _lib.PART_READY | thin, stream)
+                self._mark("pass 0 READY done", stream)
+                early = True
+            except core.Unsupported:
+                pass
+        self._pull(xs, fused_signal=cs is not None)
+        self._mark("exchange done", xs)
         done, p = 0, 0
         while done < self.st_iter:
             src, dst = p % 2, 1 - p % 2
@@ -224,8 +251,9 @@ class WeakDomain:
             if p == 0 and overlap and not last:
                 try:
                     thin = _lib.PART_THIN if self._thin() else 0
-                    self._advance(fuse, src, dst, lo, hi, own, _lib.PART_READY | thin, stream)
-                    self._mark("pass 0 READY done", stream)
+                    if not early:
+                        self._advance(fuse, src, dst, lo, hi, own, _lib.PART_READY | thin, stream)
+                        self._mark("pass 0 READY done", stream)
                     self._advance(fuse, src, dst, lo, hi, own, _lib.PART_REST | thin, cs)
                     self._mark("pass 0 REST done", cs)
                     self.ev_comm.record(cs)
@@ -233,6 +261,8 @@ class WeakDomain:
                     done, p = done + fuse, p + 1
                     continue
                 except core.Unsupported:
+                    if early:
+                        raise
                     if fuse == 2:
                         fuse = 1
                         continue

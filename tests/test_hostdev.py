@@ -31,14 +31,15 @@ def load_script(name):
 
 
 @pytest.mark.parametrize("st", [1, 2, 3, 4])
-@pytest.mark.parametrize("overlap", [False, True])
-def test_weak_loop_runs_on_the_stand_in_device(st, overlap):
+@pytest.mark.parametrize("overlap,ready_first", [(False, False), (True, False), (True, True)])
+def test_weak_loop_runs_on_the_stand_in_device(st, overlap, ready_first):
     rng = np.random.default_rng(st)
     dom = (32, 24, 16)
     field = rng.random(dom[::-1])
     with hostdev.installed(policy="random", seed=st) as dev:
         d = bk.WeakDomain(dom, st)
         d.connect()
+        d.ready_first = ready_first
         if overlap:
             d.enable_overlap()
         d.load_interior(field)
@@ -46,6 +47,9 @@ def test_weak_loop_runs_on_the_stand_in_device(st, overlap):
         bk.device_sync()
         got = d.read_interior(0)
         assert launches > 0 and dev.launches >= launches
+        if overlap:     # the READY half of pass 0 is submitted before / after the pull
+            order = [x for x in dev.executed if x.startswith("pull") or x.endswith("READY")]
+            assert len(order) == 4
     want = S.periodic_steps(st, field, 2 * oracle.ST_ITER[st])
     assert float((np.abs(got - want) / (np.abs(got) + np.abs(want))).max()) < 1e-12
 
@@ -57,11 +61,13 @@ def test_weak_loop_runs_on_the_stand_in_device(st, overlap):
     (8, [], {"hw_queues": 1, "policy": "random", "seed": 5}),
     (8, ["--no-overlap"], {"hw_queues": 2, "policy": "random", "seed": 9}),
 ])
-def test_handshake_case_script_completes_under_every_schedule(monkeypatch, capsys, ranks, extra, kw):
+@pytest.mark.parametrize("ready_first", ["0", "1"])
+def test_handshake_case_script_completes_under_every_schedule(monkeypatch, capsys, ranks, extra, kw, ready_first):
     """tools/handshake_case.py as it will run on the box (tests/test_zx_handshake_gpu.py), here on the stand-in: ranks
     ordered by the device-side flags alone; within a rank the submission order is a valid serial order, so even one
     hardware queue per rank cannot deadlock it"""
     hs = load_script("handshake_case")
+    monkeypatch.setenv("BK_READY_FIRST", ready_first)
     monkeypatch.setattr(sys, "argv", ["handshake_case.py", "--ranks", str(ranks), "--size", "16", "--periods", "3", "--stencils",
                                       "mpi7pt,mpi25pt", *extra])
     with hostdev.installed(**kw):
@@ -106,6 +112,7 @@ def test_bench_main_on_the_stand_in_device(monkeypatch, capsys):
     assert all(d["others"][k]["parity"]["ok"] for k in ("mpi13pt", "mpi25pt", "mpi125pt"))
     assert d["e2e"]["h2d_bytes_per_step"] == d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["fused_kernel"]["vs_two_sweeps"]["composed"]["mismatches"] == 0
+    assert d["submission_order"]["selected"] in ("pull first", "ready first")
     assert dev.launches > 100
 
 
