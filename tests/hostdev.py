@@ -20,14 +20,19 @@ What it models
   * one SM-resource effect, on request: with `wide_pull_spin=True` the gated pull behaves like the kernel this project
     shipped until round 2 -- the wait for the peers' flags is a spin inside EVERY CTA of the wide pull, so once the pull is
     at the head of its stream it occupies the GPU (no other kernel of that process starts) until the flags arrive.
-What it does not model: SM resources beyond that, timing, CUDA IPC.
+  * several ranks as THREADS of this process (`RankThreads`): each thread is one rank's host program, blocking calls
+    (synchronise, collectives of the stand-in for torch.distributed) hand the turn to the other threads, and a deadlock is
+    declared when every thread is blocked and nothing can run.  This is how bench.py's whole main() runs here for N ranks.
+What it does not model: SM resources beyond that, timing.  CUDA IPC handles are the addresses themselves.
 
 The arithmetic is the oracle's (oracle/oracle.c through oracle.port(): brick sweeps through the adjacency list, layout
 copies) -- this module is a checker's tool like the oracle itself and is imported by tests only.
 """
 import collections
 import ctypes as C
+import functools
 import random
+import threading
 
 import numpy as np
 
@@ -41,7 +46,7 @@ class Deadlock(RuntimeError):
     pass
 
 
-def _sid(stream):
+def _raw_sid(stream):
     if stream is None:
         return 0
     return int(stream.value or 0) if hasattr(stream, "value") else int(stream)
@@ -72,7 +77,10 @@ class HostDev:
         self.bufs = {}                      # address -> numpy buffer (device and pinned allocations)
         self.streams = {0: collections.deque()}
         self.stream_index = {0: ("null", 0)}    # stream -> (owning process, index among that process's streams)
-        self.process = 0
+        self._tls = threading.local()
+        self.mutex = threading.RLock()
+        self.cond = threading.Condition(self.mutex)
+        self.live_threads, self.waiters, self.dead = 1, {}, None     # rank threads alive / blocked (with what would let them go on)
         self.wide_pull_spin = wide_pull_spin
         self.resident = {}                  # process -> the exclusive operation that currently occupies its GPU
         self.events = {}                    # handle -> [last recorded ticket, last fired ticket, virtual time of the last firing]
@@ -87,12 +95,51 @@ class HostDev:
     def __getattr__(self, name):            # everything not emulated: the real library (host logic only)
         return getattr(self.real, name)
 
+    @property
+    def process(self):                      # whose streams are being created: per host thread (= rank)
+        return getattr(self._tls, "process", 0)
+
+    @process.setter
+    def process(self, value):
+        self._tls.process = value
+
+    def block(self, what, can_go_on):
+        """the calling rank thread cannot go on until another thread acts: hand over the turn, or declare the deadlock
+        when every live thread is blocked, none of them could go on by now, and nothing can run (call with the mutex held;
+        returns after a wake-up)"""
+        if self.dead is not None:
+            raise Deadlock(self.dead)
+        me = threading.get_ident()
+        self.waiters[me] = can_go_on
+        try:
+            if len(self.waiters) >= self.live_threads and not any(f() for f in self.waiters.values()) and not self._runnable():
+                heads = sorted((q[0].seq, f"stream {sid:#x}: {q[0].label}") for sid, q in self.streams.items() if q)
+                self.dead = f"{what}: every rank is blocked and nothing can run; queue heads: " + "; ".join(x for _, x in heads)
+                self.cond.notify_all()
+                raise Deadlock(self.dead)
+            self.cond.wait(timeout=5.0)
+            if self.dead is not None:
+                raise Deadlock(self.dead)
+        finally:
+            self.waiters.pop(me, None)
+
     def _handle(self):
         self.next_handle += 0x10
         return self.next_handle
 
+    def _sid(self, stream):
+        """stream handle -> queue key; the NULL stream is per process (= per rank thread), as every process has its own"""
+        sid = _raw_sid(stream)
+        if sid != 0 or self.process == 0:
+            return sid
+        key = -1 - int(self.process)
+        if key not in self.streams:
+            self.streams[key] = collections.deque()
+            self.stream_index[key] = (self.process, 0)
+        return key
+
     def _enqueue(self, stream, label, run, ready=None, kernel=False, exclusive=False):
-        sid = _sid(stream)
+        sid = self._sid(stream)
         if sid not in self.streams:
             raise AssertionError(f"operation on an unknown stream {sid:#x}")
         self.seq += 1
@@ -137,11 +184,14 @@ class HostDev:
                 return
             ready = self._runnable()
             if not ready:
+                if until is None and not any(self.streams.values()):
+                    return
+                if self.live_threads > 1:       # another rank's host program may still enqueue what this one waits for
+                    self.block(what, lambda: (until is not None and until()) or bool(self._runnable()))
+                    continue
                 if any(self.streams.values()):
                     stuck = sorted((q[0].seq, f"stream {sid:#x}: {q[0].label}") for sid, q in self.streams.items() if q)
                     raise Deadlock(f"{what}: nothing can run; queue heads: " + "; ".join(s for _, s in stuck))
-                if until is None or until():
-                    return
                 raise Deadlock(f"{what}: all queues are empty and the condition does not hold")
             op = min(ready, key=lambda o: o.seq) if self.policy == "fifo" else self.rng.choice(ready)
             self.streams[op.stream].popleft()
@@ -150,6 +200,8 @@ class HostDev:
             self.clock += 1.0 if op.kernel else 0.01
             op.run()
             self.executed.append(op.label)
+            if self.live_threads > 1:
+                self.cond.notify_all()
 
     def _span(self, addr, nbytes=None):
         """(numpy uint8 view from addr to the end of its allocation)"""
@@ -185,7 +237,7 @@ class HostDev:
         return self._alloc(out, nbytes)
 
     def bk_dev_free(self, ptr):
-        self.pump(what="bk_dev_free")       # cudaFree synchronises the device
+        self.bk_device_sync()               # cudaFree synchronises the device
         self.bufs.pop(_ival(ptr), None)
         return 0
 
@@ -221,18 +273,38 @@ class HostDev:
         return self.bk_stream_create(out)
 
     def bk_stream_destroy(self, stream):
-        sid = _sid(stream)
+        sid = self._sid(stream)
         self.pump(lambda: not self.streams[sid], "bk_stream_destroy")
         del self.streams[sid]
         return 0
 
     def bk_stream_sync(self, stream):
-        sid = _sid(stream)
+        sid = self._sid(stream)
         self.pump(lambda: not self.streams[sid], f"bk_stream_sync({sid:#x})")
         return 0
 
+    def _mine(self):
+        me = self.process
+        return [q for sid, q in self.streams.items() if self.stream_index[sid][0] == me or (me == 0 and sid == 0)]
+
     def bk_device_sync(self):
-        self.pump(what="bk_device_sync")
+        if self.live_threads > 1:           # a rank's device: its own streams (and the null stream)
+            self.pump(lambda: not any(self._mine()), "bk_device_sync")
+        else:
+            self.pump(what="bk_device_sync")
+        return 0
+
+    # CUDA IPC between rank threads: the handle is the address
+    def bk_ipc_export(self, ptr, handle):
+        C.memmove(handle, C.byref(C.c_uint64(_ival(ptr))), 8)
+        return 0
+
+    def bk_ipc_open(self, handle, out):
+        raw = handle if isinstance(handle, (bytes, bytearray)) else bytes(handle)
+        out._obj.value = int.from_bytes(raw[:8], "little")
+        return 0
+
+    def bk_ipc_close(self, ptr):
         return 0
 
     def bk_event_create(self, out):
@@ -447,6 +519,98 @@ class HostDev:
                 _u64(a).value = v
         return self._enqueue(stream, "pull that spins in every CTA + done flags" if spin else "pull + done flags", run,
                              (lambda: all(_u64(a).value >= v for a in fl)) if spin else None, kernel=True, exclusive=spin)
+
+
+def _locked(fn):
+    @functools.wraps(fn)
+    def call(self, *a, **k):
+        with self.mutex:
+            if self.dead is not None:
+                raise Deadlock(self.dead)
+            return fn(self, *a, **k)
+    return call
+
+
+for _name, _fn in list(vars(HostDev).items()):
+    if _name.startswith("bk_") and callable(_fn):
+        setattr(HostDev, _name, _locked(_fn))
+
+
+class RankDist:
+    """torch.distributed for rank threads: collectives that really wait for every rank (and count as blocked)"""
+
+    def __init__(self, dev, world):
+        self.dev, self.world, self.gen, self.slots = dev, world, 0, {}
+        self.log = []
+
+    def _collect(self, rank, value, what):
+        dev = self.dev
+        with dev.mutex:
+            gen = self.gen
+            box = self.slots.setdefault(gen, {})
+            box[rank] = value
+            if len(box) == self.world:
+                self.gen += 1
+                dev.cond.notify_all()
+            while len(box) < self.world:
+                dev.block(f"collective {what} (rank {rank})", lambda: len(box) >= self.world)
+            return [box[r] for r in range(self.world)]
+
+    def for_rank(self, rank):
+        return _RankView(self, rank)
+
+
+class _RankView:
+    def __init__(self, dist, rank):
+        self.dist, self.rank = dist, rank
+
+    def barrier(self, group=None):
+        self.dist._collect(self.rank, None, "host barrier" if group is not None else "barrier")
+
+    def all_gather_object(self, out, obj):
+        for i, v in enumerate(self.dist._collect(self.rank, obj, "all_gather_object")):
+            out[i] = v
+
+    def allreduce(self, value, op):
+        vals = self.dist._collect(self.rank, value, "all_reduce")
+        return max(vals) if op == "max" else sum(vals)
+
+    def destroy_process_group(self):
+        self.dist._collect(self.rank, None, "destroy")
+
+
+def run_ranks(dev, world, target):
+    """target(rank) on `world` threads, one per rank; returns the list of results; the first exception is re-raised"""
+    results, errors = [None] * world, []
+
+    def body(r):
+        try:
+            dev.process = r
+            results[r] = target(r)
+        except BaseException as exc:  # noqa: BLE001
+            errors.append((r, exc))
+            with dev.mutex:
+                if dev.dead is None and not isinstance(exc, Deadlock):
+                    dev.dead = f"rank {r} failed: {exc!r}"
+        finally:
+            with dev.mutex:
+                dev.live_threads -= 1
+                dev.cond.notify_all()
+
+    with dev.mutex:
+        dev.live_threads = world
+    threads = [threading.Thread(target=body, args=(r,), daemon=True) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    with dev.mutex:
+        dev.live_threads = 1
+    if errors:
+        errors.sort(key=lambda e: isinstance(e[1], Deadlock))      # a real failure first, the deadlocks it caused after
+        raise errors[0][1]
+    assert not any(t.is_alive() for t in threads), "a rank thread is still running"
+    return results
 
 
 class installed:

@@ -183,3 +183,38 @@ def test_the_hang_of_the_round_2_bench_reproduced():
     for issue_seed in range(4):         # ... and so is one period in flight alone
         with hostdev.installed(wide_pull_spin=True, policy="random", seed=2) as dev:
             _two_rank_pipelines(dev, 2, True, 7, issue_seed)
+
+
+@pytest.mark.parametrize("world,size,kw", [(2, 32, {}), (2, 16, {"hw_queues": 1, "policy": "random", "seed": 7}),
+                                           (4, 16, {"policy": "random", "seed": 11}), (8, 16, {"hw_queues": 2, "policy": "random", "seed": 13}),
+                                           (8, 16, {"wide_pull_spin": True, "policy": "random", "seed": 3})])
+def test_bench_main_for_several_ranks_on_the_stand_in_device(monkeypatch, capsys, world, size, kw):
+    """bench.py's main() for EVERY rank of an N-rank job at once -- one host thread per rank on the stand-in device, the
+    collectives of torch.distributed replaced by ones that really wait for every rank: rendezvous over (stand-in) IPC
+    handles, the fused-kernel and submission-order selections, the timed periods with their device-side handshake, parity
+    against the oracle on every rank, the other stencils, rank 0's driver legs behind the host barrier, the end-to-end
+    pipelines.  A protocol error anywhere in that sequence is a detected deadlock here instead of a hung 8-GPU box."""
+    import bench
+    from test_bench_dryrun import fake_run
+    monkeypatch.setattr(bench.subprocess, "run", fake_run)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", str(world), "--size", str(size), "--steps", "4"])
+    monkeypatch.delenv("BK_FUSED_VARIANT", raising=False)
+    before = bk.fused_variant()
+    with hostdev.installed(**kw) as dev:
+        dist = hostdev.RankDist(dev, world)
+        monkeypatch.setattr(bench, "dist_setup", lambda n: (dev.process, world, dist.for_rank(dev.process), "gloo"))
+        monkeypatch.setattr(bench, "max_over_ranks", lambda d, v: v if d is None else d.allreduce(v, "max"))
+        monkeypatch.setattr(bench, "sum_over_ranks", lambda d, v: v if d is None else d.allreduce(v, "sum"))
+        monkeypatch.setattr(bench, "barrier", lambda d: d.barrier() if d is not None else None)
+        hostdev.run_ranks(dev, world, lambda r: bench.main())
+    bk.fused_variant(before)
+    os.environ.pop("BK_FUSED_VARIANT", None)
+    lines = [json.loads(x) for x in capsys.readouterr().out.splitlines() if x.startswith("{")]
+    assert len(lines) == 1                          # rank 0 alone prints
+    d = lines[0]
+    assert d["n_gpus"] == world and "extras_truncated" not in d
+    assert d["parity"]["ok"] and d["parity"]["checked_points"] > 0
+    assert all(d["others"][k]["parity"]["ok"] for k in ("mpi13pt", "mpi25pt", "mpi125pt"))
+    assert d["others"]["strong"]["global_1024_sub_64"]["cmd"].endswith(f"-g {world} -S mpi7pt")
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] % world == 0
+    assert d["config"]["thin_split"] is True and d["submission_order"]["selected"] in ("pull first", "ready first")
