@@ -85,6 +85,7 @@ class HostDev:
         self.resident = {}                  # process -> the exclusive operation that currently occupies its GPU
         self.events = {}                    # handle -> [last recorded ticket, last fired ticket, virtual time of the last firing]
         self.plans = {}
+        self.adj_checked = set()
         self.next_handle = 0x1000
         self.seq = 0
         self.clock = 0.0
@@ -405,6 +406,20 @@ class HostDev:
                                       C.c_size_t(0), cf)
         assert rc == 0, rc
 
+    def _adjacency_check(self, f, grid, lo, hi, steps, stream):
+        """bk_stencil.cu: marching_matches_adjacency -- the first marching launch over a new (adj, grid, box) triple runs a
+        check kernel and SYNCHRONISES its stream (cached afterwards; BK_SKIP_ADJ_CHECK skips it).  A host that blocks here
+        cannot enqueue anything else meanwhile, which matters when one host thread feeds several emulated ranks."""
+        import os
+        if os.environ.get("BK_SKIP_ADJ_CHECK"):
+            return
+        key = (_ival(f._obj.adj), _ival(grid), tuple(int(x) for x in lo), tuple(int(x) for x in hi), steps - 1)
+        if key in self.adj_checked:
+            return
+        self.adj_checked.add(key)
+        self._enqueue(stream, "adjacency check", lambda: None, kernel=True)
+        self.bk_stream_sync(stream)
+
     def _advance(self, stencil, steps, f, grid, gdims, boxes, coeff, stream, label):
         fld = f._obj
         adj, src, dst = _ival(fld.adj), _ival(fld.inp), _ival(fld.out)
@@ -428,12 +443,16 @@ class HostDev:
         return self._enqueue(stream, label, run, kernel=True)
 
     def bk_stencil_apply(self, stencil, f, grid, gdims, lo, hi, coeff, flags, stream):
+        if flags != _lib.KERNEL_BRICK:
+            self._adjacency_check(f, grid, lo, hi, 1, stream)
         return self._advance(stencil, 1, f, grid, gdims, [(lo, hi)], coeff, stream, f"sweep st{stencil}")
 
     def bk_stencil_advance(self, stencil, steps, f, grid, gdims, lo, hi, coeff, ready_lo, ready_hi, part, stream):
         if steps == 2 and self.real.bk_stencil_radius(stencil) > 2:
             return BK_EUNSUPPORTED
         lo, hi = [int(x) for x in lo], [int(x) for x in hi]
+        if not part & _lib.PART_GRID_TOPOLOGY:
+            self._adjacency_check(f, grid, lo, hi, steps, stream)
         part &= ~(_lib.PART_THIN | _lib.PART_GRID_TOPOLOGY)
         boxes, name = [(lo, hi)], "ALL"
         if part != _lib.PART_ALL:

@@ -24,9 +24,15 @@ from oracle import schedule as S  # noqa: E402
 
 
 def load_script(name):
+    """a tools/ script as a module; what it exports to the environment at import time is undone (the tests say what they
+    want set)"""
+    saved = dict(os.environ)
     spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
+    for k in set(os.environ) - set(saved):
+        del os.environ[k]
+    os.environ.update(saved)
     return m
 
 
@@ -67,12 +73,27 @@ def test_handshake_case_script_completes_under_every_schedule(monkeypatch, capsy
     ordered by the device-side flags alone; within a rank the submission order is a valid serial order, so even one
     hardware queue per rank cannot deadlock it"""
     hs = load_script("handshake_case")
+    monkeypatch.setenv("BK_SKIP_ADJ_CHECK", "1")        # what the script sets for itself when it is run
     monkeypatch.setenv("BK_READY_FIRST", ready_first)
     monkeypatch.setattr(sys, "argv", ["handshake_case.py", "--ranks", str(ranks), "--size", "16", "--periods", "3", "--stencils",
                                       "mpi7pt,mpi25pt", *extra])
     with hostdev.installed(**kw):
         hs.main()
     assert f"handshake ok: {ranks} ranks" in capsys.readouterr().out
+
+
+def test_one_host_thread_feeding_several_ranks_must_not_block_in_the_adjacency_check(monkeypatch):
+    """why tools/handshake_case.py switches the one-time grid-vs-adjacency check off: it synchronises the stream at the first
+    launch over a new box, and a host that blocks inside rank 0's period can never enqueue the signal rank 0 waits for"""
+    hs = load_script("handshake_case")
+    monkeypatch.setattr(sys, "argv", ["handshake_case.py", "--ranks", "2", "--size", "16", "--periods", "2", "--stencils", "mpi7pt"])
+    monkeypatch.delenv("BK_SKIP_ADJ_CHECK", raising=False)      # (the script set it at import)
+    with pytest.raises(hostdev.Deadlock):
+        with hostdev.installed():
+            hs.main()
+    monkeypatch.setenv("BK_SKIP_ADJ_CHECK", "1")
+    with hostdev.installed():
+        hs.main()
 
 
 def test_composed_trial_script_reports_every_variant(monkeypatch, capsys):
@@ -121,6 +142,7 @@ def _two_rank_pipelines(dev, ranks, one_period_in_flight, steps, issue_seed):
     steps independently (a seeded interleaving, each rank in step order)"""
     import bench
     from bricklib_b200.weak import Handshake
+    os.environ["BK_SKIP_ADJ_CHECK"] = "1"   # ONE host thread feeds all ranks here (see the handshake script); undone by the caller
     cart = {2: (2, 1, 1), 4: (2, 2, 1)}[ranks]
     coords = S.cart_coords(cart)
     slots, dom = 3, (16, 16, 16)
@@ -157,9 +179,12 @@ def _two_rank_pipelines(dev, ranks, one_period_in_flight, steps, issue_seed):
 def test_end_to_end_pipelines_of_several_ranks_cannot_deadlock(kw, ranks):
     """as shipped (one period in flight per GPU): completes under shared hardware queues, random schedules, random issue
     orders -- even if the pull still spun in every CTA"""
-    for issue_seed in range(3):
-        with hostdev.installed(**kw) as dev:
-            _two_rank_pipelines(dev, ranks, True, 7, issue_seed)
+    try:
+        for issue_seed in range(3):
+            with hostdev.installed(**kw) as dev:
+                _two_rank_pipelines(dev, ranks, True, 7, issue_seed)
+    finally:
+        os.environ.pop("BK_SKIP_ADJ_CHECK", None)
 
 
 def test_the_hang_of_the_round_2_bench_reproduced():
@@ -169,20 +194,23 @@ def test_the_hang_of_the_round_2_bench_reproduced():
     sits, on the peer, behind ANOTHER field's spinning pull.  Either change made since -- the one-CTA wait kernel, or one
     period in flight -- removes it."""
     deadlocks = 0
-    for issue_seed in range(4):
-        try:
-            with hostdev.installed(wide_pull_spin=True, policy="random", seed=2) as dev:
+    try:
+        for issue_seed in range(4):
+            try:
+                with hostdev.installed(wide_pull_spin=True, policy="random", seed=2) as dev:
+                    _two_rank_pipelines(dev, 2, False, 7, issue_seed)
+            except hostdev.Deadlock as e:
+                deadlocks += 1
+                assert "pull that spins in every CTA" in str(e) and "k_signal" in str(e)
+        assert deadlocks == 4
+        for issue_seed in range(4):         # the narrow wait kernel alone is enough ...
+            with hostdev.installed(policy="random", seed=2) as dev:
                 _two_rank_pipelines(dev, 2, False, 7, issue_seed)
-        except hostdev.Deadlock as e:
-            deadlocks += 1
-            assert "pull that spins in every CTA" in str(e) and "k_signal" in str(e)
-    assert deadlocks == 4
-    for issue_seed in range(4):         # the narrow wait kernel alone is enough ...
-        with hostdev.installed(policy="random", seed=2) as dev:
-            _two_rank_pipelines(dev, 2, False, 7, issue_seed)
-    for issue_seed in range(4):         # ... and so is one period in flight alone
-        with hostdev.installed(wide_pull_spin=True, policy="random", seed=2) as dev:
-            _two_rank_pipelines(dev, 2, True, 7, issue_seed)
+        for issue_seed in range(4):         # ... and so is one period in flight alone
+            with hostdev.installed(wide_pull_spin=True, policy="random", seed=2) as dev:
+                _two_rank_pipelines(dev, 2, True, 7, issue_seed)
+    finally:
+        os.environ.pop("BK_SKIP_ADJ_CHECK", None)
 
 
 @pytest.mark.parametrize("world,size,kw", [(2, 32, {}), (2, 16, {"hw_queues": 1, "policy": "random", "seed": 7}),
@@ -199,6 +227,7 @@ def test_bench_main_for_several_ranks_on_the_stand_in_device(monkeypatch, capsys
     monkeypatch.setattr(bench.subprocess, "run", fake_run)
     monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", str(world), "--size", str(size), "--steps", "4"])
     monkeypatch.delenv("BK_FUSED_VARIANT", raising=False)
+    monkeypatch.delenv("BK_SKIP_ADJ_CHECK", raising=False)      # one host thread per rank: the check's stream synchronise is on
     before = bk.fused_variant()
     with hostdev.installed(**kw) as dev:
         dist = hostdev.RankDist(dev, world)

@@ -15,6 +15,11 @@ import sys
 # waits for a flag could sit in FRONT of the very kernel that raises it (submission order is rank by rank).  Between
 # processes this cannot happen -- each process owns its queues.  Before the CUDA context exists:
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# The first marching launch over a new (adjacency, grid, box) triple checks on the device that grid and adjacency agree and
+# SYNCHRONISES its stream (bk_stencil.cu: marching_matches_adjacency).  Between processes that is harmless; here ONE host
+# thread feeds all the ranks, and blocking inside rank 0's period -- whose stream waits for a flag rank 1 raises -- before
+# rank 1's period has been enqueued would never return (tests/hostdev.py models exactly this).  The grids are BrickDecomp's.
+os.environ["BK_SKIP_ADJ_CHECK"] = "1"
 
 import numpy as np  # noqa: E402
 
