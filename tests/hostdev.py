@@ -116,6 +116,7 @@ class HostDev:
             if len(self.waiters) >= self.live_threads and not any(f() for f in self.waiters.values()) and not self._runnable():
                 heads = sorted((q[0].seq, f"stream {sid:#x}: {q[0].label}") for sid, q in self.streams.items() if q)
                 self.dead = f"{what}: every rank is blocked and nothing can run; queue heads: " + "; ".join(x for _, x in heads)
+                self.dead += self._where_the_ranks_are()
                 self.cond.notify_all()
                 raise Deadlock(self.dead)
             self.cond.wait(timeout=5.0)
@@ -123,6 +124,18 @@ class HostDev:
                 raise Deadlock(self.dead)
         finally:
             self.waiters.pop(me, None)
+
+    def _where_the_ranks_are(self):
+        """the innermost frames of every blocked rank thread outside this module (what the deadlock report needs most)"""
+        import sys
+        import traceback
+        out = []
+        frames = sys._current_frames()
+        for ident in self.waiters:
+            fr = frames.get(ident)
+            stack = [f for f in traceback.extract_stack(fr) if "hostdev.py" not in f.filename and "threading.py" not in f.filename]
+            out.append(" <- ".join(f"{f.name}:{f.lineno}" for f in reversed(stack[-4:])))
+        return " || blocked in: " + " || ".join(out)
 
     def _handle(self):
         self.next_handle += 0x10
@@ -284,13 +297,13 @@ class HostDev:
         self.pump(lambda: not self.streams[sid], f"bk_stream_sync({sid:#x})")
         return 0
 
-    def _mine(self):
-        me = self.process
+    def _mine(self, me):
         return [q for sid, q in self.streams.items() if self.stream_index[sid][0] == me or (me == 0 and sid == 0)]
 
     def bk_device_sync(self):
         if self.live_threads > 1:           # a rank's device: its own streams (and the null stream)
-            self.pump(lambda: not any(self._mine()), "bk_device_sync")
+            me = self.process               # captured: other rank threads evaluate this condition too (deadlock check)
+            self.pump(lambda: not any(self._mine(me)), f"bk_device_sync (rank {me})")
         else:
             self.pump(what="bk_device_sync")
         return 0
@@ -380,7 +393,7 @@ class HostDev:
         return self._enqueue(stream, "fill_synthetic", run, kernel=True)
 
     def bk_compare_storage(self, grid, gdims, lo, hi, a, a_step, b, b_step, tol, mism, maxrel, stream):
-        self.bk_stream_sync(stream)
+        self.bk_device_sync()               # the real call synchronises its stream and frees its scratch (device-wide)
         ga, _ = self._grid(grid, gdims)
         lo, hi = [int(x) for x in lo], [int(x) for x in hi]
         ids = ga[lo[2]:hi[2], lo[1]:hi[1], lo[0]:hi[0]].ravel().astype(np.int64)
@@ -408,7 +421,7 @@ class HostDev:
 
     def _adjacency_check(self, f, grid, lo, hi, steps, stream):
         """bk_stencil.cu: marching_matches_adjacency -- the first marching launch over a new (adj, grid, box) triple runs a
-        check kernel and SYNCHRONISES its stream (cached afterwards; BK_SKIP_ADJ_CHECK skips it).  A host that blocks here
+        check kernel, SYNCHRONISES its stream and frees its result word -- a device-wide wait (cached afterwards; BK_SKIP_ADJ_CHECK skips it).  A host that blocks here
         cannot enqueue anything else meanwhile, which matters when one host thread feeds several emulated ranks."""
         import os
         if os.environ.get("BK_SKIP_ADJ_CHECK"):
@@ -418,7 +431,7 @@ class HostDev:
             return
         self.adj_checked.add(key)
         self._enqueue(stream, "adjacency check", lambda: None, kernel=True)
-        self.bk_stream_sync(stream)
+        self.bk_device_sync()               # cudaStreamSynchronize, then cudaFree of the result word: the whole device
 
     def _advance(self, stencil, steps, f, grid, gdims, boxes, coeff, stream, label):
         fld = f._obj
