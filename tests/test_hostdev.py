@@ -247,3 +247,32 @@ def test_bench_main_for_several_ranks_on_the_stand_in_device(monkeypatch, capsys
     assert d["others"]["strong"]["global_1024_sub_64"]["cmd"].endswith(f"-g {world} -S mpi7pt")
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] % world == 0
     assert d["config"]["thin_split"] is True and d["submission_order"]["selected"] in ("pull first", "ready first")
+
+
+@pytest.mark.parametrize("world,kw", [(2, {}), (4, {"policy": "random", "seed": 2}), (8, {"hw_queues": 1, "policy": "random", "seed": 4})])
+def test_multi_process_parity_script_with_rank_threads(monkeypatch, capsys, world, kw):
+    """tests/mgpu_weak_check.py (what tests/test_multi_gpu.py launches under torchrun on a multi-GPU box) for all its ranks at
+    once on the stand-in: rendezvous, four stencils on one domain, overlap and fused passes, parity with the oracle"""
+    import bench
+    spec = importlib.util.spec_from_file_location("mgpu_weak_check", os.path.join(ROOT, "tests", "mgpu_weak_check.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    monkeypatch.setattr(sys, "argv", ["mgpu_weak_check.py", "--size", "16", "--periods", "2"])
+    monkeypatch.setenv("WORLD_SIZE", str(world))
+    monkeypatch.delenv("BK_SKIP_ADJ_CHECK", raising=False)
+
+    def rank_main(r):
+        try:
+            m.main()
+        except SystemExit as e:
+            return e.code
+
+    with hostdev.installed(**kw) as dev:
+        dist = hostdev.RankDist(dev, world)
+        monkeypatch.setattr(bench, "dist_setup", lambda n: (dev.process, world, dist.for_rank(dev.process), "gloo"))
+        monkeypatch.setattr(bench, "max_over_ranks", lambda d, v: v if d is None else d.allreduce(v, "max"))
+        monkeypatch.setattr(bench, "barrier", lambda d: d.barrier() if d is not None else None)
+        codes = hostdev.run_ranks(dev, world, rank_main)
+    assert codes == [0] * world
+    res = json.loads([x for x in capsys.readouterr().out.splitlines() if x.startswith("{")][-1])
+    assert res["ok"] and res["world"] == world and res["max_rel"] < 1e-12
