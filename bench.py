@@ -376,76 +376,11 @@ def parity_of(bk, d, dist):
     return out
 
 
-class E2EPipeline:
-    """End to end through the public API with HOST buffers: every step uploads the field's interior bricks from pinned
-    host memory (H2D), runs one period (exchange + ST_ITER sweeps) and downloads the result bricks (D2H).  Steps are
-    independent fields, so len(doms) of them are kept in flight (one uploading, one computing, one downloading), as a
-    user streaming fields through the GPU would do.  Each slot has its own upload, compute and download stream, so both
-    PCIe directions are busy all the time: the step time is bounded by one direction's copy."""
-
-    def __init__(self, bk, doms, one_period_in_flight=True):
-        import ctypes as C
-        self.bk, self.L, self.ck = bk, bk.load(), bk._lib.check
-        L, ck = self.L, self.ck
-        d0 = doms[0]
-        lo, hi = 1, d0.decomp.sep_pos[1]        # inner + skin bricks = the interior; ghosts come from the exchange
-        self.off, self.nbytes = lo * 512 * 8, (hi - lo) * 512 * 8
-        self.serial, self.last_run, self.slots = one_period_in_flight, None, []
-        for d in doms:
-            hin, hout = C.c_void_p(), C.c_void_p()
-            ck(L.bk_host_alloc(C.byref(hin), self.nbytes))
-            ck(L.bk_host_alloc(C.byref(hout), self.nbytes))
-            st = [C.c_void_p() for _ in range(3)]   # upload, compute, download
-            for x in st:
-                ck(L.bk_stream_create(C.byref(x)))
-            ev = [bk.Event() for _ in range(3)]     # uploaded, computed, downloaded
-            ck(L.bk_memcpy_d2h(hin, d.storage[0].dat.ptr + self.off, self.nbytes, None))
-            self.slots.append((d, hin, hout, st, ev))
-        bk.device_sync()
-        for _, _, _, _, ev in self.slots:
-            for e in ev:
-                e.record(None)
-        bk.device_sync()
-
-    def step(self, i):
-        L, ck = self.L, self.ck
-        d, hin, hout, (s_up, s_run, s_down), (e_up, e_run, e_down) = self.slots[i % len(self.slots)]
-        ck(L.bk_stream_wait_event(s_up, e_down.h))         # this slot's previous result has left the device
-        ck(L.bk_memcpy_h2d(d.storage[0].dat.ptr + self.off, hin, self.nbytes, s_up))
-        e_up.record(s_up)
-        ck(L.bk_stream_wait_event(s_run, e_up.h))
-        # ONE period in flight per GPU: a period (2 ms next to 25 ms of copies) starts when the previous step's period has
-        # finished, so every rank runs the periods of all slots in one global order -- the ordering the single-domain loop
-        # is proven with.  Periods of different slots in flight at once would put kernels that wait for a peer's flag on
-        # several streams, and two ranks could then wait for each other (cross-slot, through shared hardware queues):
-        # tests/test_hostdev.py reproduces that deadlock on the CPU stand-in for the device.
-        if self.serial and self.last_run is not None:
-            ck(L.bk_stream_wait_event(s_run, self.last_run.h))
-        d.period(s_run)
-        e_run.record(s_run)
-        self.last_run = e_run
-        ck(L.bk_stream_wait_event(s_down, e_run.h))
-        ck(L.bk_memcpy_d2h(hout, d.storage[0].dat.ptr + self.off, self.nbytes, s_down))
-        e_down.record(s_down)
-
-    def sync(self):
-        for _, _, _, st, _ in self.slots:
-            for x in st:
-                self.ck(self.L.bk_stream_sync(x))
-
-    def close(self):
-        for _, hin, hout, st, _ in self.slots:
-            self.L.bk_host_free(hin)
-            self.L.bk_host_free(hout)
-            for x in st:
-                self.L.bk_stream_destroy(x)
-        self.slots = []
-
-
 def e2e_periods(bk, doms, steps):
-    """`steps` end-to-end steps through an E2EPipeline after one warm-up step per slot, all inside the timed region:
+    """`steps` end-to-end steps through a bricklib_b200.FieldPipeline (the public API for streaming host-resident fields
+    through the GPU) after one warm-up step per slot, all inside the timed region:
     H2D of the inputs, the period, D2H of the result.  Returns (seconds per step, h2d bytes, d2h bytes)."""
-    pipe = E2EPipeline(bk, doms)
+    pipe = bk.FieldPipeline(doms)
     for i in range(len(doms)):                  # warm-up: one step per slot
         pipe.step(i)
     bk.device_sync()

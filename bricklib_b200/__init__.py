@@ -9,7 +9,7 @@ from ._lib import (BK_OK, FUSED_COMPOSED, FUSED_COMPOSED_WIDE, FUSED_STAGED, KER
 from .core import (BRICK, Brick, BrickDecomp, BrickInfo, BrickStorage, DeviceBuffer, DeviceGrid, Event,  # noqa: F401
                    ExchangeView, ArrayExchangeView, array_stencil, bitset_of, StitchedGrid, compareBrick, copyFromBrick, copyToBrick, device_sync, init_grid, stencil,
                    stencil_advance, stencil_list, stencil_part, fill_synthetic, synthetic_field, compare_storage, section_owner, section_range, strong_pull_plan, zmort_decode, zmort_encode, Unsupported)
-from .weak import ArrayDomain, WeakDomain, shell_boxes  # noqa: F401
+from .weak import ArrayDomain, FieldPipeline, WeakDomain, shell_boxes  # noqa: F401
 
 
 def have_gpu():

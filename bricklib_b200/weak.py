@@ -361,3 +361,76 @@ def shell_boxes(lo, hi, in_lo, in_hi):
     if hi[0] > in_hi[0]:
         out.append(((in_hi[0], in_lo[1], in_lo[2]), (hi[0], in_hi[1], in_hi[2])))
     return out
+
+
+class FieldPipeline:
+    """Fields that live in HOST memory streamed through the GPU: every step uploads the field's interior bricks from pinned
+    host memory (H2D), runs one period (exchange + ST_ITER sweeps) and downloads the result bricks (D2H).  Steps are
+    independent fields, so len(doms) of them are kept in flight (one uploading, one computing, one downloading), as a
+    user streaming fields through the GPU would do.  Each slot has its own upload, compute and download stream, so both
+    PCIe directions are busy all the time: the step time is bounded by one direction's copy."""
+
+    def __init__(self, doms, one_period_in_flight=True):
+        self.L, self.ck = load(), check
+        L, ck = self.L, self.ck
+        d0 = doms[0]
+        lo, hi = 1, d0.decomp.sep_pos[1]        # inner + skin bricks = the interior; ghosts come from the exchange
+        self.off, self.nbytes = lo * 512 * 8, (hi - lo) * 512 * 8
+        self.serial, self.last_run, self.slots = one_period_in_flight, None, []
+        for d in doms:
+            hin, hout = C.c_void_p(), C.c_void_p()
+            ck(L.bk_host_alloc(C.byref(hin), self.nbytes))
+            ck(L.bk_host_alloc(C.byref(hout), self.nbytes))
+            st = [C.c_void_p() for _ in range(3)]   # upload, compute, download
+            for x in st:
+                ck(L.bk_stream_create(C.byref(x)))
+            ev = [core.Event() for _ in range(3)]     # uploaded, computed, downloaded
+            ck(L.bk_memcpy_d2h(hin, d.storage[0].dat.ptr + self.off, self.nbytes, None))
+            self.slots.append((d, hin, hout, st, ev))
+        core.device_sync()
+        for _, _, _, _, ev in self.slots:
+            for e in ev:
+                e.record(None)
+        core.device_sync()
+
+    def step(self, i):
+        L, ck = self.L, self.ck
+        d, hin, hout, (s_up, s_run, s_down), (e_up, e_run, e_down) = self.slots[i % len(self.slots)]
+        ck(L.bk_stream_wait_event(s_up, e_down.h))         # this slot's previous result has left the device
+        ck(L.bk_memcpy_h2d(d.storage[0].dat.ptr + self.off, hin, self.nbytes, s_up))
+        e_up.record(s_up)
+        ck(L.bk_stream_wait_event(s_run, e_up.h))
+        # ONE period in flight per GPU: a period (2 ms next to 25 ms of copies) starts when the previous step's period has
+        # finished, so every rank runs the periods of all slots in one global order -- the ordering the single-domain loop
+        # is proven with.  Periods of different slots in flight at once would put kernels that wait for a peer's flag on
+        # several streams, and two ranks could then wait for each other (cross-slot, through shared hardware queues):
+        # tests/test_hostdev.py reproduces that deadlock on the CPU stand-in for the device.
+        if self.serial and self.last_run is not None:
+            ck(L.bk_stream_wait_event(s_run, self.last_run.h))
+        d.period(s_run)
+        e_run.record(s_run)
+        self.last_run = e_run
+        ck(L.bk_stream_wait_event(s_down, e_run.h))
+        ck(L.bk_memcpy_d2h(hout, d.storage[0].dat.ptr + self.off, self.nbytes, s_down))
+        e_down.record(s_down)
+
+    def host_in(self, slot):
+        """slot's pinned input buffer as a float64 array: the interior bricks (ids [1, sep_pos[1])), 512 cells each"""
+        return np.ctypeslib.as_array((C.c_double * (self.nbytes // 8)).from_address(self.slots[slot][1].value))
+
+    def host_out(self, slot):
+        """slot's pinned result buffer (valid after the step that used the slot has been synchronised)"""
+        return np.ctypeslib.as_array((C.c_double * (self.nbytes // 8)).from_address(self.slots[slot][2].value))
+
+    def sync(self):
+        for _, _, _, st, _ in self.slots:
+            for x in st:
+                self.ck(self.L.bk_stream_sync(x))
+
+    def close(self):
+        for _, hin, hout, st, _ in self.slots:
+            self.L.bk_host_free(hin)
+            self.L.bk_host_free(hout)
+            for x in st:
+                self.L.bk_stream_destroy(x)
+        self.slots = []

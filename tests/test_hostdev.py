@@ -113,7 +113,7 @@ def test_composed_trial_script_reports_every_variant(monkeypatch, capsys):
 
 
 def test_bench_main_on_the_stand_in_device(monkeypatch, capsys):
-    """bench.py's product arm with its REAL WeakDomain / E2EPipeline / parity code on the stand-in (only the C++ driver
+    """bench.py's product arm with its REAL WeakDomain / FieldPipeline / parity code on the stand-in (only the C++ driver
     binaries, the child trial and the CPU reference timing are replaced): one complete line, parity green"""
     import bench
     from test_bench_dryrun import fake_run
@@ -138,7 +138,7 @@ def test_bench_main_on_the_stand_in_device(monkeypatch, capsys):
 
 
 def _two_rank_pipelines(dev, ranks, one_period_in_flight, steps, issue_seed):
-    """`ranks` emulated ranks, each an E2EPipeline of three fields in flight (bench.py's end-to-end leg), issuing their
+    """`ranks` emulated ranks, each a FieldPipeline of three fields in flight (bench.py's end-to-end leg), issuing their
     steps independently (a seeded interleaving, each rank in step order)"""
     import bench
     from bricklib_b200.weak import Handshake
@@ -161,7 +161,7 @@ def _two_rank_pipelines(dev, ranks, one_period_in_flight, steps, issue_seed):
     pipes = []
     for r in range(ranks):
         dev.process = r
-        pipes.append(bench.E2EPipeline(bk, [doms[s][r] for s in range(slots)], one_period_in_flight=one_period_in_flight))
+        pipes.append(bk.FieldPipeline([doms[s][r] for s in range(slots)], one_period_in_flight=one_period_in_flight))
     rng = np.random.default_rng(issue_seed)
     nxt = [0] * ranks
     while any(n < steps for n in nxt):
@@ -276,3 +276,47 @@ def test_multi_process_parity_script_with_rank_threads(monkeypatch, capsys, worl
     assert codes == [0] * world
     res = json.loads([x for x in capsys.readouterr().out.splitlines() if x.startswith("{")][-1])
     assert res["ok"] and res["world"] == world and res["max_rel"] < 1e-12
+
+
+def test_field_pipeline_streams_host_fields_through_the_device():
+    """the public streaming API behind bench.py's end-to-end leg: what goes in through the pinned input buffers comes out of
+    the result buffers advanced by one exchange period (checked against the oracle's periodic sweep)"""
+    rng = np.random.default_rng(21)
+    dom = (16, 24, 16)
+    with hostdev.installed(policy="random", seed=21):
+        doms = [bk.WeakDomain(dom, 1) for _ in range(3)]
+        for d in doms:
+            d.connect()
+            d.enable_overlap()
+        pipe = bk.FieldPipeline(doms)
+        fields, want = [], []
+        for step in range(5):
+            f = rng.random(dom[::-1])
+            fields.append(f)
+            want.append(S.periodic_steps(1, f, oracle.ST_ITER[1]))
+        got = []
+        for step, f in enumerate(fields):
+            slot = step % 3
+            if step >= 3:                       # the slot's previous result must have left before its buffers are reused
+                pipe.sync()
+                got.append((step - 3, pipe.host_out(slot).copy()))
+            doms[slot].load_interior(f)         # stage the field in brick order, then take it back as the slot's host input
+            bk.device_sync()
+            n = pipe.nbytes // 8
+            pipe.host_in(slot)[:] = doms[slot].storage[0].to_host()[512:512 + n]
+            doms[slot].storage[0].dat.zero()
+            bk.device_sync()                    # (the null stream does not order itself against the slot's upload stream)
+            pipe.step(step)
+        pipe.sync()
+        for step in range(2, 5):
+            got.append((step, pipe.host_out(step % 3).copy()))
+        got = dict(got)
+        for step in (2, 3, 4):
+            doms[0].storage[0].dat.zero()
+            bk.device_sync()
+            full = doms[0].storage[0].to_host()
+            full[512:512 + got[step].size] = got[step]
+            doms[0].storage[0].from_host(full)
+            res = doms[0].read_interior(0)
+            assert float((np.abs(res - want[step]) / (np.abs(res) + np.abs(want[step]))).max()) < 1e-12, step
+        pipe.close()
