@@ -140,10 +140,13 @@ def dry(monkeypatch):
     import bricklib_b200 as bk
     fake_lib = FakeLib(bk._lib.load())
     FakeDomain.made = 0
-    monkeypatch.setattr(bk, "load", lambda: fake_lib)
+    from bricklib_b200 import core, weak
+    for mod in (bk, core, weak):            # every module binds `load` by name
+        monkeypatch.setattr(mod, "load", lambda: fake_lib)
     monkeypatch.setattr(bk, "WeakDomain", FakeDomain)
-    monkeypatch.setattr(bk, "Event", FakeEvent)
-    monkeypatch.setattr(bk, "device_sync", lambda: None)
+    for mod in (bk, core):
+        monkeypatch.setattr(mod, "Event", FakeEvent)
+        monkeypatch.setattr(mod, "device_sync", lambda: None)
     monkeypatch.setattr(bk, "stencil_advance", lambda *a, **k: None)
     monkeypatch.setattr(bench.subprocess, "run", fake_run)
     monkeypatch.setattr(bench, "sampled_parity", lambda bk_, d, box_bricks=4: (4.3e-16, 131072))
