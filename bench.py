@@ -467,26 +467,34 @@ def select_fused_kernel(bk, d, dist, rank, want):
     return info
 
 
-def select_submission_order(bk, d, dist, periods):
-    """In which order are the two independent streams of a period fed: the pull first and the READY half of pass 0 behind
-    it (the order of rounds 1 and 2), or READY first?  Same kernels, same stream dependencies, same results -- but with
-    READY first its CTAs are on the SMs when the wide, high-priority pull arrives, which then trickles in as they retire
-    instead of taking the machine for itself.  Timed both ways on this run's own domain (max over ranks); the faster one
-    is used for the timed region."""
-    info = {"selected": "pull first"}
+def select_loop_options(bk, d, dist, periods):
+    """Two run-time choices of the weak loop that change no result, only the schedule, settled by measurement on this
+    run's own domain before anything is timed for the record (max over ranks, `periods` periods after 2 warm-ups each):
+      * which of the two independent streams of a period is fed first -- the pull and the READY half of pass 0 behind it
+        (the order of rounds 1 and 2), or READY first: its CTAs are then on the SMs when the wide, high-priority pull
+        arrives, which trickles in as they retire instead of taking the machine for itself;
+      * with neighbours on other GPUs: thin k segments for the ghost-dependent layers of the split pass (BK_PART_THIN) or
+        uniform ones (round 1 fixed this per radius from one N = 8 sweep).
+    Returns the record for the JSON line; leaves the fastest combination set on `d`."""
+    info = {"selected": {"first": "pull", "thin": bool(d._thin())}}
     if d.comm_stream is None:
         info["why"] = "no overlap"
         return info
+    forced_thin = d.thin
+    thins = [False, True] if (d.peers and forced_thin is None) else [bool(d._thin())]
     try:
         t = {}
-        for name, flag in (("pull first", False), ("ready first", True)):
-            d.ready_first = flag
-            t[name] = time_periods(bk, d, periods, 2, dist)[0] / periods
-        info["ms_per_step"] = {k: v * 1e3 for k, v in t.items()}
-        info["selected"] = min(t, key=t.get)
+        for first in ("pull", "ready"):
+            for thin in thins:
+                d.ready_first, d.thin = first == "ready", thin
+                t[(first, thin)] = time_periods(bk, d, periods, 2, dist)[0] / periods
+        best = min(t, key=t.get)
+        info["ms_per_step"] = {f"{f} first, {'thin' if th else 'uniform'} segments": v * 1e3 for (f, th), v in t.items()}
+        info["selected"] = {"first": best[0], "thin": best[1]}
     except Exception as exc:
         info["why"] = f"selection failed: {str(exc)[:200]}"
-    d.ready_first = info["selected"] == "ready first"
+    d.ready_first = info["selected"]["first"] == "ready"
+    d.thin = info["selected"]["thin"] if len(thins) > 1 else forced_thin
     return info
 
 
@@ -742,17 +750,19 @@ def main():
         if args.pull_shape:
             dm.set_pull_shape(*[int(x) for x in args.pull_shape.split(",")])
         dm.ready_first = ready_first
+        if headline_thin is not None:
+            dm.thin = headline_thin
         dm.fill_synthetic(0x5EED)          # synthetic U[0,1) field, written on the device
         bk.device_sync()
         return dm
 
-    ready_first = False
+    ready_first, headline_thin = False, None
     d = make_domain()
     fused_info = select_fused_kernel(bk, d, dist, rank, args.fused)
     if fused_info["selected"] != "staged":
         os.environ["BK_FUSED_VARIANT"] = fused_info["selected"]     # the C++ driver legs inherit the choice
-    order_info = select_submission_order(bk, d, dist, max(3, args.steps // 4))
-    ready_first = d.ready_first
+    loop_info = select_loop_options(bk, d, dist, max(3, args.steps // 4))
+    ready_first, headline_thin = d.ready_first, d.thin
 
     sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", "0")))
     if rank == 0:
@@ -793,7 +803,7 @@ def main():
         line["roofline"]["kernel"] = (f"march_body<diamond, {fused_info['selected']}> (two time steps as ONE composed 25-point update): "
                                       f"one launch = {pts} interior points x 2 step(s) x 16 B")
     line["fused_kernel"] = fused_info
-    line["submission_order"] = order_info
+    line["loop_options"] = loop_info
     line["config"]["ready_first"] = bool(d.ready_first)
 
     wd = Watchdog(rank, float(os.environ.get("BENCH_EXTRAS_DEADLINE_S", "420")))
@@ -812,6 +822,8 @@ def main():
             wd.at("others." + name)
             d.stencil, d.st_iter = sid, L.bk_stencil_st_iter(sid)
             d.fill_synthetic(0x5EED)
+            d.thin = {"auto": None, "on": True, "off": False}[args.thin]
+            opts = select_loop_options(bk, d, dist, k_other)
             s2, _ = time_periods(bk, d, k_other, 3, dist)
             k2, ks = time_sweeps(bk, d, 10)
             k2 = max_over_ranks(dist, k2)
@@ -823,9 +835,10 @@ def main():
                             "flops_note": f"nominal {flops} flop per point (FMA form, SURVEY 8d)" +
                             ("; the kernel EXECUTES ~50 flop per point (sign/permutation folds: 16 adds + 18 FMA), i.e. "
                              f"{50 * pts * ks / k2 / 1e12:.1f} TFLOP/s executed" if name == "mpi125pt" else ""),
-                            "parity": parity_of(bk, d, dist)}
+                            "loop_options": opts, "parity": parity_of(bk, d, dist)}
             wd.at("others." + name + " done", line)
         d.stencil, d.st_iter = st, it
+        d.ready_first, d.thin = ready_first, headline_thin
 
         # strong scaling (configs[4]), the array-layout baseline (8f#4) and the single driver (configs[0]) run through the
         # C++ drivers, one host thread per GPU, on ALL n GPUs: rank 0 runs them while the other ranks sit in a HOST

@@ -177,9 +177,9 @@ def test_product_arm_runs_every_leg_and_prints_one_complete_line(dry, monkeypatc
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["steps_per_launch"] == 2 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert d["fused_kernel"]["selected"] in ("staged", "composed", "wide") and "launch_ms" in d["fused_kernel"]
-    assert d["submission_order"]["selected"] in ("pull first", "ready first") and set(d["submission_order"]["ms_per_step"]) == {
-        "pull first", "ready first"}
-    assert d["config"]["ready_first"] == (d["submission_order"]["selected"] == "ready first")
+    assert d["loop_options"]["selected"]["first"] in ("pull", "ready") and len(d["loop_options"]["ms_per_step"]) == 2
+    assert d["config"]["ready_first"] == (d["loop_options"]["selected"]["first"] == "ready")
+    assert all("loop_options" in d["others"][k] for k in ("mpi13pt", "mpi25pt", "mpi125pt"))
     assert d["parity"]["ok"] and d["parity"]["fused_vs_two_sweeps"]["mismatches"] == 0
     o = d["others"]
     assert set(o) >= {"mpi13pt", "mpi25pt", "mpi125pt", "strong", "array_layout_baseline", "single_7pt_512"}

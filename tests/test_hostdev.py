@@ -133,7 +133,7 @@ def test_bench_main_on_the_stand_in_device(monkeypatch, capsys):
     assert all(d["others"][k]["parity"]["ok"] for k in ("mpi13pt", "mpi25pt", "mpi125pt"))
     assert d["e2e"]["h2d_bytes_per_step"] == d["e2e"]["d2h_bytes_per_step"] > 0
     assert d["fused_kernel"]["vs_two_sweeps"]["composed"]["mismatches"] == 0
-    assert d["submission_order"]["selected"] in ("pull first", "ready first")
+    assert d["loop_options"]["selected"]["first"] in ("pull", "ready")
     assert dev.launches > 100
 
 
@@ -246,7 +246,8 @@ def test_bench_main_for_several_ranks_on_the_stand_in_device(monkeypatch, capsys
     assert all(d["others"][k]["parity"]["ok"] for k in ("mpi13pt", "mpi25pt", "mpi125pt"))
     assert d["others"]["strong"]["global_1024_sub_64"]["cmd"].endswith(f"-g {world} -S mpi7pt")
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] % world == 0
-    assert d["config"]["thin_split"] is True and d["submission_order"]["selected"] in ("pull first", "ready first")
+    assert d["loop_options"]["selected"]["first"] in ("pull", "ready") and len(d["loop_options"]["ms_per_step"]) == 4
+    assert d["config"]["thin_split"] == d["loop_options"]["selected"]["thin"]
 
 
 @pytest.mark.parametrize("world,kw", [(2, {}), (4, {"policy": "random", "seed": 2}), (8, {"hw_queues": 1, "policy": "random", "seed": 4})])
