@@ -538,6 +538,10 @@ class HostDev:
             self.bk_flags_signal(signal, nsignal, epoch, stream)
         return 0
 
+    def bk_xplan_run_ce(self, h, wait, nwait, signal, nsignal, epoch, stream):
+        """the copy-engine transport: narrow wait kernel, the ranges as copies, a signal kernel -- the same order of events"""
+        return self.bk_xplan_run_sync(h, wait, nwait, signal, nsignal, epoch, stream)
+
     def bk_xplan_run_gate(self, h, wait, nwait, signal, nsignal, gate, epoch, stream):
         spin = bool(nwait) and self.wide_pull_spin
         if nwait and not spin:

@@ -250,15 +250,16 @@ def test_bench_main_for_several_ranks_on_the_stand_in_device(monkeypatch, capsys
     assert d["config"]["thin_split"] == d["loop_options"]["selected"]["thin"]
 
 
+@pytest.mark.parametrize("transport", ["kernel", "ce"])
 @pytest.mark.parametrize("world,kw", [(2, {}), (4, {"policy": "random", "seed": 2}), (8, {"hw_queues": 1, "policy": "random", "seed": 4})])
-def test_multi_process_parity_script_with_rank_threads(monkeypatch, capsys, world, kw):
+def test_multi_process_parity_script_with_rank_threads(monkeypatch, capsys, world, kw, transport):
     """tests/mgpu_weak_check.py (what tests/test_multi_gpu.py launches under torchrun on a multi-GPU box) for all its ranks at
     once on the stand-in: rendezvous, four stencils on one domain, overlap and fused passes, parity with the oracle"""
     import bench
     spec = importlib.util.spec_from_file_location("mgpu_weak_check", os.path.join(ROOT, "tests", "mgpu_weak_check.py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
-    monkeypatch.setattr(sys, "argv", ["mgpu_weak_check.py", "--size", "16", "--periods", "2"])
+    monkeypatch.setattr(sys, "argv", ["mgpu_weak_check.py", "--size", "16", "--periods", "2", "--transport", transport])
     monkeypatch.setenv("WORLD_SIZE", str(world))
     monkeypatch.delenv("BK_SKIP_ADJ_CHECK", raising=False)
 
