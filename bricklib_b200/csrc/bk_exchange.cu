@@ -135,6 +135,21 @@ __global__ void k_wait(const uint64_t *const *flags, int n, uint64_t value) {
   if ((int) threadIdx.x < n) spin_until(flags[threadIdx.x], value);
 }
 
+struct FlagList {
+  uint64_t *p[64];
+};
+__global__ void k_signal_list(const __grid_constant__ FlagList list, int n, uint64_t value) {
+  __threadfence_system();
+  if ((int) threadIdx.x < n) {
+    volatile uint64_t *f = list.p[threadIdx.x];
+    *f = value;
+  }
+  __threadfence_system();
+}
+__global__ void k_wait_list(const __grid_constant__ FlagList list, int n, uint64_t value) {
+  if ((int) threadIdx.x < n) spin_until(list.p[threadIdx.x], value);
+}
+
 int sm_count() {
   static int n = 0;
   if (!n) {
@@ -390,27 +405,24 @@ int bk_xplan_run_ce(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwait,
   return BK_OK;
 }
 
+// The flag addresses travel as a kernel argument (64 pointers by value = 512 B of the 4 KiB parameter space): no device
+// scratch, no stream-ordered allocation, no copy -- one launch per call.  (Until round 2 each call did cudaMallocAsync +
+// cudaMemcpyAsync + launch + cudaFreeAsync on the critical path of every period.)
 int bk_flags_signal(uint64_t *const *flags, int n, uint64_t value, void *stream) {
   BK_REQUIRE(flags && n > 0 && n <= 64, "1..64 flags");
-  uint64_t **dev = nullptr;
-  cudaStream_t s = (cudaStream_t) stream;
-  BK_CUDA(cudaMallocAsync(&dev, sizeof(uint64_t *) * n, s));
-  BK_CUDA(cudaMemcpyAsync(dev, flags, sizeof(uint64_t *) * n, cudaMemcpyHostToDevice, s));
-  k_signal<<<1, 64, 0, s>>>(dev, n, value);
+  FlagList list = {};
+  for (int i = 0; i < n; ++i) list.p[i] = flags[i];
+  k_signal_list<<<1, 64, 0, (cudaStream_t) stream>>>(list, n, value);
   BK_LAUNCHED();
-  BK_CUDA(cudaFreeAsync(dev, s));
   return BK_OK;
 }
 
 int bk_flags_wait(const uint64_t *const *flags, int n, uint64_t value, void *stream) {
   BK_REQUIRE(flags && n > 0 && n <= 64, "1..64 flags");
-  uint64_t **dev = nullptr;
-  cudaStream_t s = (cudaStream_t) stream;
-  BK_CUDA(cudaMallocAsync(&dev, sizeof(uint64_t *) * n, s));
-  BK_CUDA(cudaMemcpyAsync(dev, flags, sizeof(uint64_t *) * n, cudaMemcpyHostToDevice, s));
-  k_wait<<<1, 64, 0, s>>>(dev, n, value);
+  FlagList list = {};
+  for (int i = 0; i < n; ++i) list.p[i] = const_cast<uint64_t *>(flags[i]);
+  k_wait_list<<<1, 64, 0, (cudaStream_t) stream>>>(list, n, value);
   BK_LAUNCHED();
-  BK_CUDA(cudaFreeAsync(dev, s));
   return BK_OK;
 }
 
