@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 struct bk_xplan {
@@ -23,6 +24,11 @@ struct bk_xplan {
   // one plan enqueued on different streams (or back to back) never share a list that is still being read
   uint64_t **flagbuf_dev = nullptr;
   std::atomic<unsigned> flag_turn{0};
+  // the list of the last upload: wait / signal addresses are the same in every period (only the epoch changes, and that
+  // is a kernel argument), so a run re-uses the uploaded list unless the addresses or the stream changed
+  uint64_t *last_list[130] = {nullptr};
+  uint64_t **last_fb = nullptr;
+  cudaStream_t last_stream = nullptr;
   unsigned *done_dev = nullptr;  // CTAs of the running gated launch that have finished; wraps to 0 with the last one
   int shape_ctas = 0, shape_threads = 0;   // bk_xplan_set_shape: 0 = default (many 256-thread CTAs)
   // array-layout plans (bk_xplan_create_boxes): strided 3-D boxes instead of contiguous ranges; `chunk_first_dev` then
@@ -62,9 +68,9 @@ __global__ void __launch_bounds__(1024) k_xplan(const bk_seg_t *__restrict__ seg
                                                 const unsigned long long *__restrict__ first, int nseg,
                                                 unsigned long long nchunks, uint64_t *const *wait_flags, int nwait,
                                                 int nsignal, uint64_t *gate, unsigned *done,
-                                                const bk_box_t *__restrict__ boxes) {
+                                                const bk_box_t *__restrict__ boxes, uint64_t epoch) {
   if (nwait > 0) {
-    if ((int) threadIdx.x < nwait) spin_until(wait_flags[threadIdx.x], (uint64_t) (size_t) wait_flags[64]);
+    if ((int) threadIdx.x < nwait) spin_until(wait_flags[threadIdx.x], epoch);
     __syncthreads();
   }
   const unsigned groups = blockDim.x / kThreads, grp = threadIdx.x / kThreads, tid = threadIdx.x % kThreads;
@@ -105,7 +111,7 @@ __global__ void __launch_bounds__(1024) k_xplan(const bk_seg_t *__restrict__ seg
   }
   if (done) {
     // the last CTA to finish publishes completion: the local gate (read by the gated sweep's producer warps) and the
-    // peers' "done reading your skin" flags.  flag list layout: [65, 65+nsignal) = signal pointers, [64] = epoch
+    // peers' "done reading your skin" flags.  flag list layout: [0, nwait) wait pointers, [65, 65+nsignal) = signal pointers
     __shared__ bool last;
     __threadfence();
     __syncthreads();
@@ -113,7 +119,6 @@ __global__ void __launch_bounds__(1024) k_xplan(const bk_seg_t *__restrict__ seg
     if (threadIdx.x == 0) last = atomicInc(done, gridDim.x - 1) == gridDim.x - 1;
     __syncthreads();
     if (last) {
-      const uint64_t epoch = (uint64_t) (size_t) wait_flags[64];
       __threadfence_system();
       if (threadIdx.x == 0 && gate) *reinterpret_cast<volatile uint64_t *>(gate) = epoch;
       if ((int) threadIdx.x < nsignal) *reinterpret_cast<volatile uint64_t *>(wait_flags[65 + threadIdx.x]) = epoch;
@@ -163,6 +168,21 @@ int sm_count() {
 
 uint64_t **flag_slot(bk_xplan *p) { return p->flagbuf_dev + (size_t) (p->flag_turn++ % kFlagSlots) * kFlagSlotLen; }
 
+// device copy of a flag pointer list ([0,64) wait, [65,129) signal addresses): uploaded on `s` when it differs from the
+// last upload or the stream changed (the upload is ordered on ITS stream only), else the resident copy
+int flag_list(bk_xplan *p, uint64_t *const (&host)[130], cudaStream_t s, uint64_t ***out) {
+  if (p->last_fb && p->last_stream == s && memcmp(p->last_list, host, sizeof(host)) == 0) {
+    *out = p->last_fb;
+    return BK_OK;
+  }
+  uint64_t **fb = flag_slot(p);
+  BK_CUDA(cudaMemcpyAsync(fb, host, sizeof(host), cudaMemcpyHostToDevice, s));
+  memcpy(p->last_list, host, sizeof(host));
+  p->last_fb = fb, p->last_stream = s;
+  *out = fb;
+  return BK_OK;
+}
+
 // The wait for the peers' "my skin is final" flags is a ONE-CTA kernel (k_wait) launched just ahead of the pull on the same
 // stream, not a spin inside the pull itself: a wide pull whose every CTA spins holds all the CTA slots of the GPU for as
 // long as the slowest peer takes.  That (a) keeps the READY half of the split sweep off the SMs exactly when it should
@@ -189,7 +209,7 @@ int launch_copy(bk_xplan *p, uint64_t *const *wait_dev, int nwait, cudaStream_t 
   }
   const unsigned grid = (unsigned) (want < cap ? want : cap);
   k_xplan<<<grid, threads, 0, s>>>(p->segs_dev, p->chunk_first_dev, p->nbox ? p->nbox : p->nseg, p->nchunks, wait_dev, nwait,
-                                   nsignal, gate, publish ? p->done_dev : nullptr, p->boxes_dev);
+                                   nsignal, gate, publish ? p->done_dev : nullptr, p->boxes_dev, epoch);
   BK_LAUNCHED();
   return BK_OK;
 }
@@ -293,11 +313,11 @@ int bk_xplan_run_sync(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwai
   // flag pointer lists travel through a small device scratch: [0,64) wait pointers, [64] = epoch, [65,129) signals
   uint64_t *host[130] = {nullptr};
   for (int i = 0; i < nwait; ++i) host[i] = const_cast<uint64_t *>(wait_flags[i]);
-  host[64] = (uint64_t *) (size_t) epoch;
   for (int i = 0; i < nsignal; ++i) host[65 + i] = signal_flags[i];
-  uint64_t **fb = flag_slot(p);
-  BK_CUDA(cudaMemcpyAsync(fb, host, sizeof(host), cudaMemcpyHostToDevice, s));
-  int rc = launch_copy(p, fb, nwait, s, 0, nullptr, false, epoch);
+  uint64_t **fb = nullptr;
+  int rc = flag_list(p, host, s, &fb);
+  if (rc != BK_OK) return rc;
+  rc = launch_copy(p, fb, nwait, s, 0, nullptr, false, epoch);
   if (rc != BK_OK) return rc;
   if (nsignal > 0) {
     k_signal<<<1, 64, 0, s>>>(fb + 65, nsignal, epoch);
@@ -313,10 +333,10 @@ int bk_xplan_run_gate(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwai
   cudaStream_t s = (cudaStream_t) stream;
   uint64_t *host[130] = {nullptr};
   for (int i = 0; i < nwait; ++i) host[i] = const_cast<uint64_t *>(wait_flags[i]);
-  host[64] = (uint64_t *) (size_t) epoch;
   for (int i = 0; i < nsignal; ++i) host[65 + i] = signal_flags[i];
-  uint64_t **fb = flag_slot(p);
-  BK_CUDA(cudaMemcpyAsync(fb, host, sizeof(host), cudaMemcpyHostToDevice, s));
+  uint64_t **fb = nullptr;
+  const int rc = flag_list(p, host, s, &fb);
+  if (rc != BK_OK) return rc;
   return launch_copy(p, fb, nwait, s, nsignal, gate, true, epoch);
 }
 
@@ -372,14 +392,16 @@ int bk_xplan_run_ce(bk_xplan_t *p, const uint64_t *const *wait_flags, int nwait,
   }
   uint64_t *host[130] = {nullptr};
   for (int i = 0; i < nwait; ++i) host[i] = const_cast<uint64_t *>(wait_flags[i]);
-  host[64] = (uint64_t *) (size_t) epoch;
   for (int i = 0; i < nsignal; ++i) host[65 + i] = signal_flags[i];
-  uint64_t **fb = flag_slot(p);
-  if (nwait > 0 || nsignal > 0) BK_CUDA(cudaMemcpyAsync(fb, host, sizeof(host), cudaMemcpyHostToDevice, s));
+  uint64_t **fb = nullptr;
+  if (nwait > 0 || nsignal > 0) {
+    const int rc = flag_list(p, host, s, &fb);
+    if (rc != BK_OK) return rc;
+  }
   if (p->small_nchunks > 0 || nwait > 0) {
     const unsigned grid = (unsigned) std::max(1ull, std::min(p->small_nchunks, 32ull));
     k_xplan<<<grid, kThreads, 0, s>>>(p->small_segs_dev, p->small_first_dev, p->small_nseg, p->small_nchunks,
-                                      fb, nwait, 0, nullptr, nullptr, nullptr);
+                                      fb, nwait, 0, nullptr, nullptr, nullptr, epoch);
     BK_LAUNCHED();
   }
   if (!p->order.empty()) {
