@@ -5,7 +5,8 @@ its own compute and exchange stream and its own flag buffer, run whole exchange 
 flags orders rank r's pull against its neighbours' sweeps, exactly as between processes (there the pointers are CUDA-IPC
 mappings; here they are plain device pointers).  The result must equal the lock-step loop (exchange everybody, host
 sync, sweep everybody) to rounding (1e-14), and the oracle's periodic global sweep to 1e-12.  Prints `handshake ok`.
-Runs in a process of its own under a timeout (tests/test_zx_handshake_gpu.py): a protocol bug is a hang."""
+Runs in a process of its own under a timeout (tests/test_zx_handshake_gpu.py): a protocol bug is a hang.  Test
+infrastructure (it checks against the oracle), hence under tests/."""
 import argparse
 import ctypes as C
 import os

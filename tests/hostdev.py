@@ -1,7 +1,7 @@
 """hostdev -- an in-process stand-in for the DEVICE side of libbrick_b200's C ABI (test infrastructure, CPU only).
 
 The orchestration above the C ABI -- WeakDomain.period (exchange, flag handshake, split first pass, fused passes), the
-end-to-end leg's three fields in flight, tools/handshake_case.py, tools/composed_trial.py -- is Python that only ever runs
+end-to-end leg's three fields in flight, tests/handshake_case.py, tools/composed_trial.py -- is Python that only ever runs
 on a GPU box.  This module lets the SAME Python run here: `install()` swaps `load()` for a proxy whose device entry points
 (bk_dev_alloc, bk_memcpy_*, streams, events, bk_stencil_*, bk_xplan_*, bk_flags_*, layout calls) are implemented on host
 memory, while the host-side entry points (decomposition, rank maps, metadata, stitching) stay the real library's.

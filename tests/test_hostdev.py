@@ -1,5 +1,5 @@
 """The Python above the C ABI that only ever runs on a GPU box -- the weak loop with its device-side flag handshake, the
-end-to-end pipeline of bench.py, tools/handshake_case.py, tools/composed_trial.py, bench.py's main() -- executed here on
+end-to-end pipeline of bench.py, tests/handshake_case.py, tools/composed_trial.py, bench.py's main() -- executed here on
 tests/hostdev.py, a CPU stand-in for the device side of the library (streams as queues that run when the host blocks,
 events, kernels that wait for a flag, hardware queues shared by a process's streams, seeded schedules, deadlock
 DETECTION).  What this checks is orchestration: that every rank's operations are issued in an order that can complete
@@ -24,10 +24,11 @@ from oracle import schedule as S  # noqa: E402
 
 
 def load_script(name):
-    """a tools/ script as a module; what it exports to the environment at import time is undone (the tests say what they
-    want set)"""
+    """a script of tools/ or tests/ as a module; what it exports to the environment at import time is undone (the tests say
+    what they want set)"""
     saved = dict(os.environ)
-    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, "tools", name + ".py"))
+    where = "tools" if os.path.exists(os.path.join(ROOT, "tools", name + ".py")) else "tests"
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, where, name + ".py"))
     m = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(m)
     for k in set(os.environ) - set(saved):
@@ -69,7 +70,7 @@ def test_weak_loop_runs_on_the_stand_in_device(st, overlap, ready_first):
 ])
 @pytest.mark.parametrize("ready_first", ["0", "1"])
 def test_handshake_case_script_completes_under_every_schedule(monkeypatch, capsys, ranks, extra, kw, ready_first):
-    """tools/handshake_case.py as it will run on the box (tests/test_zx_handshake_gpu.py), here on the stand-in: ranks
+    """tests/handshake_case.py as it will run on the box (tests/test_zx_handshake_gpu.py), here on the stand-in: ranks
     ordered by the device-side flags alone; within a rank the submission order is a valid serial order, so even one
     hardware queue per rank cannot deadlock it"""
     hs = load_script("handshake_case")
@@ -83,7 +84,7 @@ def test_handshake_case_script_completes_under_every_schedule(monkeypatch, capsy
 
 
 def test_one_host_thread_feeding_several_ranks_must_not_block_in_the_adjacency_check(monkeypatch):
-    """why tools/handshake_case.py switches the one-time grid-vs-adjacency check off: it synchronises the stream at the first
+    """why tests/handshake_case.py switches the one-time grid-vs-adjacency check off: it synchronises the stream at the first
     launch over a new box, and a host that blocks inside rank 0's period can never enqueue the signal rank 0 waits for"""
     hs = load_script("handshake_case")
     monkeypatch.setattr(sys, "argv", ["handshake_case.py", "--ranks", "2", "--size", "16", "--periods", "2", "--stencils", "mpi7pt"])

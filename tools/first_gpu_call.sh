@@ -6,8 +6,8 @@ mkdir -p gpurun_out
 run() { local name=$1 limit=$2; shift 2; echo "== $name"; timeout "$limit" "$@" > "gpurun_out/fc_$name.log" 2>&1; echo "rc=$? ($name)"; tail -3 "gpurun_out/fc_$name.log"; }
 run smoke 120 python -c "import __graft_entry__ as g; g.smoke()"
 run trial 300 python tools/composed_trial.py
-run handshake2 200 python tools/handshake_case.py --ranks 2
-run handshake4 200 python tools/handshake_case.py --ranks 4
+run handshake2 200 python tests/handshake_case.py --ranks 2
+run handshake4 200 python tests/handshake_case.py --ranks 4
 run pytest 1200 python -m pytest tests -m gpu -x -q
 run bench1 600 python bench.py --steps 20 --warmup 5
 for v in staged composed wide; do
