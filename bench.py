@@ -637,6 +637,37 @@ def array_baseline_leg(n, wd=None):
     return out
 
 
+def direct_exchange_leg(n, wd=None):
+    """THE EXCHANGE INSIDE THE SWEEP against the pull on this run's workload and all n GPUs (tools/direct_exchange_trial.py:
+    two domains per rank on the same field, the same periods through both, results compared over the whole interior on the
+    device, both timed).  A child job of n processes: the in-place kernels were written in a round without GPU time."""
+    timeout = leg_timeout(wd, 200)
+    if not timeout:
+        return {"skipped": "no time left inside the bench's deadline for extras"}
+    script = os.path.join(ROOT, "tools", "direct_exchange_trial.py")
+    if n == 1:
+        cmd = [sys.executable, script]
+    else:
+        import socket
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+               "--master-port", str(port), script]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT",
+                                                            "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "ROLE_WORLD_SIZE",
+                                                            "TORCHELASTIC_RUN_ID", "BK_FUSED_VARIANT")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=env)
+        lines = [x for x in r.stdout.splitlines() if x.startswith("{")]
+        if r.returncode == 0 and lines:
+            return json.loads(lines[-1])
+        return {"ok": False, "rc": r.returncode, "tail": (r.stdout + r.stderr)[-500:]}
+    except Exception as exc:
+        return {"ok": False, "error": str(exc)[:300]}
+
+
 def single_leg(wd=None):
     """BASELINE.json configs[0]: the single-GPU 7-point case of single/cuda.cpp (coeff[] stencil, in/out interleaved in one
     storage, step 1024), through the C++ single driver: kernel-only sweep rate + the host array sweep it validates against"""
@@ -855,6 +886,8 @@ def main():
             others["strong"] = strong_leg(n, wd)
             wd.at("array baseline", line)
             others["array_layout_baseline"] = array_baseline_leg(n, wd)
+            wd.at("exchange inside the sweep", line)
+            others["exchange_inside_the_sweep"] = direct_exchange_leg(n, wd)
             if n == 1:
                 wd.at("single", line)
                 others["single_7pt_512"] = single_leg(wd)

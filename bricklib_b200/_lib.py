@@ -116,6 +116,8 @@ SIGNATURES = {
     "bk_adjacency_forget": (C.c_int, [vp]),
     "bk_stencil_apply_part": (C.c_int, [C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp]),
     "bk_stencil_advance": (C.c_int, [C.c_int, C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp]),
+    "bk_stencil_advance_remote": (C.c_int, [C.c_int, C.c_int, C.POINTER(Field), vp, up, up, up, dp, up, up, C.c_int, vp, C.c_uint,
+                                            C.c_uint, vp]),
     "bk_stencil_apply_list": (C.c_int, [C.c_int, C.POINTER(Field), vp, sz, dp, vp]),
     "bk_array_stencil_apply": (C.c_int, [C.c_int, vp, vp, lp, lp, lp, dp, vp]),
     "bk_stencil_apply_multi": (C.c_int, [C.c_int, vp, C.c_uint, vp, up, up, up, dp, vp]),

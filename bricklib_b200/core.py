@@ -214,15 +214,22 @@ def stencil_part(stencil_id, grid, b_in, b_out, lo, hi, ready_lo, ready_hi, part
 
 
 def stencil_advance(stencil_id, steps, grid, b_in, b_out, lo=None, hi=None, ready=None, part=_lib.PART_ALL, coeff=None,
-                    stream=None):
+                    stream=None, remote=None):
     """`steps` (1 or 2) time steps in one pass (bk_stencil_advance); ready = (ready_lo, ready_hi) for split launches.
-    Raises Unsupported when there is no fused kernel for this stencil/layout."""
+    remote = (table, ghost_lo, ghost_n): the exchange inside the sweep (bk_stencil_advance_remote) -- ghost brick
+    ghost_lo + g of the input is read from the address table[g] (DeviceBuffer of device-visible pointers) instead of
+    the own storage.  Raises Unsupported when there is no such kernel for this stencil/layout."""
     lo = (0, 0, 0) if lo is None else lo
     hi = grid.dims if hi is None else hi
     f = _field(b_in, b_out)
     rl, rh = (_u3(ready[0]), _u3(ready[1])) if ready else (None, None)
-    rc = load().bk_stencil_advance(stencil_id, steps, C.byref(f), grid.dev.ptr, _u3(grid.dims), _u3(lo), _u3(hi),
-                                   _coeff(coeff), rl, rh, part, stream)
+    if remote is not None:
+        table, g_lo, g_n = remote
+        rc = load().bk_stencil_advance_remote(stencil_id, steps, C.byref(f), grid.dev.ptr, _u3(grid.dims), _u3(lo), _u3(hi),
+                                              _coeff(coeff), rl, rh, part, table.ptr, int(g_lo), int(g_n), stream)
+    else:
+        rc = load().bk_stencil_advance(stencil_id, steps, C.byref(f), grid.dev.ptr, _u3(grid.dims), _u3(lo), _u3(hi),
+                                       _coeff(coeff), rl, rh, part, stream)
     if rc == _lib.BK_EUNSUPPORTED:
         raise Unsupported(f"no {steps}-step kernel for stencil {stencil_id}")
     check(rc)

@@ -34,6 +34,15 @@ struct TiledArgs {
   } box[6];
 };
 
+// Ghost bricks read straight out of the neighbours' storages (the exchange inside the sweep): brick id ghost_lo + g of the
+// INPUT field is not read from in + id*step but from remap[g] -- the address of the peer's skin brick that this ghost
+// brick mirrors (a CUDA-IPC / peer mapping, or the own storage for a self-neighbour).  Third argument of the *_remote
+// kernels only; the other kernels do not know it exists.
+struct RemoteArgs {
+  const double *const *remap;
+  unsigned ghost_lo, ghost_n;
+};
+
 // k range of segment `q`: [head of kh layers] [uniform segments of kl layers] [tail of kt layers]
 __host__ __device__ __forceinline__ void seg_range(const TiledArgs &a, int q, int &kb0, int &nl) {
   const int nz = a.hi[2] - a.lo[2], mid = nz - a.kh - a.kt;

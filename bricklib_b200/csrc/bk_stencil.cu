@@ -104,6 +104,10 @@ int coef_spec_for(int stencil, const double *coeff, CoefSpec *o) {
 int launch_tiled(const CoefSpec &spec, const bk_field_t &f, const bk_field_t *multi_dev, unsigned nsub, const unsigned *grid,
                  const unsigned *gdims, const unsigned *lo, const unsigned *hi, cudaStream_t s, int part = BK_PART_ALL,
                  const unsigned *ready_lo = nullptr, const unsigned *ready_hi = nullptr, int steps = 1);
+// implemented in bk_stencil_remote.cu
+int launch_tiled_remote(const CoefSpec &spec, const bk_field_t &f, const unsigned *grid, const unsigned *gdims, const unsigned *lo,
+                        const unsigned *hi, cudaStream_t s, int part, const unsigned *ready_lo, const unsigned *ready_hi, int steps,
+                        const double *const *remap, unsigned ghost_lo, unsigned ghost_n);
 
 }  // namespace bk
 
@@ -439,6 +443,33 @@ int bk_stencil_advance(int stencil, int steps, const bk_field_t *f, const unsign
   if (ok <= 0) return ok < 0 ? ok : adjacency_mismatch();
   return bk::launch_tiled(spec, *f, nullptr, 1, grid, gdims, lo, hi, (cudaStream_t) stream, part, ready_lo, ready_hi,
                           steps);
+}
+
+// bk_stencil_advance with the ghost bricks of the INPUT read in place from the neighbours' storages: brick id
+// ghost_lo + g comes from remap_dev[g] (device array of ghost_n device-visible addresses, each one brick of 512 doubles)
+// instead of f->in + id * in_step.  The exchange then happens inside the sweep: no pull, no ghost write and re-read.
+int bk_stencil_advance_remote(int stencil, int steps, const bk_field_t *f, const unsigned *grid, const unsigned *gdims,
+                              const unsigned *lo, const unsigned *hi, const double *coeff, const unsigned *ready_lo,
+                              const unsigned *ready_hi, int part, const double *const *remap_dev, unsigned ghost_lo,
+                              unsigned ghost_n, void *stream) {
+  BK_REQUIRE(stencil >= 0 && stencil < BK_ST_COUNT, "unknown stencil id");
+  BK_REQUIRE(steps == 1 || steps == 2, "steps must be 1 or 2");
+  BK_REQUIRE(f && f->adj && f->in && f->out && grid && gdims && lo && hi && remap_dev && ghost_n > 0, "null argument");
+  const bool trust_grid = (part & BK_PART_GRID_TOPOLOGY) != 0;
+  part &= ~BK_PART_GRID_TOPOLOGY;
+  BK_REQUIRE(part == BK_PART_ALL ||
+                 (ready_lo && ready_hi && ((part & ~BK_PART_THIN) == BK_PART_READY || (part & ~BK_PART_THIN) == BK_PART_REST)),
+             "bad part");
+  BK_REQUIRE(f->in_step >= 512 && f->out_step >= 512, "brick step smaller than a brick");
+  BK_REQUIRE(f->in != f->out, "in-place sweep is not defined");
+  BK_REQUIRE(check_box(gdims, lo, hi) == BK_OK, "brick box outside the grid");
+  bk::CoefSpec spec;
+  if (bk::coef_spec_for(stencil, coeff, &spec) != BK_OK) return BK_EINVAL;
+  const int ok = trust_grid ? 1 : marching_matches_adjacency(f->adj, grid, gdims, lo, hi, steps - 1, spec.kind == 1 ? kSlotsAll : kSlotsStar,
+                                                            (cudaStream_t) stream);
+  if (ok <= 0) return ok < 0 ? ok : adjacency_mismatch();
+  return bk::launch_tiled_remote(spec, *f, grid, gdims, lo, hi, (cudaStream_t) stream, part, ready_lo, ready_hi, steps, remap_dev,
+                                 ghost_lo, ghost_n);
 }
 
 int bk_stencil_apply_list(int stencil, const bk_field_t *f, const unsigned *ids, size_t n, const double *coeff,

@@ -82,8 +82,16 @@ struct Cfg {
   __host__ __device__ static constexpr int slotoff(int bi, int bj) { return (bj * SW + bi) * SLOTP; }
 };
 
+// bk_stencil_remote.cu compiles this file a second time with BK_REMOTE_TU defined: the same marching body with ONE more
+// line in the producer (ghost bricks are read in place from the neighbours' storages, RemoteArgs) and its own entry
+// point.  Keeping that variant in a translation unit of its own leaves the code of the kernels below untouched.
+#ifdef BK_REMOTE_TU
+#define BK_REM_PARAM , const RemoteArgs &rem
+#else
+#define BK_REM_PARAM
+#endif
 template <class C>
-__device__ __forceinline__ void march_body(const TiledArgs &a, const typename C::Coef &cf) {
+__device__ __forceinline__ void march_body(const TiledArgs &a, const typename C::Coef &cf BK_REM_PARAM) {
   constexpr int R = C::R, YT = C::YT, TI = C::TI, TJ = C::TJ, G = C::G, D = C::D, W = C::W, RUP = C::RUP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // dynamic shared memory is only guaranteed 16-B aligned: align the ring to 128 B by hand
@@ -180,6 +188,12 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
 #pragma unroll
       for (int q = 0; q < C::JOBS; ++q) {
         const double *src = fin + (size_t) idc[q] * in_step + pz * 64;
+#ifdef BK_REMOTE_TU
+        {  // a ghost brick: the neighbour's skin brick it mirrors, where it lies (over NVLink for a peer's)
+          const unsigned g = idc[q] - rem.ghost_lo;
+          if (g < rem.ghost_n) src = rem.remap[g] + pz * 64;
+        }
+#endif
         if (kind[q] == 1) {
           bulk_g2s(sb + dsto[q], src, G * 512, fb);
         } else if (kind[q] >= 2) {
@@ -473,6 +487,7 @@ __device__ __forceinline__ void march_body(const TiledArgs &a, const typename C:
   }
 }
 
+#ifndef BK_REMOTE_TU
 template <class C>
 __global__ void __launch_bounds__(C::NT) k_star(const __grid_constant__ TiledArgs a,
                                                 const __grid_constant__ typename C::Coef cf) {
@@ -484,7 +499,26 @@ __global__ void __launch_bounds__(C::NT) __maxnreg__(C::MAXREG) k_star_capped(co
                                                                                const __grid_constant__ typename C::Coef cf) {
   march_body<C>(a, cf);
 }
+#else
+// the same three flavours (plain, register cap, register re-balancing) with the RemoteArgs table as a third argument
+template <class C>
+__global__ void __launch_bounds__(C::NT) k_star_remote(const __grid_constant__ TiledArgs a, const __grid_constant__ typename C::Coef cf,
+                                                       const __grid_constant__ RemoteArgs r) {
+  march_body<C>(a, cf, r);
+}
+template <class C>
+__global__ void __launch_bounds__(C::NT) __maxnreg__(C::MAXREG)
+    k_star_capped_remote(const __grid_constant__ TiledArgs a, const __grid_constant__ typename C::Coef cf, const __grid_constant__ RemoteArgs r) {
+  march_body<C>(a, cf, r);
+}
+template <class C>
+__global__ void __launch_bounds__(C::NT, 1)
+    k_star_rebal_remote(const __grid_constant__ TiledArgs a, const __grid_constant__ typename C::Coef cf, const __grid_constant__ RemoteArgs r) {
+  march_body<C>(a, cf, r);
+}
+#endif
 
+#ifndef BK_REMOTE_TU
 // ==================================================================================================================
 // Two time steps per pass (temporal blocking) for the star stencils.
 //
@@ -918,6 +952,8 @@ __global__ void __launch_bounds__(C::NT, 1) k_star_rebal(const __grid_constant__
   march_body<C>(a, cf);
 }
 
+#endif  // !BK_REMOTE_TU
+
 // Brick layers per k segment.  Every CTA streams 8*layers + ovh planes (ovh = halo planes + pipeline fill) and CTAs are
 // dealt to the `slots` resident CTA slots in blockIdx order (all tiles of segment 0, then segment 1, ...; the last
 // segment may be shorter).  Long segments amortise ovh, short ones fill the last wave: the launch is list-scheduled
@@ -1048,6 +1084,7 @@ int device_slots(const void *kern, int threads, size_t smem) {
   return sms * (per_sm > 0 ? per_sm : 1);
 }
 
+#ifndef BK_REMOTE_TU
 template <class C>
 int launch_cfg(const TiledArgs &a0, const typename C::Coef &cf, cudaStream_t s, unsigned nsub, int part,
                const int *rdy_lo, const int *rdy_hi) {
@@ -1104,6 +1141,10 @@ int bk_stencil_fused_variant_set(int variant) {
   return before;
 }
 int bk_stencil_fused_variant_get(void) { return fused_variant(); }
+}
+
+namespace bk {
+int fused_variant_now() { return fused_variant(); }  // for bk_stencil_remote.cu
 }
 
 namespace bk {
@@ -1222,3 +1263,78 @@ int launch_generated(const void *kernel, const GenGeom &gg, const void *coef, co
 size_t tiled_args_bytes() { return sizeof(TiledArgs); }
 
 }  // namespace bk
+#else  // BK_REMOTE_TU ================================================================================================
+
+template <class C>
+int launch_cfg_remote(const TiledArgs &a0, const typename C::Coef &cf, const RemoteArgs &rem, cudaStream_t s, int part,
+                      const int *rdy_lo, const int *rdy_hi) {
+  void (*kern)(const TiledArgs, const typename C::Coef, const RemoteArgs);
+  if constexpr (C::CREG > 0) kern = k_star_rebal_remote<C>;
+  else if constexpr (C::MAXREG < 255) kern = k_star_capped_remote<C>;
+  else kern = k_star_remote<C>;
+  BK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) C::SMEM));
+  static std::atomic<int> slots_cached{0};
+  int slots = slots_cached.load(std::memory_order_relaxed);
+  if (!slots) {
+    slots = device_slots((const void *) kern, C::NT, C::SMEM);
+    slots_cached.store(slots, std::memory_order_relaxed);
+  }
+  const Geom g = {C::TI, C::TJ, C::OVH};
+  return launch_geom(g, slots, a0, 1, part, rdy_lo, rdy_hi, [&](dim3 grid, const TiledArgs &a) -> int {
+    kern<<<grid, C::NT, C::SMEM, s>>>(a, cf, rem);
+    BK_LAUNCHED();
+    return BK_OK;
+  });
+}
+
+}  // namespace
+
+namespace bk {
+
+int fused_variant_now();  // bk_stencil_tiled.cu
+
+// The default geometry of every stencil (and of the composed two-step update) with the ghost bricks of the input read in
+// place through `remap` (bk_stencil_advance_remote).  The staged two-step kernel and the developer geometries have no such
+// variant: BK_EUNSUPPORTED.
+int launch_tiled_remote(const CoefSpec &spec, const bk_field_t &f, const unsigned *grid, const unsigned *gdims, const unsigned *lo,
+                        const unsigned *hi, cudaStream_t s, int part, const unsigned *ready_lo, const unsigned *ready_hi, int steps,
+                        const double *const *remap, unsigned ghost_lo, unsigned ghost_n) {
+  if (((size_t) f.in | (size_t) f.out) & 15 || (f.in_step & 1) || (f.out_step & 1)) return BK_EUNSUPPORTED;
+  TiledArgs a;
+  a.in = f.in, a.out = f.out, a.in_step = f.in_step, a.out_step = f.out_step, a.grid = grid;
+  a.gx = (int) gdims[0], a.gy = (int) gdims[1], a.gz = (int) gdims[2];
+  for (int d = 0; d < 3; ++d) a.lo[d] = (int) lo[d], a.hi[d] = (int) hi[d];
+  a.ntx = a.kl = a.kh = a.kt = 0;
+  a.multi = nullptr;
+  a.nbox = 0;
+  int rdy_lo[3] = {0, 0, 0}, rdy_hi[3] = {0, 0, 0};
+  if (part != BK_PART_ALL)
+    for (int d = 0; d < 3; ++d) rdy_lo[d] = (int) ready_lo[d], rdy_hi[d] = (int) ready_hi[d];
+  const RemoteArgs rem = {remap, ghost_lo, ghost_n};
+  if (getenv("BK_STAR_VARIANT") && atoi(getenv("BK_STAR_VARIANT")) != 0) return BK_EUNSUPPORTED;
+  if (spec.kind == 1) {
+    if (steps != 1) return BK_EUNSUPPORTED;
+    return launch_cfg_remote<Cfg<2, 2, 6, 4, 2, 3, 255, 4, true, 152, 40>>(a, spec.cc, rem, s, part, rdy_lo, rdy_hi);
+  }
+  const StarCoef &sc = spec.sc;
+  const int r = spec.radius;
+  if (steps == 2) {
+    if (r != 1 || fused_variant_now() == BK_FUSED_STAGED) {
+      set_error("ghost bricks read in place: the staged two-step kernel has no such variant (BK_FUSED_VARIANT=composed|wide has)");
+      return BK_EUNSUPPORTED;
+    }
+    const bk::DiamondCoef dc = bk::diamond_coef(sc.c0, sc.cp[0][0], sc.cm[0][0], sc.cp[1][0], sc.cm[1][0], sc.cp[2][0], sc.cm[2][0]);
+    if (fused_variant_now() == BK_FUSED_COMPOSED_WIDE)
+      return launch_cfg_remote<Cfg<2, 4, 8, 4, 2, 3, 255, 4, false, 232, 40, 2>>(a, dc, rem, s, part, rdy_lo, rdy_hi);
+    return launch_cfg_remote<Cfg<2, 4, 4, 4, 2, 3, 168, 2, false, 0, 40, 2>>(a, dc, rem, s, part, rdy_lo, rdy_hi);
+  }
+  if (r == 1) return launch_cfg_remote<Cfg<1, 4, 4, 4, 2, 3, 255, 2>>(a, sc, rem, s, part, rdy_lo, rdy_hi);
+  if (r == 2) return launch_cfg_remote<Cfg<2, 4, 4, 4, 2, 3, 128, 2>>(a, sc, rem, s, part, rdy_lo, rdy_hi);
+  const long nx = a.hi[0] - a.lo[0], ny = a.hi[1] - a.lo[1];
+  const long pad64 = ((nx + 5) / 6) * 6 * ((ny + 3) / 4) * 4, pad84 = ((nx + 7) / 8) * 8 * ((ny + 3) / 4) * 4;
+  if (pad84 <= pad64) return launch_cfg_remote<Cfg<4, 4, 8, 4, 2, 4, 255, 4, false, 232, 40>>(a, sc, rem, s, part, rdy_lo, rdy_hi);
+  return launch_cfg_remote<Cfg<4, 2, 6, 4, 2, 3, 255, 4, false, 152, 40>>(a, sc, rem, s, part, rdy_lo, rdy_hi);
+}
+
+}  // namespace bk
+#endif  // BK_REMOTE_TU

@@ -78,6 +78,10 @@ class WeakDomain:
         self.thin = None
         self.trace = None    # developer aid: a list collects (label, Event) marks of one period (tools/period_trace.py)
         self.fuse = 2        # time steps per pass where a fused kernel exists (7/13-point); 1 = one sweep per pass
+        # "pull": ghost bricks are filled by the pull kernel, then swept; "direct": THE EXCHANGE INSIDE THE SWEEP -- the
+        # launches of pass 0 that touch ghosts read them in place from the neighbours' storages (no pull, no ghost copy)
+        self.exchange_mode = os.environ.get("BK_EXCHANGE_MODE", "pull")
+        self.remap = None    # direct mode: DeviceBuffer of one address per ghost brick (built by connect())
         # submit the READY half of pass 0 ahead of the pull (see period()); BK_READY_FIRST=1 makes it the default
         self.ready_first = os.environ.get("BK_READY_FIRST", "0") not in ("", "0")
 
@@ -88,6 +92,15 @@ class WeakDomain:
         ptrs[self.rank] = self.storage[0].dat.ptr
         self.view = core.ExchangeView(self.decomp, self.storage[0], ptrs, self.rank)
         self.hs = handshake
+        # the same plan as one address per ghost BRICK: where the skin brick it mirrors lies (a peer's storage or my own)
+        lo, hi = self.decomp.sep_pos[1], self.decomp.sep_pos[2]
+        table = np.zeros(hi - lo, dtype=np.uint64)
+        brick = self.storage[0].step * 8
+        for peer, src_off, dst_off, nbytes in core.ExchangeView.plan(self.decomp, self.storage[0].step):
+            first, n = dst_off // brick - lo, nbytes // brick
+            table[first:first + n] = ptrs[peer] + src_off + np.arange(n, dtype=np.uint64) * np.uint64(brick)
+        assert np.all(table != 0), "every ghost brick mirrors a skin brick"
+        self.remap = (core.DeviceBuffer.from_numpy(table), lo, hi - lo)
 
     def set_pull_shape(self, ctas=0, threads=0):
         self.view.set_shape(ctas, threads)
@@ -230,6 +243,8 @@ class WeakDomain:
         # order in which the two independent streams are fed changes): its CTAs are on the SMs when the pull's arrive, and
         # the high-priority pull trickles in as they retire instead of taking the machine first.  Which order is faster
         # is a measurement (bench.py times both); correctness does not depend on it.
+        if self.direct_active(fuse):
+            return self._period_direct(stream, n0, fuse, full, own, cs)
         early = False
         if self.ready_first and overlap and fuse < self.st_iter:
             try:
@@ -282,6 +297,70 @@ class WeakDomain:
         assert p % 2 == 0 or self.st_iter % 2 == 1, "result must end in storage[0]"
         return load().bk_launch_count() - n0
 
+    def direct_active(self, fuse=None):
+        """does period() run with the exchange inside the sweep?  Asked for (exchange_mode == "direct"), wired (connect()),
+        and a kernel for it exists: every marching kernel but the STAGED two-step one (7-point needs
+        BK_FUSED_VARIANT=composed|wide, or one sweep per pass); else period() uses the pull"""
+        if self.exchange_mode != "direct" or self.remap is None or self.kernel == _lib.KERNEL_BRICK:
+            return False
+        fuse = self.steps_per_pass() if fuse is None else fuse
+        return not (fuse == 2 and load().bk_stencil_fused_variant_get() == _lib.FUSED_STAGED)
+
+    def _period_direct(self, stream, n0, fuse, full, own, cs):
+        """the rest of a period with THE EXCHANGE INSIDE THE SWEEP (after the announcement): pass 0 reads the ghost bricks
+        in place from the neighbours' storages (bk_stencil_advance_remote), so there is no pull, no ghost write and no
+        re-read.  With an exchange stream: READY half on the compute stream at once, the REST half (the only launches that
+        touch ghosts) on the exchange stream behind a wait for the neighbours' announcements; then I tell them I am done
+        reading their skins.  Pass 1 waits for their same message as in pull mode."""
+        have_peers = self.hs is not None and bool(self.peers)
+        xs = cs if cs is not None else stream
+        waits = [self.hs.ready_flag_on(self.rank, p) for p in self.peers] if have_peers else []
+        dones = [self.hs.done_flag_on(p, self.rank) for p in self.peers] if have_peers else []
+
+        def wait_for_neighbours(s):
+            if have_peers:
+                w = (C.c_void_p * len(waits))(*waits)
+                check(load().bk_flags_wait(w, len(waits), self.epoch, s))
+
+        def done_reading(s):
+            if have_peers:
+                d = (C.c_void_p * len(dones))(*dones)
+                check(load().bk_flags_signal(d, len(dones), self.epoch, s))
+
+        last0 = fuse >= self.st_iter
+        lo, hi = own if last0 else full
+        thin = _lib.PART_THIN if self._thin() else 0
+        if cs is not None and not last0:
+            self._advance(fuse, 0, 1, lo, hi, own, _lib.PART_READY | thin, stream)          # reads no ghost: plain kernel
+            self._mark("pass 0 READY done", stream)
+            wait_for_neighbours(cs)
+            self._advance(fuse, 0, 1, lo, hi, own, _lib.PART_REST | thin, cs, remote=self.remap)
+            done_reading(cs)
+            self._mark("pass 0 REST done", cs)
+            self.ev_comm.record(cs)
+            check(load().bk_stream_wait_event(stream, self.ev_comm.h))
+        else:
+            wait_for_neighbours(xs)
+            core.stencil_advance(self.stencil, fuse, self.grid, self.bricks[0], self.bricks[1], lo, hi, None, _lib.PART_ALL, None,
+                                 xs, remote=self.remap)
+            done_reading(xs)
+            if cs is not None:
+                self.ev_comm.record(cs)
+                check(load().bk_stream_wait_event(stream, self.ev_comm.h))
+            self._mark("pass 0 done", xs)
+        done, p = fuse, 1
+        while done < self.st_iter:
+            src, dst = p % 2, 1 - p % 2
+            last = done + fuse >= self.st_iter
+            lo, hi = own if last else full
+            if p == 1:
+                self._wait_peers_done(stream)  # pass 1 rewrites storage[0], whose skin the peers were reading
+            self._advance(fuse, src, dst, lo, hi, None, _lib.PART_ALL, stream)
+            self._mark(f"pass {p} done", stream)
+            done, p = done + fuse, p + 1
+        assert p % 2 == 0 or self.st_iter % 2 == 1, "result must end in storage[0]"
+        return load().bk_launch_count() - n0
+
     def steps_per_pass(self):
         """time steps one launch advances: 2 where the fused kernel pays off (7-point), else 1"""
         fuse = min(max(1, self.fuse), load().bk_stencil_fused_steps(self.stencil))
@@ -289,12 +368,12 @@ class WeakDomain:
             fuse = 1
         return fuse
 
-    def _advance(self, steps, src, dst, lo, hi, ready, part, stream):
-        if steps == 1 and part == _lib.PART_ALL:
+    def _advance(self, steps, src, dst, lo, hi, ready, part, stream, remote=None):
+        if steps == 1 and part == _lib.PART_ALL and remote is None:
             self._sweep(src, dst, lo, hi, stream)
         else:
             core.stencil_advance(self.stencil, steps, self.grid, self.bricks[src], self.bricks[dst], lo, hi, ready, part,
-                                 None, stream)
+                                 None, stream, remote=remote)
 
 
 class ArrayDomain:

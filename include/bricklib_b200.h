@@ -233,6 +233,15 @@ int bk_adjacency_forget(const void *adj_or_grid_dev);
 int bk_stencil_advance(int stencil, int steps, const bk_field_t *f, const unsigned *grid_dev, const unsigned *gdims,
                        const unsigned *lo, const unsigned *hi, const double *coeff_host, const unsigned *ready_lo,
                        const unsigned *ready_hi, int part, void *stream);
+/* bk_stencil_advance with THE EXCHANGE INSIDE THE SWEEP: ghost brick id ghost_lo + g of the input field is read from
+ * remap_dev[g] -- the address (peer access / CUDA IPC / own storage) of the neighbour's skin brick it mirrors, what
+ * BrickDecomp::exchange (include/brick-mpi.h:466-495) would have copied into it -- instead of f->in + id * in_step.  Only
+ * the launches that read freshly exchanged ghosts need it (the REST half of a period's first pass).  BK_EUNSUPPORTED for
+ * the staged two-step kernel and the developer geometries. */
+int bk_stencil_advance_remote(int stencil, int steps, const bk_field_t *f, const unsigned *grid, const unsigned *gdims,
+                              const unsigned *lo, const unsigned *hi, const double *coeff, const unsigned *ready_lo,
+                              const unsigned *ready_hi, int part, const double *const *remap_dev, unsigned ghost_lo,
+                              unsigned ghost_n, void *stream);
 /* same over an explicit list of brick ids (inner / skin / ghost lists for overlap; any adjacency-defined set) */
 int bk_stencil_apply_list(int stencil, const bk_field_t *f, const unsigned *ids_dev, size_t n,
                           const double *coeff_host, void *stream);

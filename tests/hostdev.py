@@ -480,6 +480,23 @@ class HostDev:
                 boxes, name = ([(lo, hi)] if empty else weak.shell_boxes(tuple(lo), tuple(hi), tuple(in_lo), tuple(in_hi))), "REST"
         return self._advance(stencil, steps, f, grid, gdims, boxes, coeff, stream, f"advance st{stencil} x{steps} {name}")
 
+    def bk_stencil_advance_remote(self, stencil, steps, f, grid, gdims, lo, hi, coeff, ready_lo, ready_hi, part, remap, ghost_lo,
+                                  ghost_n, stream):
+        """the exchange inside the sweep: when the launch EXECUTES, every ghost brick of the input is read through the
+        address table (here: copied through it into the ghost brick first, which no other launch reads in this mode)"""
+        if steps == 2 and self.real.bk_stencil_fused_variant_get() == _lib.FUSED_STAGED:
+            return BK_EUNSUPPORTED
+        fld = f._obj
+        src, s_in, table, g0, gn = _ival(fld.inp), int(fld.in_step), _ival(remap), int(ghost_lo), int(ghost_n)
+
+        def through_the_table():
+            addr = np.frombuffer(self._span(table, 8 * gn)[:8 * gn], dtype=np.uint64)
+            for g in range(gn):
+                self._span(int(addr[g]), 4096)          # must be a live brick of this (stand-in) node
+                C.memmove(src + (g0 + g) * s_in * 8, int(addr[g]), 4096)
+        self._enqueue(stream, "ghost bricks through the address table", through_the_table)
+        return self.bk_stencil_advance(stencil, steps, f, grid, gdims, lo, hi, coeff, ready_lo, ready_hi, part, stream)
+
     def bk_stencil_apply_part(self, stencil, f, grid, gdims, lo, hi, coeff, ready_lo, ready_hi, part, stream):
         return self.bk_stencil_advance(stencil, 1, f, grid, gdims, lo, hi, coeff, ready_lo, ready_hi, part, stream)
 

@@ -121,8 +121,12 @@ class R:
 
 def fake_run(cmd, **kw):
     exe = os.path.basename(cmd[0]) if not cmd[0].endswith("python") and "python" not in os.path.basename(cmd[0]) else os.path.basename(cmd[1])
+    if exe == "-m":
+        exe = cmd[2]
     if exe == "composed_trial.py":
         return R(json.dumps({"ok": True, "composed": {"ok": True, "launch_ms": 0.39}, "wide": {"ok": True, "launch_ms": 0.4}}) + "\n")
+    if exe == "direct_exchange_trial.py" or (exe == "torch.distributed.run" or "direct_exchange_trial.py" in " ".join(cmd)):
+        return R(json.dumps({"ok": True, "n_gpus": 1, "mpi25pt": {"pull_ms": 0.95, "direct_ms": 0.85, "mismatches": 0, "ok": True}}) + "\n")
     if exe == "strong":
         tail = "result match (worst relative difference 4e-16 after 24 steps)\n" if "-v" in cmd else ""
         return R("calc : [0.001, 0.001, 0.001] (s: 0)\ncall : [1e-05, 1e-05, 1e-05] (s: 0)\nwait : [1e-06, 1e-06, 1e-06] (s: 0)\nperf 1086.7 GStencil/s\n" + tail)
@@ -187,6 +191,7 @@ def test_product_arm_runs_every_leg_and_prints_one_complete_line(dry, monkeypatc
     assert o["strong"]["global_1024_sub_64"]["GStencil/s"] == 1086.7 and "share_512_stitched" in o["strong"]
     assert o["array_layout_baseline"]["mpi25pt"]["arr_equals_bri"] is True
     assert o["single_7pt_512"]["GStencil/s"] == 375.5 and o["single_7pt_512"]["validation"] == "result match"
+    assert o["exchange_inside_the_sweep"]["ok"] and o["exchange_inside_the_sweep"]["mpi25pt"]["mismatches"] == 0
     assert d["e2e"]["h2d_bytes_per_step"] == d["e2e"]["d2h_bytes_per_step"] == (262145 - 1) * 4096 and d["e2e"]["value"] > 0
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 16
     assert d["baseline_configs"]["configs[4] strong 1024^3 in 64^3 subdomains"] == 1086.7

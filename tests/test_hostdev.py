@@ -38,14 +38,18 @@ def load_script(name):
 
 
 @pytest.mark.parametrize("st", [1, 2, 3, 4])
+@pytest.mark.parametrize("mode", ["pull", "direct"])
 @pytest.mark.parametrize("overlap,ready_first", [(False, False), (True, False), (True, True)])
-def test_weak_loop_runs_on_the_stand_in_device(st, overlap, ready_first):
+def test_weak_loop_runs_on_the_stand_in_device(st, overlap, ready_first, mode):
     rng = np.random.default_rng(st)
     dom = (32, 24, 16)
     field = rng.random(dom[::-1])
+    before = bk.fused_variant(bk.FUSED_COMPOSED if mode == "direct" else bk.FUSED_STAGED)
     with hostdev.installed(policy="random", seed=st) as dev:
         d = bk.WeakDomain(dom, st)
         d.connect()
+        d.exchange_mode = mode
+        assert d.direct_active() == (mode == "direct")
         d.ready_first = ready_first
         if overlap:
             d.enable_overlap()
@@ -54,9 +58,11 @@ def test_weak_loop_runs_on_the_stand_in_device(st, overlap, ready_first):
         bk.device_sync()
         got = d.read_interior(0)
         assert launches > 0 and dev.launches >= launches
-        if overlap:     # the READY half of pass 0 is submitted before / after the pull
+        if overlap:     # the READY half of pass 0 is submitted before / after the pull -- or there is no pull at all
             order = [x for x in dev.executed if x.startswith("pull") or x.endswith("READY")]
-            assert len(order) == 4
+            assert len(order) == (4 if mode == "pull" else 2)
+        assert ("ghost bricks through the address table" in dev.executed) == (mode == "direct")
+    bk.fused_variant(before)
     want = S.periodic_steps(st, field, 2 * oracle.ST_ITER[st])
     assert float((np.abs(got - want) / (np.abs(got) + np.abs(want))).max()) < 1e-12
 
@@ -68,18 +74,22 @@ def test_weak_loop_runs_on_the_stand_in_device(st, overlap, ready_first):
     (8, [], {"hw_queues": 1, "policy": "random", "seed": 5}),
     (8, ["--no-overlap"], {"hw_queues": 2, "policy": "random", "seed": 9}),
 ])
-@pytest.mark.parametrize("ready_first", ["0", "1"])
-def test_handshake_case_script_completes_under_every_schedule(monkeypatch, capsys, ranks, extra, kw, ready_first):
+@pytest.mark.parametrize("ready_first,mode", [("0", "pull"), ("1", "pull"), ("0", "direct")])
+def test_handshake_case_script_completes_under_every_schedule(monkeypatch, capsys, ranks, extra, kw, ready_first, mode):
     """tests/handshake_case.py as it will run on the box (tests/test_zx_handshake_gpu.py), here on the stand-in: ranks
     ordered by the device-side flags alone; within a rank the submission order is a valid serial order, so even one
     hardware queue per rank cannot deadlock it"""
     hs = load_script("handshake_case")
     monkeypatch.setenv("BK_SKIP_ADJ_CHECK", "1")        # what the script sets for itself when it is run
     monkeypatch.setenv("BK_READY_FIRST", ready_first)
+    monkeypatch.setenv("BK_EXCHANGE_MODE", mode)            # "direct": the exchange inside the sweep (no pull at all)
+    before = bk.fused_variant(bk.FUSED_COMPOSED if mode == "direct" else bk.FUSED_STAGED)
     monkeypatch.setattr(sys, "argv", ["handshake_case.py", "--ranks", str(ranks), "--size", "16", "--periods", "3", "--stencils",
                                       "mpi7pt,mpi25pt", *extra])
-    with hostdev.installed(**kw):
+    with hostdev.installed(**kw) as dev:
         hs.main()
+    bk.fused_variant(before)
+    assert ("ghost bricks through the address table" in dev.executed) == (mode == "direct")
     assert f"handshake ok: {ranks} ranks" in capsys.readouterr().out
 
 
@@ -323,3 +333,31 @@ def test_field_pipeline_streams_host_fields_through_the_device():
             res = doms[0].read_interior(0)
             assert float((np.abs(res - want[step]) / (np.abs(res) + np.abs(want[step]))).max()) < 1e-12, step
         pipe.close()
+
+
+@pytest.mark.parametrize("world,kw", [(1, {}), (2, {"policy": "random", "seed": 1}), (4, {"hw_queues": 1, "policy": "random", "seed": 6})])
+def test_direct_exchange_trial_script_on_the_stand_in_device(monkeypatch, capsys, world, kw):
+    """tools/direct_exchange_trial.py (the child job behind bench.py's `exchange_inside_the_sweep` leg) for all its ranks:
+    a pull domain and a direct domain per rank on the same field, the same periods through both, the same numbers out"""
+    import bench
+    m = load_script("direct_exchange_trial")
+    monkeypatch.setattr(sys, "argv", ["direct_exchange_trial.py", "--size", "16", "--periods", "2"])
+    monkeypatch.setenv("WORLD_SIZE", str(world))
+    monkeypatch.delenv("BK_SKIP_ADJ_CHECK", raising=False)
+    before = bk.fused_variant()
+    with hostdev.installed(**kw) as dev:
+        if world == 1:
+            m.main()
+        else:
+            dist = hostdev.RankDist(dev, world)
+            monkeypatch.setattr(bench, "dist_setup", lambda n: (dev.process, world, dist.for_rank(dev.process), "gloo"))
+            monkeypatch.setattr(bench, "max_over_ranks", lambda d, v: v if d is None else d.allreduce(v, "max"))
+            monkeypatch.setattr(bench, "sum_over_ranks", lambda d, v: v if d is None else d.allreduce(v, "sum"))
+            monkeypatch.setattr(bench, "barrier", lambda d: d.barrier() if d is not None else None)
+            hostdev.run_ranks(dev, world, lambda r: m.main())
+        assert "ghost bricks through the address table" in dev.executed and any(x.startswith("pull") for x in dev.executed)
+    bk.fused_variant(before)
+    out = json.loads([x for x in capsys.readouterr().out.splitlines() if x.startswith("{")][-1])
+    assert out["ok"] and out["n_gpus"] == world
+    for name in ("mpi7pt", "mpi13pt", "mpi25pt", "mpi125pt"):
+        assert out[name]["ok"] and out[name]["mismatches"] == 0 and out[name]["pull_ms"] > 0 and out[name]["direct_ms"] > 0

@@ -8,6 +8,7 @@ run smoke 120 python -c "import __graft_entry__ as g; g.smoke()"
 run trial 300 python tools/composed_trial.py
 run handshake2 200 python tests/handshake_case.py --ranks 2
 run handshake4 200 python tests/handshake_case.py --ranks 4
+run direct 400 python tools/direct_exchange_trial.py
 run pytest 1200 python -m pytest tests -m gpu -x -q
 run bench1 600 python bench.py --steps 20 --warmup 5
 for v in staged composed wide; do
